@@ -1,0 +1,20 @@
+/*
+ * ORACLE (test infrastructure, NOT product code) -- see nsf_oracle_impl.h.
+ * Builds the float ("_f32") and double ("_f64") restatements of the NF-iSAM
+ * autoregressive spline flow into liboracle_nsf.so (oracle/Makefile).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#define REAL float
+#define SUFFIX _f32
+#include "nsf_oracle_impl.h"
+#undef REAL
+#undef SUFFIX
+
+#define REAL double
+#define SUFFIX _f64
+#include "nsf_oracle_impl.h"
+#undef REAL
+#undef SUFFIX
