@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the NF-iSAM clique-flow hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port on the host cores)
+
+Metric (BASELINE.json): "RQS flow log-prob samples/sec" on the synthetic microbench
+(configs[2]: dim 12, K 9, hidden 8, 1e7 samples per GPU); the companion "clique-flow train+sample
+s/incr-step" is reported in the same JSON line under "incr_step".
+
+A step = one log-prob pass over one batch of n samples.  `value` is measured with the batch
+resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` goes through the
+C ABI's host-buffer call with pinned host memory, H2D/D2H inside the timed region.
+The batch (n*d*4 B = 480 MB) is larger than the 126 MB L2, so no explicit L2 flush is needed.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D, K_BINS, HID, TAIL = 12, 9, 8, 5.0
+N_PER_GPU = 10_000_000
+
+
+def flops_fwd(d, H, K):
+    """algorithmic FLOPs of one forward / log-prob / inverse per sample."""
+    macs = H * d * (d - 1) // 2 + (d - 1) * (H * H + H * (3 * K - 1))
+    return 2 * macs + (d - 1) * (2 * H + 3 * K - 1) + d * (15 * K + 45)
+
+
+def sfu_fwd(d, H, K):
+    return 2 * H * (d - 1) + d * (4 * K + 4)
+
+
+def make_inputs(n, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    mask = rng.random((n, d), dtype=np.float32) < 0.005   # 0.5 % of entries in the |x| > B tails
+    x[mask] *= 8.0
+    return x
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def trained_like_theta(d, K, H, seed=0):
+    """PyTorch default init of the reference flow (torch.manual_seed(seed)), state_dict order."""
+    import torch
+
+    from nfisam_b200.flows import NSF_AR
+
+    torch.manual_seed(seed)
+    flow = NSF_AR(dim=d, K=K, B=TAIL, hidden_dim=H)
+    return flow.flat_parameters()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is Python/torch, nothing to compile into oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+def cpu_log_prob_rate(theta, n_sample, seed=123):
+    from oracle import nsf_oracle as orc
+
+    x = make_inputs(n_sample, D, seed)
+    t0 = time.perf_counter()
+    orc.log_prob(theta, D, K_BINS, HID, TAIL, x)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def cpu_baseline_block(theta, target_s=12.0):
+    from oracle import nsf_oracle as orc  # noqa: F401  (build if needed)
+
+    rate, _ = cpu_log_prob_rate(theta, 100_000)
+    n = int(min(max(rate * target_s, 100_000), 20_000_000))
+    rate, dt = cpu_log_prob_rate(theta, n)
+    return {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle/nsf_oracle.c log_prob (OpenMP, {os.cpu_count()} threads) on {n} of the "
+                      f"{N_PER_GPU} samples of the workload, {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    theta = trained_like_theta(D, K_BINS, HID)
+    rate0, _ = cpu_log_prob_rate(theta, 50_000)
+    n = int(min(max(rate0 * 4.0, 50_000), N_PER_GPU))   # ~4 s per step
+    for _ in range(args.warmup):
+        cpu_log_prob_rate(theta, n)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_log_prob_rate(theta, n)
+    dt = time.perf_counter() - t0
+    rate = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "rqs_flow_log_prob_samples_per_sec", "value": rate, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[2] synthetic RQS flow microbench: log_prob, dim {D}, K {K_BINS}, hidden {HID}, "
+                               f"{N_PER_GPU} samples per GPU (CPU arm: bounded sample of {n} per step)"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{n} samples per step, oracle/nsf_oracle.c with OpenMP on {os.cpu_count()} threads "
+                                   "(the reference itself is Python/torch and cannot travel to the GPU box)"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from nfisam_b200 import _lib
+    from nfisam_b200.flows import NSF_AR
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    _lib.require_device()
+
+    n = args.samples
+    theta = trained_like_theta(D, K_BINS, HID)
+    flow = NSF_AR(dim=D, K=K_BINS, B=TAIL, hidden_dim=HID, device=local_rank, reference_layout=False)
+    flow.load_flat_parameters(theta)
+    h = flow.handle()
+    x_host = torch.from_numpy(make_inputs(n, D, 1000 + rank)).pin_memory()
+    x_dev = x_host.to(dev)
+    logp = torch.empty(n, dtype=torch.float32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def step():
+        _lib.check(lib.nfisam_flow_log_prob(h, x_dev.data_ptr(), n, D, logp.data_ptr(), stream))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = _lib.launch_count()
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = float(np.mean([ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
+    out_host = torch.empty(n, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        _lib.check(lib.nfisam_flow_log_prob_host(h, x_host.data_ptr(), n, D, out_host.data_ptr()))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (nf_forward_kernel<9,8>), live CUDA-event timing
+        fp32_peak = ctypes.c_double(0.0)
+        mufu_peak = ctypes.c_double(0.0)
+        _lib.check(lib.nfisam_probe_pipe_peaks(local_rank, ctypes.byref(fp32_peak), ctypes.byref(mufu_peak)))
+        fl = flops_fwd(D, HID, K_BINS)
+        achieved_tflops = fl * n / (per_launch_ms * 1e-3) * 1e-12
+        alg_bytes = (4 * D + 4) * n
+        hbm_peak, hbm_src = measured_peaks()
+        hbm_ach = alg_bytes / (per_launch_ms * 1e-3) * 1e-9
+        roofline = {
+            "bound": "fp32_fma", "kernel": "nf_forward_kernel<K=9,H=8> (log_prob mode)",
+            "achieved": achieved_tflops, "peak": fp32_peak.value, "unit": "TFLOP/s",
+            "frac": achieved_tflops / fp32_peak.value if fp32_peak.value > 0 else None,
+            "peak_source": "measured live: FFMA-only probe kernel (nfisam_probe_pipe_peaks); MEASURED_PEAKS.json holds no "
+                           "FP32 figure. The kernel is FMA/MUFU-bound (95 flop/B), not HBM- or tensor-bound (SURVEY.md 8d)",
+            "flops_per_sample": fl, "sfu_ops_per_sample": sfu_fwd(D, HID, K_BINS),
+            "mufu": {"achieved_gops": sfu_fwd(D, HID, K_BINS) * n / (per_launch_ms * 1e-3) * 1e-9, "peak_gops": mufu_peak.value},
+            "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                    "algorithmic_bytes_per_sample": 4 * D + 4, "peak_source": hbm_src},
+            "traffic": None,
+            "launch_ms": per_launch_ms,
+        }
+        extra = secondary_measurements(lib, _lib, dev, local_rank) if not args.no_extra else None
+        cpu = cpu_baseline_block(theta) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": "rqs_flow_log_prob_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[2] synthetic RQS flow microbench: log_prob, dim {D}, K {K_BINS}, hidden {HID}, "
+                                   f"{n} samples per GPU, 0.5% tail entries, PyTorch-default-init weights (seed 0)",
+                       "l2": "inputs (480 MB per pass) larger than the 126 MB L2; no flush needed",
+                       "parallelism": "replicas: samples sharded over ranks, no collective on the data path"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 4 * D * n, "d2h_bytes_per_step": 4 * n,
+                    "api": "nfisam_flow_log_prob_host (C ABI, pinned host buffers, 2-stream chunked pipeline)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if extra is not None:
+            line["incr_step"] = extra
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def secondary_measurements(lib, _lib, dev, local_rank):
+    """Companion metric: one synthetic clique fit (2000 samples, dim 11, K 9, 2000 Adam iterations,
+    the reference's small-graph setting) + 1000-sample posterior draw = seconds per incremental
+    step on a chain-shaped Bayes tree (one clique retrained per step)."""
+    import torch
+
+    from nfisam_b200.flows import NSF_AR
+
+    rng = np.random.default_rng(7)
+    d = 11
+    x = rng.standard_normal((2000, d)).astype(np.float32)
+    for i in range(1, d):
+        x[:, i] = 0.6 * x[:, i] + 0.5 * np.tanh(x[:, i - 1]) ** 2
+    x = (x - x.mean(0)) / x.std(0)
+    xd = torch.from_numpy(x).to(dev)
+    torch.manual_seed(0)
+    flow = NSF_AR(dim=d, K=9, hidden_dim=8, device=local_rank)
+    theta0 = flow.flat_parameters()
+    iters = 2000
+    flow.fit(xd, 50, 0.025, average_window=0)          # warm-up (module load, attribute set-up)
+    res = {}
+    times = []
+    for _ in range(3):
+        flow.load_flat_parameters(theta0)
+        flow.handle()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        hist, ran = flow.fit(xd, iters, 0.025, average_window=0, pull=False)
+        torch.cuda.synchronize(dev)
+        times.append(time.perf_counter() - t0)
+    res["train_2000_iters_s"] = float(np.median(times))
+    res["train_us_per_iter"] = 1e6 * res["train_2000_iters_s"] / iters
+    res["loss_first_last"] = [float(hist[0]), float(hist[ran - 1])]
+    z = torch.randn(1000, d - 5, device=dev)
+    xs = xd[:1000, :5].contiguous()
+    flow.inverse_given_separator(z, xs)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        flow.inverse_given_separator(z, xs)
+    torch.cuda.synchronize(dev)
+    res["sample_1000_s"] = (time.perf_counter() - t0) / 10
+    res["s_per_incr_step"] = res["train_2000_iters_s"] + res["sample_1000_s"]
+    res["config"] = "1 clique/step: n=2000, dim=11, K=9, hidden=8, 2000 full-batch Adam iterations (no early stop), lr .025; 1000 posterior draws"
+    # large-batch training throughput (one Adam step over 1e6 samples, dim 12)
+    xl = torch.randn(1_000_000, 12, device=dev)
+    fl = NSF_AR(dim=12, K=9, hidden_dim=8, device=local_rank)
+    fl.fit(xl, 2, 0.01, average_window=0, pull=False)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    fl.fit(xl, 10, 0.01, average_window=0, pull=False)
+    torch.cuda.synchronize(dev)
+    res["train_step_1e6_samples_per_s"] = 10 * 1_000_000 / (time.perf_counter() - t0)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=int, default=N_PER_GPU)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the incr_step companion measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,203 @@
+/*
+ * nfisam_b200.h -- C ABI of libnfisam_b200.so, the B200 (sm_100a) implementation of
+ * NF-iSAM's per-clique normalizing-flow hot path.
+ *
+ * The reference (MarineRoboticsGroup/NF-iSAM) has no FFI: its plugin surface is Python.
+ * Every entry point below names the reference Python interface it replaces (file:line are
+ * relative to the reference checkout).  The Python drop-ins in nfisam_b200/ bind these
+ * symbols with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions, no Python/torch objects cross the boundary;
+ *   - every function returns an nf_status (0 = ok, < 0 = error); nfisam_last_error() gives text;
+ *   - `*_dev` pointers are device memory on the handle's device, `*_host` pointers are host memory;
+ *   - matrices are dense row-major;  flow data are float32, factor data are float64
+ *     (the reference's dtypes: torch.float32 in src/flows, numpy float64 in src/factors);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *     calls are asynchronous on that stream unless the name ends in `_host` or says otherwise;
+ *   - a handle is not thread-safe; distinct handles may be used concurrently.
+ *
+ * Flow parameters cross the boundary as ONE float32 vector in the reference's state_dict order
+ * (src/flows/flows.py:51-63): init_param[3K-1], then for i = 1..dim-1 the conditioner FCNN(i)
+ * (src/flows/flows.py:26-41): W1[H][i], b1[H], W2[H][H], b2[H], W3[3K-1][H], b3[3K-1].
+ */
+#ifndef NFISAM_B200_H_
+#define NFISAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum nf_status {
+    NF_OK = 0,
+    NF_ERR_BAD_ARG = -1,
+    NF_ERR_CUDA = -2,
+    NF_ERR_NAN_LOSS = -3,          /* training produced a NaN/inf loss */
+    NF_ERR_NEG_DISCRIMINANT = -4,  /* inverse spline: b^2-4ac < 0 (reference asserts, src/flows/utils.py:133) */
+    NF_ERR_OOM = -5,
+    NF_ERR_UNSUPPORTED = -6        /* (K, hidden) combination not compiled in, dim too large, ... */
+} nf_status;
+
+typedef struct nf_flow nf_flow_t;
+
+/* ------------------------------------------------------------------------------------------
+ * Library / device
+ * ---------------------------------------------------------------------------------------- */
+/* Version string, e.g. "nfisam_b200 0.1 (sm_100a)". */
+const char* nfisam_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* nfisam_last_error(void);
+/* Number of CUDA devices visible; < 0 on error.  The library never falls back to the CPU. */
+int nfisam_device_count(void);
+/* Number of kernels this library launched so far in this process (bench.py's gpu_launches). */
+int64_t nfisam_launch_count(void);
+/* Measured peaks of the FP32 FMA pipe (TFLOP/s, 2 flops per FMA) and of the MUFU/SFU pipe (Gop/s) on
+ * `device`, from two register-only probe kernels: the roofline denominators of the flow kernels,
+ * which are FMA/MUFU-bound.  Synchronous, ~10 ms. */
+int nfisam_probe_pipe_peaks(int device, double* fp32_tflops, double* mufu_gops);
+/* sizeof of an ABI struct, for binding validation: 0 nf_train_cfg, 1 nf_factor_desc, 2 nf_affine. */
+int nfisam_struct_size(int which);
+
+/* ------------------------------------------------------------------------------------------
+ * Flow handle  -- replaces NSF_AR.__init__/state_dict (src/flows/flows.py:43-63)
+ * ---------------------------------------------------------------------------------------- */
+/* dim >= 1, K = number of spline bins ("num_knots"), hidden = FCNN width, tail_bound = B. */
+int nfisam_flow_create(int dim, int K, int hidden, float tail_bound, int device, nf_flow_t** out);
+int nfisam_flow_destroy(nf_flow_t* f);
+int nfisam_flow_num_params(const nf_flow_t* f, int64_t* n);
+/* Host vectors in state_dict order; synchronous. Setting parameters resets the Adam state. */
+int nfisam_flow_set_params(nf_flow_t* f, const float* theta_host, int64_t n);
+int nfisam_flow_get_params(const nf_flow_t* f, float* theta_host, int64_t n);
+
+/* ------------------------------------------------------------------------------------------
+ * Forward / log-prob / inverse
+ * ---------------------------------------------------------------------------------------- */
+/* NSF_AR.forward (src/flows/flows.py:65-93) on the first d_in <= dim columns (d_in < dim is
+ * what NormalizingFlowModelWithSeparator.separator_forward needs, src/slam/NFiSAM.py:157-173).
+ *   x_dev (n, d_in);  z_dev (n, d_in) or NULL;  logdet_dev (n) or NULL.
+ * layout 0: mathematically per-sample rows.
+ * layout 1: the reference's output layout -- z is the (d_in, n) dim-major buffer the reference
+ *           reshapes to (n, d_in) and logdet sums d_in consecutive entries of that flattening
+ *           (src/flows/flows.py:88-93).  Bit-for-bit the same values,
+ *           permuted.  Needs ws_dev: n*d_in floats of scratch (may be NULL when logdet_dev is). */
+int nfisam_flow_forward(nf_flow_t* f, const float* x_dev, int64_t n, int d_in,
+                        float* z_dev, float* logdet_dev, int layout, float* ws_dev, void* stream);
+
+/* NormalizingFlowModel.forward's prior_logprob + log_det (src/flows/models.py:11-24) with the
+ * N(0,I) base density (src/flows/prior_dist.py:5-12), per sample:  logp_dev (n). */
+int nfisam_flow_log_prob(nf_flow_t* f, const float* x_dev, int64_t n, int d_in,
+                         float* logp_dev, void* stream);
+
+/* Optional affine (un)normalisation fused into the inverse, replacing
+ * NormalizingFlowModelWithSeparator.normalize_samples / unnormalize_samples
+ * (src/slam/NFiSAM.py:96-118): x_norm = wrap?(x - mean) / std on the separator columns,
+ * x = wrap?(x_norm * std + mean) on the frontal columns, wrap = theta_to_pipi
+ * (src/utils/Functions.py:20-21) on columns flagged circular.  All arrays have `dim` entries
+ * and live on the device.  Pass NULL for `norm` to work in normalised space. */
+typedef struct nf_affine {
+    const float* mean_dev;
+    const float* std_dev;
+    const uint8_t* circular_dev;
+} nf_affine;
+
+/* NSF_AR.inverse (sep_dim = 0, src/flows/flows.py:95-113) and NSF_AR.inverse_given_separator
+ * (src/flows/flows.py:115-137):
+ *   z_dev (n, dim - sep_dim) latent draws, x_sep_dev (n, sep_dim) or NULL when sep_dim = 0,
+ *   x_out_dev (n, dim - sep_dim), logdet_dev (n) or NULL (the value NSF_AR.inverse returns).
+ * Samples whose discriminant is negative are counted in the handle; query with
+ * nfisam_flow_pop_bad_count (synchronises the stream). */
+int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim,
+                        float* x_out_dev, float* logdet_dev, const nf_affine* norm, void* stream);
+int nfisam_flow_pop_bad_count(nf_flow_t* f, void* stream, int64_t* count);
+
+/* Host-buffer convenience used for the end-to-end numbers: pinned staging, chunked
+ * H2D -> kernel -> D2H pipelining on two internal streams.  Synchronous. */
+int nfisam_flow_log_prob_host(nf_flow_t* f, const float* x_host, int64_t n, int d_in, float* logp_host);
+int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_sep_host, int64_t n, int sep_dim,
+                             float* x_out_host, const float* mean_host, const float* std_host,
+                             const uint8_t* circular_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Training  -- replaces the Adam loop of NFiSAM.fit_clique_density_model
+ * (src/slam/NFiSAM.py:425-491): loss = -mean(prior_logprob + log_det), torch.optim.Adam
+ * defaults, windowed early stop.  The whole loop runs in one persistent kernel.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nf_train_cfg {
+    int32_t max_iters;          /* flow_iterations */
+    float lr;                   /* learning_rate */
+    float beta1, beta2, eps;    /* 0.9, 0.999, 1e-8 */
+    int32_t average_window;     /* 50; <= 0 disables the early stop */
+    float loss_delta_tol;       /* 1e-2 */
+    /* validation ("slower stop", src/slam/NFiSAM.py:452-468); n_val = 0 disables */
+    const float* val_dev;       /* (n_val, dim) normalised validation rows */
+    int64_t n_val;
+    int32_t validation_interval;
+    float slower_stop_rate;
+    int32_t reset_optimizer;    /* non-zero: zero Adam moments and step count first */
+} nf_train_cfg;
+
+/* data_dev (n, dim) normalised training rows (device).  loss_hist_host: max_iters floats (host),
+ * entries >= *iters_run are set to 0 like the reference's preallocated iter_loss.
+ * Synchronous (returns after the loop finished and the history was copied back). */
+int nfisam_flow_train(nf_flow_t* f, const float* data_dev, int64_t n, const nf_train_cfg* cfg,
+                      float* loss_hist_host, int32_t* iters_run, void* stream);
+/* Asynchronous split of the above, for training several cliques concurrently on separate
+ * streams: _launch enqueues, _finish synchronises the stream and collects the history. */
+int nfisam_flow_train_launch(nf_flow_t* f, const float* data_dev, int64_t n, const nf_train_cfg* cfg, void* stream);
+int nfisam_flow_train_finish(nf_flow_t* f, float* loss_hist_host, int32_t max_iters, int32_t* iters_run, void* stream);
+
+/* loss and d loss / d theta (state_dict order, host) at the current parameters, no update:
+ * what loss.backward() leaves in .grad (src/slam/NFiSAM.py:470-474).  Synchronous. */
+int nfisam_flow_loss_grad(nf_flow_t* f, const float* data_dev, int64_t n, float* loss_host, float* grad_host,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Factor log-likelihoods  (src/factors/Factors.py, float64)
+ * ---------------------------------------------------------------------------------------- */
+typedef enum nf_factor_type {
+    NF_FACTOR_SE2_PRIOR = 1,     /* UnarySE2ApproximateGaussianPriorFactor.log_pdf, Factors.py:823-827 */
+    NF_FACTOR_SE2_BETWEEN = 2,   /* SE2RelativeGaussianLikelihoodFactor.log_pdf,   Factors.py:1443-1448 */
+    NF_FACTOR_RANGE = 3,         /* SE2R2Range / R2Range GaussianLikelihoodFactor.log_pdf, Factors.py:2724-2730, 2195-2201 */
+    NF_FACTOR_GAUSS_PRIOR = 4    /* ExplicitPriorFactor over a Gaussian (R2 landmark priors), Factors.py:328-360 */
+} nf_factor_type;
+
+#define NF_FACTOR_MAX_COLS 6
+
+/* One Gaussian component.  A mixture factor (BinaryFactorMixture / AmbiguousDataAssociationFactor /
+ * BinaryFactorWithNullHypo, Factors.py:3043-3462) is a run of `n_comp` consecutive descriptors
+ * sharing mix_id; log_pdf = log(sum_c weight_c * exp(comp_c)) -- the reference's plain log-of-sum
+ * (Factors.py:3126-3133), not a stabilised log-sum-exp.  Plain factors have n_comp = 1. */
+typedef struct nf_factor_desc {
+    int32_t type;                       /* nf_factor_type */
+    int32_t n_comp;                     /* on the first descriptor of a group: group size; else 0 */
+    int32_t cols[NF_FACTOR_MAX_COLS];   /* column indices into the sample row; unused = -1.
+                                           SE2: (x, y, th) [+ (x2, y2, th2)]; RANGE: (x1, y1, x2, y2);
+                                           GAUSS_PRIOR: up to 3 columns */
+    int32_t n_cols;
+    int32_t pad_;
+    double weight;                      /* mixture weight (normalised); 1 for plain factors */
+    double obs[3];                      /* SE2: observation / prior pose (x, y, th); RANGE: obs[0] = range; GAUSS: mean */
+    double info[9];                     /* SE2 / GAUSS: precision matrix row-major (3x3 or top-left n x n);
+                                           RANGE: info[0] = 1 / sigma^2 */
+    double lnorm;                       /* log normalisation constant: -0.5*(dim*ln(2pi) + ln det Sigma) */
+} nf_factor_desc;
+
+/* JointFactor.log_pdf (src/sampler/sampler_utils.py:86-99): out_dev[s] = sum over factor groups of
+ * log_pdf(x[s, cols]).  descs_host (n_desc) is copied to the device per call (small).
+ * x_dev (n, D) float64, out_dev (n) float64.  If per_factor_dev != NULL it receives the per-group
+ * values, (n_groups, n) row-major. */
+int nfisam_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const double* x_dev, int64_t n, int D,
+                         double* out_dev, double* per_factor_dev, int device, void* stream);
+
+/* BinaryFactorMixture.posterior_weights (Factors.py:3159-3180) for ONE mixture group:
+ * per-sample responsibilities (0.5 each where the sum underflows to 0), summed over samples and
+ * normalised.  weights_out_host: n_desc doubles.  Synchronous. */
+int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_desc, const double* x_dev, int64_t n,
+                                     int D, double* weights_out_host, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFISAM_B200_H_ */

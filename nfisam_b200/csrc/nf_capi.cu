@@ -1,0 +1,591 @@
+// C ABI of libnfisam_b200 (see include/nfisam_b200.h): handles, parameter (de)serialisation between
+// the reference's state_dict order and the kernels' packed layout, stream plumbing.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "nf_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// error / bookkeeping helpers
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+int nf_set_error(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+int nf_cuda_fail(cudaError_t e, const char* what) {
+    cudaGetLastError();
+    return nf_set_error(e == cudaErrorMemoryAllocation ? NF_ERR_OOM : NF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+int nf_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return nf_cuda_fail(e, what);
+    return NF_OK;
+}
+void nf_count_launch(int64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+int nf_sm_count(int device) {
+    static int cache[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64) return 148;
+    if (cache[device] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        cache[device] = v;
+    }
+    return cache[device];
+}
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+}  // namespace
+
+struct nf_flow {
+    int device = 0;
+    NfFlowDims fd{};
+    int64_t n_theta = 0;     // parameters in state_dict order
+    int64_t n_packed = 0;    // floats in the kernels' packed layout
+    std::vector<int32_t> pk2th;  // packed index -> state_dict index (-1 = padding)
+    float* d_pk = nullptr;
+    float* d_m = nullptr;
+    float* d_v = nullptr;
+    float* d_grad = nullptr;
+    int adam_steps = 0;
+    unsigned long long* d_bad = nullptr;
+    // training scratch
+    float* d_loss_part = nullptr;
+    size_t loss_part_cap = 0;
+    NfTrainCtrl* d_ctrl = nullptr;
+    int pending_iters = 0;
+    int pending_launches = 0;
+    // host-API staging
+    float* d_stage_in[2] = {nullptr, nullptr};
+    float* d_stage_aux[2] = {nullptr, nullptr};
+    float* d_stage_out[2] = {nullptr, nullptr};
+    size_t stage_in_cap = 0, stage_aux_cap = 0, stage_out_cap = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    float* d_norm = nullptr;       // mean | std (2 * dim floats)
+    uint8_t* d_circ = nullptr;
+};
+
+static void build_index_map(nf_flow* f) {
+    const int d = f->fd.d, K = f->fd.K, H = f->fd.H, P = f->fd.P, Pp = f->fd.Pp;
+    f->pk2th.assign((size_t)f->n_packed, -1);
+    for (int p = 0; p < P; ++p) f->pk2th[p] = p;
+    int64_t th = P;
+    for (int i = 1; i < d; ++i) {
+        const int off = nf_block_off(i, H, Pp);
+        const int oW1 = off, ob1 = oW1 + i * H, oW2 = ob1 + H, ob2 = oW2 + H * H, oW3 = ob2 + H, ob3 = oW3 + H * Pp;
+        for (int j = 0; j < H; ++j)
+            for (int k = 0; k < i; ++k) f->pk2th[oW1 + k * H + j] = (int32_t)(th + j * i + k);
+        th += (int64_t)H * i;
+        for (int j = 0; j < H; ++j) f->pk2th[ob1 + j] = (int32_t)(th + j);
+        th += H;
+        for (int j = 0; j < H; ++j)
+            for (int k = 0; k < H; ++k) f->pk2th[oW2 + k * H + j] = (int32_t)(th + j * H + k);
+        th += (int64_t)H * H;
+        for (int j = 0; j < H; ++j) f->pk2th[ob2 + j] = (int32_t)(th + j);
+        th += H;
+        for (int p = 0; p < P; ++p)
+            for (int k = 0; k < H; ++k) f->pk2th[oW3 + k * Pp + p] = (int32_t)(th + p * H + k);
+        th += (int64_t)P * H;
+        for (int p = 0; p < P; ++p) f->pk2th[ob3 + p] = (int32_t)(th + p);
+        th += P;
+    }
+    (void)K;
+}
+
+extern "C" {
+
+const char* nfisam_version(void) { return "nfisam_b200 0.1 (sm_100a)"; }
+const char* nfisam_last_error(void) { return g_last_error.c_str(); }
+int nfisam_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { nf_cuda_fail(e, "cudaGetDeviceCount"); return NF_ERR_CUDA; }
+    return n;
+}
+int64_t nfisam_launch_count(void) { return g_launches.load(); }
+int nfisam_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(nf_train_cfg);
+        case 1: return (int)sizeof(nf_factor_desc);
+        case 2: return (int)sizeof(nf_affine);
+        default: return -1;
+    }
+}
+
+int nfisam_flow_create(int dim, int K, int hidden, float tail_bound, int device, nf_flow_t** out) {
+    if (!out) return nf_set_error(NF_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (dim < 1 || dim > NF_MAX_DIM) return nf_set_error(NF_ERR_UNSUPPORTED, "dim %d outside [1, %d]", dim, NF_MAX_DIM);
+    if (K < 2 || hidden < 1 || !(tail_bound > 0.0f)) return nf_set_error(NF_ERR_BAD_ARG, "bad K / hidden / tail bound");
+    bool ok = false;
+#define NF_CASE(KK, HH) ok = ok || (K == KK && hidden == HH);
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    if (!ok) return nf_set_error(NF_ERR_UNSUPPORTED, "(K=%d, hidden=%d) is not compiled into this build", K, hidden);
+    int ndev = 0;
+    NF_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return nf_set_error(NF_ERR_BAD_ARG, "device %d of %d", device, ndev);
+    nf_flow* f = new (std::nothrow) nf_flow();
+    if (!f) return nf_set_error(NF_ERR_OOM, "host allocation failed");
+    f->device = device;
+    f->fd.d = dim; f->fd.K = K; f->fd.H = hidden; f->fd.P = 3 * K - 1; f->fd.Pp = nf_pp(K); f->fd.B = tail_bound;
+    const int64_t P = f->fd.P;
+    f->n_theta = P;
+    for (int i = 1; i < dim; ++i) f->n_theta += (int64_t)hidden * i + hidden + (int64_t)hidden * hidden + hidden + P * hidden + P;
+    f->n_packed = nf_packed_size(dim, hidden, f->fd.Pp);
+    build_index_map(f);
+    DeviceGuard g(device);
+    cudaError_t e = cudaSuccess;
+    const size_t bytes = sizeof(float) * (size_t)f->n_packed;
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_pk, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_m, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_v, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_grad, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_bad, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_ctrl, 2 * sizeof(NfTrainCtrl));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_norm, 2 * sizeof(float) * dim);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_circ, dim);
+    if (e == cudaSuccess) e = cudaMemset(f->d_pk, 0, bytes);
+    if (e == cudaSuccess) e = cudaMemset(f->d_m, 0, bytes);
+    if (e == cudaSuccess) e = cudaMemset(f->d_v, 0, bytes);
+    if (e == cudaSuccess) e = cudaMemset(f->d_bad, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        int rc = nf_cuda_fail(e, "flow_create allocation");
+        nfisam_flow_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return NF_OK;
+}
+
+int nfisam_flow_destroy(nf_flow_t* f) {
+    if (!f) return NF_OK;
+    DeviceGuard g(f->device);
+    cudaFree(f->d_pk); cudaFree(f->d_m); cudaFree(f->d_v); cudaFree(f->d_grad); cudaFree(f->d_bad);
+    cudaFree(f->d_loss_part); cudaFree(f->d_ctrl); cudaFree(f->d_norm); cudaFree(f->d_circ);
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(f->d_stage_in[s]); cudaFree(f->d_stage_aux[s]); cudaFree(f->d_stage_out[s]);
+        if (f->streams[s]) cudaStreamDestroy(f->streams[s]);
+    }
+    cudaGetLastError();
+    delete f;
+    return NF_OK;
+}
+
+int nfisam_flow_num_params(const nf_flow_t* f, int64_t* n) {
+    if (!f || !n) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    *n = f->n_theta;
+    return NF_OK;
+}
+
+int nfisam_flow_set_params(nf_flow_t* f, const float* theta_host, int64_t n) {
+    if (!f || !theta_host) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n != f->n_theta) return nf_set_error(NF_ERR_BAD_ARG, "expected %lld parameters, got %lld", (long long)f->n_theta, (long long)n);
+    std::vector<float> pk((size_t)f->n_packed, 0.0f);
+    for (int64_t p = 0; p < f->n_packed; ++p)
+        if (f->pk2th[p] >= 0) pk[p] = theta_host[f->pk2th[p]];
+    DeviceGuard g(f->device);
+    const size_t bytes = sizeof(float) * (size_t)f->n_packed;
+    NF_CUDA(cudaMemcpy(f->d_pk, pk.data(), bytes, cudaMemcpyHostToDevice));
+    NF_CUDA(cudaMemset(f->d_m, 0, bytes));
+    NF_CUDA(cudaMemset(f->d_v, 0, bytes));
+    f->adam_steps = 0;
+    return NF_OK;
+}
+
+static int unpack_to_host(const nf_flow* f, const float* d_src, float* dst_host) {
+    std::vector<float> pk((size_t)f->n_packed);
+    NF_CUDA(cudaMemcpy(pk.data(), d_src, sizeof(float) * (size_t)f->n_packed, cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < f->n_packed; ++p)
+        if (f->pk2th[p] >= 0) dst_host[f->pk2th[p]] = pk[p];
+    return NF_OK;
+}
+
+int nfisam_flow_get_params(const nf_flow_t* f, float* theta_host, int64_t n) {
+    if (!f || !theta_host) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n != f->n_theta) return nf_set_error(NF_ERR_BAD_ARG, "expected %lld parameters, got %lld", (long long)f->n_theta, (long long)n);
+    DeviceGuard g(f->device);
+    return unpack_to_host(f, f->d_pk, theta_host);
+}
+
+int nfisam_flow_forward(nf_flow_t* f, const float* x_dev, int64_t n, int d_in, float* z_dev, float* logdet_dev,
+                        int layout, float* ws_dev, void* stream) {
+    if (!f || (!x_dev && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n < 0 || d_in < 1 || d_in > f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / d_in");
+    if (layout != 0 && layout != 1) return nf_set_error(NF_ERR_BAD_ARG, "layout must be 0 or 1");
+    if (layout == 1 && logdet_dev && !ws_dev) return nf_set_error(NF_ERR_BAD_ARG, "layout 1 with logdet needs ws_dev");
+    DeviceGuard g(f->device);
+    return nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, z_dev, logdet_dev, nullptr, ws_dev, layout, f->device,
+                             (cudaStream_t)stream);
+}
+
+int nfisam_flow_log_prob(nf_flow_t* f, const float* x_dev, int64_t n, int d_in, float* logp_dev, void* stream) {
+    if (!f || ((!x_dev || !logp_dev) && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n < 0 || d_in < 1 || d_in > f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / d_in");
+    DeviceGuard g(f->device);
+    return nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, nullptr, nullptr, logp_dev, nullptr, 0, f->device,
+                             (cudaStream_t)stream);
+}
+
+int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim,
+                        float* x_out_dev, float* logdet_dev, const nf_affine* norm, void* stream) {
+    if (!f || ((!z_dev || !x_out_dev) && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n < 0 || sep_dim < 0 || sep_dim >= f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / sep_dim");
+    if (sep_dim > 0 && !x_sep_dev && n > 0) return nf_set_error(NF_ERR_BAD_ARG, "x_sep_dev is NULL");
+    const float* mean = nullptr; const float* stdv = nullptr; const uint8_t* circ = nullptr;
+    if (norm) {
+        if (!norm->mean_dev || !norm->std_dev || !norm->circular_dev) return nf_set_error(NF_ERR_BAD_ARG, "incomplete nf_affine");
+        mean = norm->mean_dev; stdv = norm->std_dev; circ = norm->circular_dev;
+    }
+    DeviceGuard g(f->device);
+    return nf_launch_inverse(f->fd, f->d_pk, z_dev, x_sep_dev, n, sep_dim, x_out_dev, logdet_dev, mean, stdv, circ,
+                             f->d_bad, f->device, (cudaStream_t)stream);
+}
+
+int nfisam_flow_pop_bad_count(nf_flow_t* f, void* stream, int64_t* count) {
+    if (!f || !count) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard g(f->device);
+    unsigned long long h = 0;
+    NF_CUDA(cudaMemcpyAsync(&h, f->d_bad, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    NF_CUDA(cudaMemsetAsync(f->d_bad, 0, sizeof(h), (cudaStream_t)stream));
+    NF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *count = (int64_t)h;
+    return NF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer pipelines
+// ------------------------------------------------------------------------------------------------
+static int ensure_streams(nf_flow* f) {
+    for (int s = 0; s < 2; ++s)
+        if (!f->streams[s]) NF_CUDA(cudaStreamCreateWithFlags(&f->streams[s], cudaStreamNonBlocking));
+    return NF_OK;
+}
+static int ensure_cap(float** bufs, size_t* cap, size_t want) {
+    if (*cap >= want) return NF_OK;
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(bufs[s]);
+        bufs[s] = nullptr;
+    }
+    *cap = 0;
+    for (int s = 0; s < 2; ++s) NF_CUDA(cudaMalloc(&bufs[s], want * sizeof(float)));
+    *cap = want;
+    return NF_OK;
+}
+
+int nfisam_flow_log_prob_host(nf_flow_t* f, const float* x_host, int64_t n, int d_in, float* logp_host) {
+    if (!f || ((!x_host || !logp_host) && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n < 0 || d_in < 1 || d_in > f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / d_in");
+    if (n == 0) return NF_OK;
+    DeviceGuard g(f->device);
+    int rc = ensure_streams(f);
+    if (rc != NF_OK) return rc;
+    const int64_t chunk = n < (1 << 20) ? (n + 1) / 2 > 0 ? (n + 1) / 2 : 1 : (1 << 20);
+    if ((rc = ensure_cap(f->d_stage_in, &f->stage_in_cap, (size_t)chunk * d_in)) != NF_OK) return rc;
+    if ((rc = ensure_cap(f->d_stage_out, &f->stage_out_cap, (size_t)chunk)) != NF_OK) return rc;
+    int s = 0;
+    for (int64_t o = 0; o < n; o += chunk, s ^= 1) {
+        const int64_t m = n - o < chunk ? n - o : chunk;
+        cudaStream_t st = f->streams[s];
+        NF_CUDA(cudaMemcpyAsync(f->d_stage_in[s], x_host + o * d_in, sizeof(float) * (size_t)m * d_in, cudaMemcpyHostToDevice, st));
+        rc = nf_launch_forward(f->fd, f->d_pk, f->d_stage_in[s], m, d_in, nullptr, nullptr, f->d_stage_out[s], nullptr, 0,
+                               f->device, st);
+        if (rc != NF_OK) return rc;
+        NF_CUDA(cudaMemcpyAsync(logp_host + o, f->d_stage_out[s], sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    }
+    NF_CUDA(cudaStreamSynchronize(f->streams[0]));
+    NF_CUDA(cudaStreamSynchronize(f->streams[1]));
+    return NF_OK;
+}
+
+int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_sep_host, int64_t n, int sep_dim,
+                             float* x_out_host, const float* mean_host, const float* std_host,
+                             const uint8_t* circular_host) {
+    if (!f || ((!z_host || !x_out_host) && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n < 0 || sep_dim < 0 || sep_dim >= f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / sep_dim");
+    if (sep_dim > 0 && !x_sep_host && n > 0) return nf_set_error(NF_ERR_BAD_ARG, "x_sep_host is NULL");
+    if (n == 0) return NF_OK;
+    const int d = f->fd.d, fr = d - sep_dim;
+    DeviceGuard g(f->device);
+    int rc = ensure_streams(f);
+    if (rc != NF_OK) return rc;
+    const bool has_norm = mean_host && std_host && circular_host;
+    if (has_norm) {
+        NF_CUDA(cudaMemcpyAsync(f->d_norm, mean_host, sizeof(float) * d, cudaMemcpyHostToDevice, f->streams[0]));
+        NF_CUDA(cudaMemcpyAsync(f->d_norm + d, std_host, sizeof(float) * d, cudaMemcpyHostToDevice, f->streams[0]));
+        NF_CUDA(cudaMemcpyAsync(f->d_circ, circular_host, d, cudaMemcpyHostToDevice, f->streams[0]));
+        NF_CUDA(cudaStreamSynchronize(f->streams[0]));
+    }
+    const int64_t chunk = n < (1 << 20) ? (n + 1) / 2 > 0 ? (n + 1) / 2 : 1 : (1 << 20);
+    if ((rc = ensure_cap(f->d_stage_in, &f->stage_in_cap, (size_t)chunk * d)) != NF_OK) return rc;
+    if ((rc = ensure_cap(f->d_stage_aux, &f->stage_aux_cap, (size_t)chunk * d)) != NF_OK) return rc;
+    if ((rc = ensure_cap(f->d_stage_out, &f->stage_out_cap, (size_t)chunk * d)) != NF_OK) return rc;
+    int s = 0;
+    for (int64_t o = 0; o < n; o += chunk, s ^= 1) {
+        const int64_t m = n - o < chunk ? n - o : chunk;
+        cudaStream_t st = f->streams[s];
+        NF_CUDA(cudaMemcpyAsync(f->d_stage_in[s], z_host + o * fr, sizeof(float) * (size_t)m * fr, cudaMemcpyHostToDevice, st));
+        if (sep_dim > 0)
+            NF_CUDA(cudaMemcpyAsync(f->d_stage_aux[s], x_sep_host + o * sep_dim, sizeof(float) * (size_t)m * sep_dim,
+                                    cudaMemcpyHostToDevice, st));
+        rc = nf_launch_inverse(f->fd, f->d_pk, f->d_stage_in[s], sep_dim > 0 ? f->d_stage_aux[s] : nullptr, m, sep_dim,
+                               f->d_stage_out[s], nullptr, has_norm ? f->d_norm : nullptr, has_norm ? f->d_norm + d : nullptr,
+                               has_norm ? f->d_circ : nullptr, f->d_bad, f->device, st);
+        if (rc != NF_OK) return rc;
+        NF_CUDA(cudaMemcpyAsync(x_out_host + o * fr, f->d_stage_out[s], sizeof(float) * (size_t)m * fr, cudaMemcpyDeviceToHost, st));
+    }
+    NF_CUDA(cudaStreamSynchronize(f->streams[0]));
+    NF_CUDA(cudaStreamSynchronize(f->streams[1]));
+    unsigned long long h = 0;
+    NF_CUDA(cudaMemcpy(&h, f->d_bad, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h) {
+        cudaMemset(f->d_bad, 0, sizeof(h));
+        return nf_set_error(NF_ERR_NEG_DISCRIMINANT, "%llu samples hit a negative discriminant in the inverse spline", h);
+    }
+    return NF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training
+// ------------------------------------------------------------------------------------------------
+static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const nf_train_cfg* cfg, NfTrainArgs* a,
+                           cudaStream_t st) {
+    if (cfg->max_iters < 1) return nf_set_error(NF_ERR_BAD_ARG, "max_iters < 1");
+    if (!(cfg->lr > 0.0f) || !(cfg->beta1 >= 0.0f && cfg->beta1 < 1.0f) || !(cfg->beta2 >= 0.0f && cfg->beta2 < 1.0f))
+        return nf_set_error(NF_ERR_BAD_ARG, "bad Adam hyper-parameters");
+    const size_t need = nf_train_loss_part_elems(f->fd, cfg->max_iters);
+    if (f->loss_part_cap < need) {
+        cudaFree(f->d_loss_part);
+        f->d_loss_part = nullptr;
+        f->loss_part_cap = 0;
+        NF_CUDA(cudaMalloc(&f->d_loss_part, need * sizeof(float)));
+        f->loss_part_cap = need;
+    }
+    if (cfg->reset_optimizer) {
+        const size_t bytes = sizeof(float) * (size_t)f->n_packed;
+        NF_CUDA(cudaMemsetAsync(f->d_m, 0, bytes, st));
+        NF_CUDA(cudaMemsetAsync(f->d_v, 0, bytes, st));
+        f->adam_steps = 0;
+    }
+    NF_CUDA(cudaMemsetAsync(f->d_ctrl, 0, 2 * sizeof(NfTrainCtrl), st));
+    memset(a, 0, sizeof(*a));
+    a->pk = f->d_pk; a->adam_m = f->d_m; a->adam_v = f->d_v;
+    a->data = data_dev; a->n = n;
+    a->val = cfg->val_dev; a->n_val = cfg->n_val;
+    a->max_iters = cfg->max_iters;
+    a->lr = cfg->lr; a->beta1 = cfg->beta1; a->beta2 = cfg->beta2; a->eps = cfg->eps;
+    a->average_window = cfg->average_window;
+    a->loss_delta_tol = cfg->loss_delta_tol;
+    a->validation_interval = cfg->validation_interval;
+    a->slower_stop_rate = cfg->slower_stop_rate;
+    a->step0 = f->adam_steps;
+    a->grad_only = 0;
+    a->grad_out = f->d_grad;
+    a->loss_part = f->d_loss_part;
+    a->ctrl = f->d_ctrl;
+    return NF_OK;
+}
+
+int nfisam_flow_train_launch(nf_flow_t* f, const float* data_dev, int64_t n, const nf_train_cfg* cfg, void* stream) {
+    if (!f || !data_dev || !cfg) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n < 1) return nf_set_error(NF_ERR_BAD_ARG, "empty training set");
+    if (f->pending_launches) return nf_set_error(NF_ERR_BAD_ARG, "a training run is already pending on this handle");
+    DeviceGuard g(f->device);
+    NfTrainArgs a;
+    int rc = fill_train_args(f, data_dev, n, cfg, &a, (cudaStream_t)stream);
+    if (rc != NF_OK) return rc;
+    rc = nf_launch_train(f->fd, a, f->device, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    f->pending_launches = rc;
+    f->pending_iters = cfg->max_iters;
+    return NF_OK;
+}
+
+int nfisam_flow_train_finish(nf_flow_t* f, float* loss_hist_host, int32_t max_iters, int32_t* iters_run, void* stream) {
+    if (!f) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (!f->pending_launches) return nf_set_error(NF_ERR_BAD_ARG, "no training run pending on this handle");
+    DeviceGuard g(f->device);
+    const int iters = f->pending_iters, launches = f->pending_launches;
+    f->pending_launches = 0;
+    f->pending_iters = 0;
+    const int d = f->fd.d;
+    std::vector<float> part((size_t)iters * d);
+    NfTrainCtrl ctrl[2];
+    NF_CUDA(cudaMemcpyAsync(part.data(), f->d_loss_part, part.size() * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    NF_CUDA(cudaMemcpyAsync(ctrl, f->d_ctrl, sizeof(ctrl), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    NF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const NfTrainCtrl& fin = ctrl[launches & 1];
+    const int ran = fin.stop ? fin.iters_run : iters;
+    f->adam_steps += ran;
+    if (iters_run) *iters_run = ran;
+    bool nan = fin.status != 0;
+    for (int t = 0; t < iters; ++t) {
+        float acc = 0.0f;
+        if (t < ran) {
+            for (int i = 0; i < d; ++i) acc += part[(size_t)t * d + i];
+            if (!(acc == acc) || acc > 3.0e38f || acc < -3.0e38f) nan = true;
+        }
+        if (loss_hist_host && t < max_iters) loss_hist_host[t] = acc;
+    }
+    if (loss_hist_host)
+        for (int t = iters; t < max_iters; ++t) loss_hist_host[t] = 0.0f;
+    if (nan) return nf_set_error(NF_ERR_NAN_LOSS, "training loss became NaN/inf");
+    return NF_OK;
+}
+
+int nfisam_flow_train(nf_flow_t* f, const float* data_dev, int64_t n, const nf_train_cfg* cfg, float* loss_hist_host,
+                      int32_t* iters_run, void* stream) {
+    int rc = nfisam_flow_train_launch(f, data_dev, n, cfg, stream);
+    if (rc != NF_OK) return rc;
+    return nfisam_flow_train_finish(f, loss_hist_host, cfg->max_iters, iters_run, stream);
+}
+
+int nfisam_flow_loss_grad(nf_flow_t* f, const float* data_dev, int64_t n, float* loss_host, float* grad_host,
+                          void* stream) {
+    if (!f || !data_dev) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n < 1) return nf_set_error(NF_ERR_BAD_ARG, "empty data");
+    if (f->pending_launches) return nf_set_error(NF_ERR_BAD_ARG, "a training run is pending on this handle");
+    DeviceGuard g(f->device);
+    nf_train_cfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.max_iters = 1; cfg.lr = 1e-3f; cfg.beta1 = 0.9f; cfg.beta2 = 0.999f; cfg.eps = 1e-8f;
+    NfTrainArgs a;
+    int rc = fill_train_args(f, data_dev, n, &cfg, &a, (cudaStream_t)stream);
+    if (rc != NF_OK) return rc;
+    a.grad_only = 1;
+    NF_CUDA(cudaMemsetAsync(f->d_grad, 0, sizeof(float) * (size_t)f->n_packed, (cudaStream_t)stream));
+    rc = nf_launch_train(f->fd, a, f->device, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    NF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (grad_host) {
+        rc = unpack_to_host(f, f->d_grad, grad_host);
+        if (rc != NF_OK) return rc;
+    }
+    if (loss_host) {
+        std::vector<float> part((size_t)f->fd.d);
+        NF_CUDA(cudaMemcpy(part.data(), f->d_loss_part, part.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        float acc = 0.0f;
+        for (float v : part) acc += v;
+        *loss_host = acc;
+    }
+    return NF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// factors
+// ------------------------------------------------------------------------------------------------
+static int validate_descs(const nf_factor_desc* d, int n_desc, int D, int* n_groups) {
+    int groups = 0;
+    for (int i = 0; i < n_desc;) {
+        const int nc = d[i].n_comp < 1 ? 1 : d[i].n_comp;
+        if (i + nc > n_desc) return nf_set_error(NF_ERR_BAD_ARG, "mixture group at %d overruns the descriptor list", i);
+        for (int c = 0; c < nc; ++c) {
+            const nf_factor_desc& f = d[i + c];
+            int need = 0;
+            switch (f.type) {
+                case NF_FACTOR_SE2_PRIOR: need = 3; break;
+                case NF_FACTOR_SE2_BETWEEN: need = 6; break;
+                case NF_FACTOR_RANGE: need = 4; break;
+                case NF_FACTOR_GAUSS_PRIOR: need = f.n_cols; if (need < 1 || need > 3) need = -1; break;
+                default: need = -1;
+            }
+            if (need < 0 || f.n_cols != need) return nf_set_error(NF_ERR_BAD_ARG, "descriptor %d: bad type / n_cols", i + c);
+            for (int k = 0; k < need; ++k)
+                if (f.cols[k] < 0 || f.cols[k] >= D) return nf_set_error(NF_ERR_BAD_ARG, "descriptor %d: column out of range", i + c);
+        }
+        i += nc;
+        ++groups;
+    }
+    *n_groups = groups;
+    return NF_OK;
+}
+
+int nfisam_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const double* x_dev, int64_t n, int D,
+                         double* out_dev, double* per_factor_dev, int device, void* stream) {
+    if (!descs_host || n_desc < 1 || ((!x_dev || !out_dev) && n > 0) || D < 1 || n < 0)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    int groups = 0;
+    int rc = validate_descs(descs_host, n_desc, D, &groups);
+    if (rc != NF_OK) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    nf_factor_desc* d_desc = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    NF_CUDA(cudaMallocAsync(&d_desc, sizeof(nf_factor_desc) * (size_t)n_desc, st));
+    cudaError_t e = cudaMemcpyAsync(d_desc, descs_host, sizeof(nf_factor_desc) * (size_t)n_desc, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = nf_launch_factor_logpdf(d_desc, n_desc, groups, x_dev, n, D, out_dev, per_factor_dev, device, st);
+    cudaFreeAsync(d_desc, st);
+    if (e != cudaSuccess) return nf_cuda_fail(e, "descriptor upload");
+    // descs_host may be pageable and short-lived: make sure the upload is complete before returning
+    NF_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_desc, const double* x_dev, int64_t n, int D,
+                                     double* weights_out_host, int device, void* stream) {
+    if (!descs_host || n_desc < 1 || !x_dev || !weights_out_host || n < 1 || D < 1)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    int groups = 0;
+    std::vector<nf_factor_desc> tmp(descs_host, descs_host + n_desc);
+    tmp[0].n_comp = n_desc;
+    for (int c = 1; c < n_desc; ++c) tmp[c].n_comp = 0;
+    int rc = validate_descs(tmp.data(), n_desc, D, &groups);
+    if (rc != NF_OK) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    cudaStream_t st = (cudaStream_t)stream;
+    nf_factor_desc* d_desc = nullptr;
+    double* d_part = nullptr;
+    int n_part = 1024;
+    NF_CUDA(cudaMallocAsync(&d_desc, sizeof(nf_factor_desc) * (size_t)n_desc, st));
+    NF_CUDA(cudaMallocAsync(&d_part, sizeof(double) * 16 * (size_t)n_part, st));
+    NF_CUDA(cudaMemcpyAsync(d_desc, tmp.data(), sizeof(nf_factor_desc) * (size_t)n_desc, cudaMemcpyHostToDevice, st));
+    rc = nf_launch_mixture_weights(d_desc, n_desc, x_dev, n, D, d_part, &n_part, device, st);
+    std::vector<double> part((size_t)16 * n_part);
+    if (rc == NF_OK) {
+        cudaError_t e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = nf_cuda_fail(e, "partial download");
+    }
+    cudaFreeAsync(d_desc, st);
+    cudaFreeAsync(d_part, st);
+    NF_CUDA(cudaStreamSynchronize(st));
+    if (rc != NF_OK) return rc;
+    double total = 0.0;
+    for (int c = 0; c < n_desc; ++c) {
+        double v = 0.0;
+        for (int b = 0; b < n_part; ++b) v += part[(size_t)b * 16 + c];
+        weights_out_host[c] = v;
+        total += v;
+    }
+    for (int c = 0; c < n_desc; ++c) weights_out_host[c] /= total;
+    return NF_OK;
+}
+
+}  // extern "C"

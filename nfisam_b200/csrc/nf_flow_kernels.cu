@@ -1,0 +1,225 @@
+// Fused autoregressive rational-quadratic-spline flow kernels: forward / log-prob / inverse.
+// One thread owns one sample and walks the dims; the whole model sits in shared memory and every
+// lane of a warp evaluates the same conditioner, so weights are float4 shared-memory broadcasts.
+//
+// Reference: NSF_AR.forward / inverse / inverse_given_separator (src/flows/flows.py:65-137),
+// NormalizingFlowModel.forward (src/flows/models.py:11-24).
+#include "nf_internal.h"
+
+namespace {
+
+constexpr int TPB = 128;
+
+__device__ __forceinline__ void load_weights(float* sw, const float* __restrict__ pk, int count) {
+    const float4* src = reinterpret_cast<const float4*>(pk);
+    float4* dst = reinterpret_cast<float4*>(sw);
+    for (int t = threadIdx.x; t < count / 4; t += blockDim.x) dst[t] = src[t];
+}
+
+// mode bits
+constexpr int WANT_Z = 1, WANT_LD = 2, WANT_LP = 4, REF_LAYOUT = 8;
+
+template <int K, int H>
+__global__ void __launch_bounds__(TPB)
+nf_forward_kernel(const float* __restrict__ pk, int wcount, int d_in, float B, const float* __restrict__ x, int64_t n,
+                  float* __restrict__ z, float* __restrict__ logdet, float* __restrict__ logp, float* __restrict__ ws,
+                  int mode) {
+    constexpr int PP = ((3 * K - 1) + 3) & ~3;
+    extern __shared__ __align__(16) float smem[];
+    float* sw = smem;
+    const int dp = d_in | 1;                      // odd row stride: conflict-free per-thread rows
+    float* xs = sw + wcount;
+    float* zs = xs + TPB * dp;
+    load_weights(sw, pk, wcount);
+    const int64_t tiles = (n + TPB - 1) / TPB;
+    const bool ref_layout = mode & REF_LAYOUT;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * TPB;
+        const int cnt = (int)min((int64_t)TPB, n - s0);
+        __syncthreads();                           // weights ready / previous tile drained
+        const float* xg = x + s0 * d_in;
+        for (int t = threadIdx.x; t < cnt * d_in; t += TPB) {
+            const int r = t / d_in, c = t - r * d_in;
+            xs[r * dp + c] = xg[t];
+        }
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            const float* xrow = xs + threadIdx.x * dp;
+            float* zrow = zs + threadIdx.x * dp;
+            const int64_t s = s0 + threadIdx.x;
+            float ld_acc = 0.0f, sq_acc = 0.0f;
+            for (int i = 0; i < d_in; ++i) {
+                float out[PP];
+                nf_conditioner<K, H>(sw, i, xrow, out);
+                float ld;
+                const float zz = nf_rqs_forward<K>(out, B, xrow[i], ld);
+                ld_acc += ld;
+                sq_acc = fmaf(zz, zz, sq_acc);
+                if (ref_layout) {
+                    if (mode & WANT_Z) z[(int64_t)i * n + s] = zz;
+                    if (mode & WANT_LD) ws[(int64_t)i * n + s] = ld;
+                } else if (mode & WANT_Z) {
+                    zrow[i] = zz;
+                }
+            }
+            if (!ref_layout && (mode & WANT_LD)) logdet[s] = ld_acc;
+            if (mode & WANT_LP) logp[s] = ld_acc - 0.5f * sq_acc - 0.91893853320467274178f * (float)d_in;
+        }
+        if (!ref_layout && (mode & WANT_Z)) {
+            __syncthreads();
+            float* zg = z + s0 * d_in;
+            for (int t = threadIdx.x; t < cnt * d_in; t += TPB) {
+                const int r = t / d_in, c = t - r * d_in;
+                zg[t] = zs[r * dp + c];
+            }
+        }
+    }
+}
+
+// reference layout: logdet[r] = sum_c ws[r * d_in + c]  (src/flows/flows.py:93)
+__global__ void nf_rowsum_kernel(const float* __restrict__ ws, int64_t n, int d_in, float* __restrict__ logdet) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float acc = 0.0f;
+    for (int c = 0; c < d_in; ++c) acc += ws[r * d_in + c];
+    logdet[r] = acc;
+}
+
+template <int K, int H>
+__global__ void __launch_bounds__(TPB)
+nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, float B, const float* __restrict__ zin,
+                  const float* __restrict__ xsep, int64_t n, float* __restrict__ xout, float* __restrict__ logdet,
+                  const float* __restrict__ mean, const float* __restrict__ stdv, const uint8_t* __restrict__ circ,
+                  unsigned long long* __restrict__ bad_count) {
+    constexpr int PP = ((3 * K - 1) + 3) & ~3;
+    extern __shared__ __align__(16) float smem[];
+    float* sw = smem;
+    const int dp = d | 1;
+    const int f = d - sep;
+    float* xs = sw + wcount;                       // [TPB][dp]  separator columns then generated ones
+    float* zs = xs + TPB * dp;                     // [TPB][dp]  latent draws (first f columns used)
+    load_weights(sw, pk, wcount);
+    const bool has_norm = mean != nullptr;
+    const int64_t tiles = (n + TPB - 1) / TPB;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * TPB;
+        const int cnt = (int)min((int64_t)TPB, n - s0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt * sep; t += TPB) {
+            const int r = t / sep, c = t - r * sep;
+            float v = xsep[s0 * sep + t];
+            if (has_norm) {
+                v = v - mean[c];
+                if (circ[c]) v = nf_wrap_pipi(v);
+                v = v / stdv[c];
+            }
+            xs[r * dp + c] = v;
+        }
+        for (int t = threadIdx.x; t < cnt * f; t += TPB) {
+            const int r = t / f, c = t - r * f;
+            zs[r * dp + c] = zin[s0 * f + t];
+        }
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            float* xrow = xs + threadIdx.x * dp;
+            const float* zrow = zs + threadIdx.x * dp;
+            float ld_acc = 0.0f;
+            bool bad = false;
+            for (int i = sep; i < d; ++i) {
+                float out[PP];
+                nf_conditioner<K, H>(sw, i, xrow, out);
+                float ld;
+                const float xi = nf_rqs_inverse<K>(out, B, zrow[i - sep], ld, bad);
+                ld_acc += ld;
+                xrow[i] = xi;
+            }
+            if (logdet) logdet[s0 + threadIdx.x] = ld_acc;
+            if (bad) atomicAdd(bad_count, 1ULL);
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt * f; t += TPB) {
+            const int r = t / f, c = t - r * f;
+            float v = xs[r * dp + sep + c];
+            if (has_norm) {
+                v = fmaf(v, stdv[sep + c], mean[sep + c]);
+                if (circ[sep + c]) v = nf_wrap_pipi(v);
+            }
+            xout[s0 * f + t] = v;
+        }
+    }
+}
+
+template <typename KernelT>
+int grid_for(KernelT kernel, size_t smem_bytes, int64_t tiles, int device) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, smem_bytes);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = (int64_t)nf_sm_count(device) * per_sm;
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+template <int K, int H>
+int launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_t n, int d_in, float* z, float* logdet,
+                   float* logp, float* ws, int mode, int device, cudaStream_t st) {
+    const int wcount = nf_block_off(d_in, H, fd.Pp);
+    const int dp = d_in | 1;
+    const size_t smem = sizeof(float) * ((size_t)wcount + 2 * (size_t)TPB * dp);
+    auto kern = nf_forward_kernel<K, H>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return nf_set_error(NF_ERR_UNSUPPORTED, "flow does not fit in shared memory");
+    }
+    const int64_t tiles = (n + TPB - 1) / TPB;
+    const int grid = grid_for(kern, smem, tiles, device);
+    kern<<<grid, TPB, smem, st>>>(pk, wcount, d_in, fd.B, x, n, z, logdet, logp, ws, mode);
+    nf_count_launch();
+    if ((mode & REF_LAYOUT) && (mode & WANT_LD)) {
+        nf_rowsum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, n, d_in, logdet);
+        nf_count_launch();
+    }
+    return nf_check_launch("nf_forward_kernel");
+}
+
+template <int K, int H>
+int launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep,
+                   float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
+                   unsigned long long* bad, int device, cudaStream_t st) {
+    const int wcount = nf_block_off(fd.d, H, fd.Pp);
+    const int dp = fd.d | 1;
+    const size_t smem = sizeof(float) * ((size_t)wcount + 2 * (size_t)TPB * dp);
+    auto kern = nf_inverse_kernel<K, H>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return nf_set_error(NF_ERR_UNSUPPORTED, "flow does not fit in shared memory");
+    }
+    const int64_t tiles = (n + TPB - 1) / TPB;
+    const int grid = grid_for(kern, smem, tiles, device);
+    kern<<<grid, TPB, smem, st>>>(pk, wcount, fd.d, sep, fd.B, zin, xsep, n, xout, logdet, mean, stdv, circ, bad);
+    nf_count_launch();
+    return nf_check_launch("nf_inverse_kernel");
+}
+
+}  // namespace
+
+int nf_launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_t n, int d_in, float* z,
+                      float* logdet, float* logp, float* ws, int layout, int device, cudaStream_t st) {
+    if (n == 0) return NF_OK;
+    int mode = (z ? WANT_Z : 0) | (logdet ? WANT_LD : 0) | (logp ? WANT_LP : 0) | (layout == 1 ? REF_LAYOUT : 0);
+#define NF_CASE(KK, HH) \
+    if (fd.K == KK && fd.H == HH) return launch_forward<KK, HH>(fd, pk, x, n, d_in, z, logdet, logp, ws, mode, device, st);
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
+}
+
+int nf_launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep,
+                      float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
+                      unsigned long long* bad, int device, cudaStream_t st) {
+    if (n == 0) return NF_OK;
+#define NF_CASE(KK, HH) \
+    if (fd.K == KK && fd.H == HH) \
+        return launch_inverse<KK, HH>(fd, pk, zin, xsep, n, sep, xout, logdet, mean, stdv, circ, bad, device, st);
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
+}

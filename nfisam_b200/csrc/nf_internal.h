@@ -1,0 +1,77 @@
+// Internal (non-ABI) declarations shared by the translation units of libnfisam_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nfisam_b200.h"
+#include "nf_common.cuh"
+
+// (K, hidden) combinations compiled into the library.  K: spline bins, hidden: FCNN width.
+// Reference defaults/examples: K in {5, 9, 12, 15}, hidden 8 (src/slam/NFiSAM.py:18-40,
+// example/slam/*/run_nfisam.py).
+#define NF_FOREACH_KH(X) \
+    X(5, 8) X(9, 8) X(12, 8) X(15, 8) X(5, 16) X(9, 16) X(12, 16) X(15, 16)
+
+struct NfFlowDims {
+    int d, K, H, P, Pp;
+    float B;
+};
+
+int nf_set_error(int code, const char* fmt, ...);
+int nf_check_launch(const char* what);
+int nf_cuda_fail(cudaError_t e, const char* what);
+void nf_count_launch(int64_t k = 1);
+int nf_sm_count(int device);
+
+#define NF_CUDA(expr)                                            \
+    do {                                                         \
+        cudaError_t e__ = (expr);                                \
+        if (e__ != cudaSuccess) return nf_cuda_fail(e__, #expr); \
+    } while (0)
+
+// nf_flow_kernels.cu
+int nf_launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_t n, int d_in, float* z,
+                      float* logdet, float* logp, float* ws, int layout, int device, cudaStream_t st);
+int nf_launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep,
+                      float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
+                      unsigned long long* bad, int device, cudaStream_t st);
+
+// nf_train_kernel.cu
+struct NfTrainCtrl {
+    int stop;               // 1: the stopping rule fired (or the loss went NaN)
+    int iters_run;          // valid when stop = 1
+    int have_avg;
+    int status;             // 1: NaN / inf loss
+    float loss_avg;
+    int pad_[3];
+};
+struct NfTrainArgs {
+    float* pk;              // packed parameters (updated in place)
+    float* adam_m;          // packed Adam first moment
+    float* adam_v;          // packed Adam second moment
+    const float* data;      // (n, d)
+    int64_t n;
+    const float* val;       // (n_val, d) or null
+    int64_t n_val;
+    int max_iters;
+    float lr, beta1, beta2, eps;
+    int average_window;
+    float loss_delta_tol;
+    int validation_interval;
+    float slower_stop_rate;
+    int step0;              // Adam steps already taken (bias correction continues from here)
+    int grad_only;          // 1: write the reduced gradient to grad_out (packed order), no update
+    float* grad_out;        // packed-size buffer (grad_only)
+    float* loss_part;       // (max_iters, d) per-dim loss contributions
+    NfTrainCtrl* ctrl;      // [2] double-buffered early-stop record (zeroed before the first launch)
+};
+// Returns the number of launches enqueued (>= 1) or a negative nf_status.  The final control record
+// is ctrl[launches & 1].
+int nf_launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st);
+size_t nf_train_loss_part_elems(const NfFlowDims& fd, int max_iters);
+
+// nf_factor_kernels.cu
+int nf_launch_factor_logpdf(const nf_factor_desc* descs_dev, int n_desc, int n_groups, const double* x, int64_t n, int D,
+                            double* out, double* per_factor, int device, cudaStream_t st);
+int nf_launch_mixture_weights(const nf_factor_desc* descs_dev, int n_desc, const double* x, int64_t n, int D,
+                              double* partial_dev, int* n_partial, int device, cudaStream_t st);

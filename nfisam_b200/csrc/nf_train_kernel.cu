@@ -1,0 +1,507 @@
+// Persistent clique-flow training kernel: the whole Adam loop of
+// NFiSAM.fit_clique_density_model (src/slam/NFiSAM.py:451-491) in ONE launch.
+//
+// Decomposition.  The training loss -mean(log N(z;0,I) + logdet) (NFiSAM.py:470-472) is a sum over
+// (sample, dim) pairs and the parameters of conditioner i only see dim i's terms (the data x are
+// constants: no gradient flows through the conditioner inputs).  So dim i is trained by its own
+// thread-block CLUSTER (grid = (C, d), cluster = (C,1,1)):
+//   * each warp walks 32-sample tiles: forward + hand-written backward per lane, then the
+//     parameter-gradient outer products are reduced over the tile through a shared-memory staging
+//     tile with lane-owned accumulators that stay in registers across tiles;
+//   * per iteration the C blocks of a cluster reduce their gradients over distributed shared memory,
+//     each block applies the fused Adam update to its slice of the conditioner and broadcasts the
+//     new weights back over DSMEM: two cluster barriers per iteration, no grid-wide barrier and no
+//     host round trip;
+//   * clusters never wait for each other inside a launch.  One launch runs one early-stop window
+//     (`average_window` iterations); the windows are enqueued back to back on the stream and every
+//     block evaluates the reference's windowed stopping rule on the finished window's losses when
+//     the next launch starts (a double-buffered control record carries loss_avg / the stop flag), so
+//     the loop needs neither a cooperative launch nor a host synchronisation.
+// All reductions run in a fixed order: results are bitwise reproducible run to run.
+#include <cooperative_groups.h>
+
+#include "nf_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr float HALF_LOG_2PI = 0.91893853320467274178f;
+
+// d f / d out for one (sample, dim), f = -z^2/2 + logdet; `o` holds the conditioner outputs on
+// entry and gscale * df/dout on exit.  Returns f.
+template <int K>
+__device__ __forceinline__ float nf_rqs_grad(float (&o)[((3 * K - 1) + 3) & ~3], float B, float x, float gscale) {
+    constexpr int P = 3 * K - 1;
+    constexpr int PP = (P + 3) & ~3;
+    if (!(x >= -B && x <= B)) {
+#pragma unroll
+        for (int p = 0; p < PP; ++p) o[p] = 0.0f;
+        return -0.5f * x * x;
+    }
+    float cw[K + 1], chh[K + 1], pw[K], ph[K];
+    nf_knots<K, true>(o, B, cw, pw);
+    const int bin = nf_search<K>(cw, x);
+    float xk, xk1, yk, yk1, a, bq, uk, uk1;
+    nf_select2<K>(cw, bin, xk, xk1);
+    nf_knots<K, true>(o + K, B, chh, ph);
+    nf_select2<K>(chh, bin, yk, yk1);
+    nf_derivs<K>(o + 2 * K, bin, a, bq, uk, uk1);
+    const float wk = xk1 - xk, hk = yk1 - yk;
+    const float rw = 1.0f / wk;
+    const float s = hk / wk;
+    const float t = (x - xk) / wk, u = t * (1.0f - t), omt = 1.0f - t;
+    const float N = hk * (s * t * t + a * u);
+    const float Dn = s + (a + bq - 2.0f * s) * u;
+    const float Q = bq * t * t + 2.0f * s * u + a * omt * omt;
+    const float M = s * s * Q;
+    const float rD = 1.0f / Dn;
+    const float z = yk + N * rD;
+    const float f = -0.5f * z * z + logf(M) - 2.0f * logf(Dn);
+    const float cN = -z * rD, cD = z * N * rD * rD - 2.0f * rD, cM = 1.0f / M;
+    const float N_s = hk * t * t, N_a = hk * u, N_t = hk * (2.0f * s * t + a * (1.0f - 2.0f * t)), N_h = s * t * t + a * u;
+    const float D_s = 1.0f - 2.0f * u, D_t = (a + bq - 2.0f * s) * (1.0f - 2.0f * t);
+    const float M_s = 2.0f * s * Q + 2.0f * s * s * u, M_a = s * s * omt * omt, M_b = s * s * t * t;
+    const float M_t = s * s * (2.0f * bq * t + 2.0f * s * (1.0f - 2.0f * t) - 2.0f * a * omt);
+    const float f_s = cN * N_s + cD * D_s + cM * M_s;
+    const float f_a = cN * N_a + cD * u + cM * M_a;
+    const float f_b = cD * u + cM * M_b;
+    const float f_t = cN * N_t + cD * D_t + cM * M_t;
+    const float g_hk = cN * N_h + f_s * rw;
+    const float g_wk = -(f_s * s + f_t * t) * rw;
+    const float g_xk = -f_t * rw;
+    const float g_yk = -z;
+    const float c1 = (float)(1.0 - 1e-3 * (double)K) * gscale;
+    const float twoB = 2.0f * B;
+    {   // widths: knots bin (if interior) and bin+1 (if interior) receive gradient
+        const float A = bin >= 1 ? twoB * (g_xk - g_wk) : 0.0f;
+        const float Bc = bin + 1 <= K - 1 ? twoB * g_wk : 0.0f;
+        float dot = 0.0f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float gw = (j < bin ? A : 0.0f) + (j <= bin ? Bc : 0.0f);
+            dot = fmaf(pw[j], gw, dot);
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float gw = (j < bin ? A : 0.0f) + (j <= bin ? Bc : 0.0f);
+            o[j] = c1 * pw[j] * (gw - dot);
+        }
+    }
+    {   // heights
+        const float A = bin >= 1 ? twoB * (g_yk - g_hk) : 0.0f;
+        const float Bc = bin + 1 <= K - 1 ? twoB * g_hk : 0.0f;
+        float dot = 0.0f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float gh = (j < bin ? A : 0.0f) + (j <= bin ? Bc : 0.0f);
+            dot = fmaf(ph[j], gh, dot);
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float gh = (j < bin ? A : 0.0f) + (j <= bin ? Bc : 0.0f);
+            o[K + j] = c1 * ph[j] * (gh - dot);
+        }
+    }
+    const float ga = gscale * f_a * nf_sigmoid_sp(uk);
+    const float gb = gscale * f_b * nf_sigmoid_sp(uk1);
+#pragma unroll
+    for (int k = 1; k < K; ++k) o[2 * K + k - 1] = (bin == k ? ga : 0.0f) + (bin + 1 == k ? gb : 0.0f);
+#pragma unroll
+    for (int p = P; p < PP; ++p) o[p] = 0.0f;
+    return f;
+}
+
+template <int K, int H, int W>
+__global__ void __launch_bounds__(W * 32)
+nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_begin, int it_end, int launch_idx) {
+    constexpr int P = 3 * K - 1;
+    constexpr int PP = (P + 3) & ~3;
+    constexpr int NC3 = (PP + 31) / 32;            // W3 columns owned per lane
+    constexpr int N2 = H * H / 32;                 // W2 entries owned per lane
+    constexpr int LG = 32 / H;                     // lane groups (distinct k per pass)
+    constexpr int M1 = (NF_MAX_DIM + LG - 1) / LG; // W1 entries owned per lane (upper bound)
+    constexpr int STG = PP + 4 * H;                // staging row: gout | h2 | g2 | h1 | g1
+    static_assert(H % 4 == 0 && 32 % H == 0, "hidden width must divide 32 and be a multiple of 4");
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int r = (int)cluster.block_rank();
+    const int i = blockIdx.y;                      // the dim / conditioner this cluster trains
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = W * 32;
+
+    // local offsets inside block i
+    const int oW1 = 0, ob1 = i * H, oW2 = ob1 + H, ob2 = oW2 + H * H, oW3 = ob2 + H, ob3 = i == 0 ? 0 : oW3 + H * PP;
+    const int G = nf_block_size(i, H, PP);
+    const int goff = nf_block_off(i, H, PP);       // offset of block i in the packed vector
+    const int Gs = (G + C - 1) / C;                // slice per cluster rank
+    const int p_lo = r * Gs, p_hi = min(G, p_lo + Gs);
+    const int dp = (i + 1) | 1;
+
+    extern __shared__ __align__(16) float smem[];
+    float* s_w = smem;                              // [G]  (G is a multiple of 4)
+    float* s_g = s_w + G;                           // [G]
+    float* s_wg = s_g + G;                          // [W][G]
+    float* s_m = s_wg + W * G;                      // [Gs]
+    float* s_v = s_m + Gs;                          // [Gs]
+    float* s_loss = s_v + Gs;                       // [W]
+    float* s_misc = s_loss + W;                     // [8]
+    float* s_stage = s_misc + 8;                    // [W][32][STG]
+    s_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_stage) + 15) & ~uintptr_t(15));
+    float* s_x = s_stage + W * 32 * STG;            // [W][mt_res][32][dp]
+
+    const int64_t n = a.n;
+    const int64_t ntiles = (n + 31) / 32;
+    const int TW = C * W;
+    const int gw = r * W + warp;
+    float* stage = s_stage + warp * 32 * STG;
+    float* xslots = s_x + (size_t)warp * mt_res * 32 * dp;
+
+    // ---------------- early stop: windowed relative loss change (NFiSAM.py:481-491) ----------------
+    // Evaluated on the window the previous launch finished; identical in every block.
+    {
+        const NfTrainCtrl cin = a.ctrl[launch_idx & 1];
+        NfTrainCtrl cout = cin;
+        if (!cin.stop && launch_idx > 0 && a.average_window > 0 && !a.grad_only && it_begin % a.average_window == 0) {
+            float wsum = 0.0f;
+            const int t0 = it_begin - a.average_window;
+            for (int tt = 0; tt < a.average_window; ++tt) {
+                float li = 0.0f;                 // iteration loss: dims summed in ascending order
+                for (int j = 0; j < d; ++j) li += __ldcg(a.loss_part + (size_t)(t0 + tt) * d + j);
+                wsum += li;
+            }
+            const float nw = wsum / (float)a.average_window;
+            if (!(nw == nw) || fabsf(nw) > 3.0e38f) {
+                cout.stop = 1; cout.status = 1;
+            } else if (cin.have_avg && cin.loss_avg != 0.0f) {
+                if (fabsf(1.0f - nw / cin.loss_avg) < a.loss_delta_tol) cout.stop = 1;
+            }
+            cout.loss_avg = nw;
+            cout.have_avg = 1;
+            if (cout.stop) cout.iters_run = it_begin;
+        }
+        if (i == 0 && r == 0 && threadIdx.x == 0) a.ctrl[(launch_idx + 1) & 1] = cout;
+        if (cout.stop) return;
+    }
+    for (int p = threadIdx.x; p < G; p += T) s_w[p] = a.pk[goff + p];
+    for (int p = p_lo + threadIdx.x; p < p_hi; p += T) {
+        s_m[p - p_lo] = a.adam_m[goff + p];
+        s_v[p - p_lo] = a.adam_v[goff + p];
+    }
+    auto load_slot = [&](float* slot, int64_t tile) {
+        const int64_t s0 = tile * 32;
+        const int cols = i + 1;
+        for (int t = lane; t < 32 * cols; t += 32) {
+            const int rr = t / cols, c = t - rr * cols;
+            const int64_t s = s0 + rr;
+            slot[rr * dp + c] = s < n ? a.data[s * d + c] : 0.0f;
+        }
+    };
+    if (resident) {
+        int m = 0;
+        for (int64_t tile = gw; tile < ntiles; tile += TW, ++m) load_slot(xslots + (size_t)m * 32 * dp, tile);
+    }
+    __syncthreads();
+
+    const float inv_n = 1.0f / (float)n;
+    const int adam0 = a.step0 + it_begin;                       // Adam steps taken before this launch
+    double b1t = pow((double)a.beta1, (double)adam0), b2t = pow((double)a.beta2, (double)adam0);
+
+    for (int it = it_begin; it < it_end; ++it) {
+        // ---------------- local gradient over this warp's tiles ----------------
+        float acc3[NC3][H], accb3[NC3], acc2[N2], accb2 = 0.0f, acc1[M1], accb1 = 0.0f, floss = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NC3; ++c) {
+            accb3[c] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < H; ++k) acc3[c][k] = 0.0f;
+        }
+#pragma unroll
+        for (int m = 0; m < N2; ++m) acc2[m] = 0.0f;
+#pragma unroll
+        for (int m = 0; m < M1; ++m) acc1[m] = 0.0f;
+
+        int mslot = 0;
+        for (int64_t tile = gw; tile < ntiles; tile += TW, ++mslot) {
+            float* slot = resident ? xslots + (size_t)mslot * 32 * dp : xslots;
+            if (!resident) { __syncwarp(); load_slot(slot, tile); __syncwarp(); }
+            const int64_t s = tile * 32 + lane;
+            const bool valid = s < n;
+            const float* xrow = slot + lane * dp;
+            float out[PP];
+            float h1[H], h2[H];
+            if (i == 0) {
+#pragma unroll
+                for (int p = 0; p < PP; ++p) out[p] = s_w[p];
+            } else {
+                nf_mlp_hidden<H>(s_w, i, xrow, h1, h2);
+                nf_mlp_out<H, PP>(s_w, i, h2, out);
+            }
+            float f = nf_rqs_grad<K>(out, B, xrow[i], -inv_n);
+            if (!valid) {
+                f = 0.0f;
+#pragma unroll
+                for (int p = 0; p < PP; ++p) out[p] = 0.0f;
+            } else {
+                f -= HALF_LOG_2PI;
+            }
+            floss += f;
+            float* row = stage + lane * STG;
+#pragma unroll
+            for (int p = 0; p < PP; p += 4)
+                *reinterpret_cast<float4*>(row + p) = make_float4(out[p], out[p + 1], out[p + 2], out[p + 3]);
+            if (i > 0) {
+                float g2[H], g1[H];
+                const float* W3t = s_w + oW3;
+                const float* W2t = s_w + oW2;
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    const float4* wr = reinterpret_cast<const float4*>(W3t + k * PP);
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int p4 = 0; p4 < PP / 4; ++p4) {
+                        const float4 w4 = wr[p4];
+                        acc = fmaf(w4.x, out[4 * p4], acc);
+                        acc = fmaf(w4.y, out[4 * p4 + 1], acc);
+                        acc = fmaf(w4.z, out[4 * p4 + 2], acc);
+                        acc = fmaf(w4.w, out[4 * p4 + 3], acc);
+                    }
+                    g2[k] = acc * (1.0f - h2[k] * h2[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    const float4* wr = reinterpret_cast<const float4*>(W2t + k * H);
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j4 = 0; j4 < H / 4; ++j4) {
+                        const float4 w4 = wr[j4];
+                        acc = fmaf(w4.x, g2[4 * j4], acc);
+                        acc = fmaf(w4.y, g2[4 * j4 + 1], acc);
+                        acc = fmaf(w4.z, g2[4 * j4 + 2], acc);
+                        acc = fmaf(w4.w, g2[4 * j4 + 3], acc);
+                    }
+                    g1[k] = acc * (1.0f - h1[k] * h1[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < H; k += 4) {
+                    *reinterpret_cast<float4*>(row + PP + k) = make_float4(h2[k], h2[k + 1], h2[k + 2], h2[k + 3]);
+                    *reinterpret_cast<float4*>(row + PP + H + k) = make_float4(g2[k], g2[k + 1], g2[k + 2], g2[k + 3]);
+                    *reinterpret_cast<float4*>(row + PP + 2 * H + k) = make_float4(h1[k], h1[k + 1], h1[k + 2], h1[k + 3]);
+                    *reinterpret_cast<float4*>(row + PP + 3 * H + k) = make_float4(g1[k], g1[k + 1], g1[k + 2], g1[k + 3]);
+                }
+            }
+            __syncwarp();
+            // ------------- outer products over the tile, lane-owned accumulators -------------
+            const int jl = lane % H, kg = lane / H;
+            if (i == 0) {
+                for (int ss = 0; ss < 32; ++ss) {
+                    const float* rw_ = stage + ss * STG;
+#pragma unroll
+                    for (int c = 0; c < NC3; ++c) {
+                        const int p = lane + 32 * c;
+                        if (p < PP) accb3[c] += rw_[p];
+                    }
+                }
+            } else {
+                for (int ss = 0; ss < 32; ++ss) {
+                    const float* rw_ = stage + ss * STG;
+                    float hv[H];
+#pragma unroll
+                    for (int k = 0; k < H; k += 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(rw_ + PP + k);
+                        hv[k] = v.x; hv[k + 1] = v.y; hv[k + 2] = v.z; hv[k + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int c = 0; c < NC3; ++c) {
+                        const int p = lane + 32 * c;
+                        if (p < PP) {
+                            const float g = rw_[p];
+                            accb3[c] += g;
+#pragma unroll
+                            for (int k = 0; k < H; ++k) acc3[c][k] = fmaf(g, hv[k], acc3[c][k]);
+                        }
+                    }
+                    const float g2j = rw_[PP + H + jl];
+                    accb2 += g2j;
+#pragma unroll
+                    for (int m = 0; m < N2; ++m) acc2[m] = fmaf(g2j, rw_[PP + 2 * H + kg + LG * m], acc2[m]);
+                    const float g1j = rw_[PP + 3 * H + jl];
+                    accb1 += g1j;
+                    const float* xr = slot + ss * dp;
+#pragma unroll
+                    for (int m = 0; m < M1; ++m) {
+                        const int k = kg + LG * m;
+                        if (k < i) acc1[m] = fmaf(g1j, xr[k], acc1[m]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---------------- per-warp partials -> shared ----------------
+        {
+            float* wg = s_wg + warp * G;
+#pragma unroll
+            for (int c = 0; c < NC3; ++c) {
+                const int p = lane + 32 * c;
+                if (p < PP) {
+                    wg[ob3 + p] = accb3[c];
+                    if (i > 0) {
+#pragma unroll
+                        for (int k = 0; k < H; ++k) wg[oW3 + k * PP + p] = acc3[c][k];
+                    }
+                }
+            }
+            if (i > 0) {
+                const int jl = lane % H, kg = lane / H;
+#pragma unroll
+                for (int m = 0; m < N2; ++m) wg[oW2 + (kg + LG * m) * H + jl] = acc2[m];
+#pragma unroll
+                for (int m = 0; m < M1; ++m) {
+                    const int k = kg + LG * m;
+                    if (k < i) wg[oW1 + k * H + jl] = acc1[m];
+                }
+                if (lane < H) { wg[ob2 + lane] = accb2; wg[ob1 + lane] = accb1; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) floss += __shfl_xor_sync(0xffffffffu, floss, off);
+            if (lane == 0) s_loss[warp] = floss;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < G; p += T) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int w = 0; w < W; ++w) acc += s_wg[w * G + p];
+            s_g[p] = acc;
+        }
+        if (threadIdx.x == 0) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int w = 0; w < W; ++w) acc += s_loss[w];
+            s_misc[0] = acc;
+        }
+        cluster.sync();                                           // (A) every block's s_g / loss ready
+        // ---------------- slice reduce over the cluster + fused Adam ----------------
+        b1t *= (double)a.beta1;
+        b2t *= (double)a.beta2;
+        const float step = (float)((double)a.lr / (1.0 - b1t));
+        const float bc2s = (float)sqrt(1.0 - b2t);
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += T) {
+            float g = 0.0f;
+            for (int q = 0; q < C; ++q) g += cluster.map_shared_rank(s_g, q)[p];
+            if (a.grad_only) {
+                a.grad_out[goff + p] = g;
+            } else {
+                float m = s_m[p - p_lo], v = s_v[p - p_lo];
+                m = m + (g - m) * (1.0f - a.beta1);
+                v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+                s_m[p - p_lo] = m;
+                s_v[p - p_lo] = v;
+                const float den = sqrtf(v) / bc2s + a.eps;
+                const float th = s_w[p] - step * (m / den);
+                for (int q = 0; q < C; ++q) cluster.map_shared_rank(s_w, q)[p] = th;
+            }
+        }
+        if (r == 0 && threadIdx.x == 0) {
+            float acc = 0.0f;
+            for (int q = 0; q < C; ++q) acc += cluster.map_shared_rank(s_misc, q)[0];
+            a.loss_part[(size_t)it * d + i] = -acc * inv_n;
+        }
+        cluster.sync();                                           // (B) new weights visible, s_g reusable
+    }
+    // ---------------- write back ----------------
+    if (!a.grad_only) {
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += T) {
+            a.pk[goff + p] = s_w[p];
+            a.adam_m[goff + p] = s_m[p - p_lo];
+            a.adam_v[goff + p] = s_v[p - p_lo];
+        }
+    }
+}
+
+template <int K, int H, int W>
+size_t train_smem_bytes(int i_max, int C, int mt_res) {
+    constexpr int PP = ((3 * K - 1) + 3) & ~3;
+    constexpr int STG = PP + 4 * H;
+    const int G = nf_block_size(i_max, H, PP);
+    const int Gs = (G + C - 1) / C;
+    const int dp = (i_max + 1) | 1;
+    size_t fl = (size_t)G * (2 + W) + 2 * (size_t)Gs + W + 8 + 4 /*align slack*/ + (size_t)W * 32 * STG +
+                (size_t)W * mt_res * 32 * dp;
+    return fl * sizeof(float);
+}
+
+// Enqueues the whole training loop: one launch per early-stop window, no host synchronisation.
+template <int K, int H, int W>
+int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st, bool* fits) {
+    *fits = true;
+    const int d = fd.d;
+    const int64_t ntiles = (a.n + 31) / 32;
+    // cluster size: enough blocks per dim that a warp owns about one tile, max 8 (portable limit)
+    int C = 1;
+    while (C < 8 && (int64_t)C * W < ntiles) C *= 2;
+    auto kern = nf_train_kernel<K, H, W>;
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const int window = a.grad_only ? 1 : (a.average_window > 0 ? a.average_window : 64);
+    for (;; C /= 2) {
+        const int TW = C * W;
+        int mt = (int)((ntiles + TW - 1) / TW);
+        if (mt < 1) mt = 1;
+        int resident = 1;
+        size_t smem = train_smem_bytes<K, H, W>(d - 1, C, mt);
+        if (smem > 100 * 1024) { resident = 0; mt = 1; smem = train_smem_bytes<K, H, W>(d - 1, C, 1); }
+        if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C, d, 1);
+        cfg.blockDim = dim3(W * 32, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attrs[1];
+        attrs[0].id = cudaLaunchAttributeClusterDimension;
+        attrs[0].val.clusterDim.x = C;
+        attrs[0].val.clusterDim.y = 1;
+        attrs[0].val.clusterDim.z = 1;
+        cfg.attrs = attrs;
+        cfg.numAttrs = 1;
+        int launch_idx = 0;
+        bool retry = false;
+        for (int it0 = 0; it0 < a.max_iters; it0 += window, ++launch_idx) {
+            const int it1 = it0 + window < a.max_iters ? it0 + window : a.max_iters;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                if (launch_idx > 0 || C == 1) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel)");
+                retry = true;                       // cluster shape not schedulable: halve it
+                break;
+            }
+            nf_count_launch();
+        }
+        if (!retry) return launch_idx;              // number of launches enqueued (>= 1)
+    }
+}
+
+template <int K, int H>
+int launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st) {
+    bool fits = false;
+    int rc = launch_train_w<K, H, 8>(fd, a, device, st, &fits);
+    if (rc < 0 || fits) return rc;
+    rc = launch_train_w<K, H, 4>(fd, a, device, st, &fits);
+    if (rc < 0 || fits) return rc;
+    return nf_set_error(NF_ERR_UNSUPPORTED, "training kernel does not fit on the device for this (dim, K, hidden)");
+}
+
+}  // namespace
+
+size_t nf_train_loss_part_elems(const NfFlowDims& fd, int max_iters) { return (size_t)max_iters * fd.d; }
+
+int nf_launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st) {
+    if (a.n <= 0 || a.max_iters <= 0) return nf_set_error(NF_ERR_BAD_ARG, "empty training set or no iterations");
+    if (a.n_val > 0) return nf_set_error(NF_ERR_UNSUPPORTED, "validation-set early stop is not implemented yet");
+#define NF_CASE(KK, HH) \
+    if (fd.K == KK && fd.H == HH) return launch_train<KK, HH>(fd, a, device, st);
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
+}

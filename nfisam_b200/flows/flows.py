@@ -1,0 +1,255 @@
+"""Drop-in for the reference's flow module (src/flows/flows.py): same class names, constructor
+arguments, parameter names / state_dict layout and method signatures; the arithmetic runs in the
+fused sm_100a kernels of libnfisam_b200.so.
+
+    FCNN      src/flows/flows.py:26-41   (host-side parameter container here)
+    NSF_AR    src/flows/flows.py:43-137  forward / inverse / inverse_given_separator
+
+The nn.Parameters are a host-side mirror: they are pushed to the device handle whenever they
+change (load_state_dict, manual edits) and pulled back after on-device training.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.init as init
+
+from .. import _lib
+
+
+class FCNN(nn.Module):
+    """Linear(in, H) - tanh - Linear(H, H) - tanh - Linear(H, out): parameter container only.
+    The conditioners are evaluated inside the fused CUDA kernels, never through this module."""
+
+    def __init__(self, in_dim, out_dim, hidden_dim):
+        super().__init__()
+        self.network = nn.Sequential(
+            nn.Linear(in_dim, hidden_dim),
+            nn.Tanh(),
+            nn.Linear(hidden_dim, hidden_dim),
+            nn.Tanh(),
+            nn.Linear(hidden_dim, out_dim),
+        )
+
+    def forward(self, x):
+        raise RuntimeError("nfisam_b200.FCNN is a parameter container; conditioners run inside the CUDA kernels")
+
+
+def _cuda_index(device):
+    if device is None:
+        return torch.cuda.current_device() if torch.cuda.is_available() else 0
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError("nfisam_b200 flows compute on CUDA devices only")
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+class NSF_AR(nn.Module):
+    """Neural spline flow, auto-regressive [Durkan et al. 2019] -- reference signature
+    ``NSF_AR(dim, K=5, B=5.0, hidden_dim=8, base_network=FCNN)``.
+
+    Extra keyword arguments (not in the reference):
+      device            CUDA device the flow computes on (default: current device)
+      reference_layout  True (default): ``forward`` returns exactly what the reference returns,
+                        including its dim-major output permutation for n > 1;
+                        False: mathematically per-sample rows.
+    """
+
+    def __init__(self, dim, K=5, B=5.0, hidden_dim=8, base_network=FCNN, device=None, reference_layout=True):
+        super().__init__()
+        self.dim = dim
+        self.K = K
+        self.B = B
+        self.hidden_dim = hidden_dim
+        self.reference_layout = reference_layout
+        self.layers = nn.ModuleList()
+        self.init_param = nn.Parameter(torch.Tensor(3 * K - 1))
+        for i in range(1, dim):
+            self.layers += [base_network(i, 3 * K - 1, hidden_dim)]
+        self.reset_parameters()
+        self._device_index = device
+        self._h = None
+        self._synced = None
+
+    def reset_parameters(self):
+        init.uniform_(self.init_param, -1 / 2, 1 / 2)
+
+    # ------------------------------------------------------------------ handle / parameter mirror
+    def _ordered_params(self):
+        ps = [self.init_param]
+        for layer in self.layers:
+            for j in (0, 2, 4):
+                ps.append(layer.network[j].weight)
+                ps.append(layer.network[j].bias)
+        return ps
+
+    def flat_parameters(self) -> np.ndarray:
+        """state_dict order, float32 (the order of the C ABI's parameter vector)."""
+        return np.concatenate([p.detach().cpu().numpy().astype(np.float32).ravel() for p in self._ordered_params()])
+
+    def load_flat_parameters(self, theta):
+        theta = np.asarray(theta, dtype=np.float32)
+        off = 0
+        with torch.no_grad():
+            for p in self._ordered_params():
+                k = p.numel()
+                p.copy_(torch.from_numpy(theta[off:off + k].reshape(tuple(p.shape)).copy()))
+                off += k
+        assert off == theta.size
+
+    @property
+    def device_index(self):
+        if self._device_index is None or not isinstance(self._device_index, int):
+            self._device_index = _cuda_index(self._device_index)
+        return self._device_index
+
+    def handle(self):
+        lib = _lib.load()
+        if self._h is None:
+            _lib.require_device()
+            h = ctypes.c_void_p()
+            _lib.check(lib.nfisam_flow_create(int(self.dim), int(self.K), int(self.hidden_dim), float(self.B),
+                                              int(self.device_index), ctypes.byref(h)))
+            self._h = h
+            self._synced = None
+        ver = tuple(p._version for p in self._ordered_params())
+        if ver != self._synced:
+            theta = self.flat_parameters()
+            _lib.check(lib.nfisam_flow_set_params(self._h, theta.ctypes.data_as(ctypes.c_void_p), theta.size))
+            self._synced = ver
+        return self._h
+
+    def pull_parameters(self):
+        """Copy the device parameters (e.g. after on-device training) back into the nn.Parameters."""
+        lib = _lib.load()
+        n = sum(p.numel() for p in self._ordered_params())
+        theta = np.empty(n, np.float32)
+        _lib.check(lib.nfisam_flow_get_params(self._h, theta.ctypes.data_as(ctypes.c_void_p), n))
+        self.load_flat_parameters(theta)
+        self._synced = tuple(p._version for p in self._ordered_params())
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.load().nfisam_flow_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _dev(self):
+        return torch.device("cuda", self.device_index)
+
+    def _in(self, t):
+        """float32, contiguous, on the flow's device."""
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.asarray(t))
+        return t.detach().to(device=self._dev(), dtype=torch.float32).contiguous()
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self._dev()).cuda_stream)
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, x: torch.Tensor, reference_layout=None):
+        """(z, log_det) like src/flows/flows.py:65-93; x may have fewer columns than dim (prefix)."""
+        ref = self.reference_layout if reference_layout is None else reference_layout
+        lib = _lib.load()
+        h = self.handle()
+        src_device = x.device if torch.is_tensor(x) else torch.device("cpu")
+        xd = self._in(x)
+        n, d_in = xd.shape
+        z = torch.empty((n, d_in), dtype=torch.float32, device=xd.device)
+        ld = torch.empty((n,), dtype=torch.float32, device=xd.device)
+        ws = torch.empty((n * d_in,), dtype=torch.float32, device=xd.device) if ref else None
+        _lib.check(lib.nfisam_flow_forward(h, xd.data_ptr(), n, d_in, z.data_ptr(), ld.data_ptr(), 1 if ref else 0,
+                                           ws.data_ptr() if ref else None, self._stream()))
+        return z.to(src_device), ld.to(src_device)
+
+    def log_prob(self, x: torch.Tensor):
+        """Per-sample log N(z; 0, I) + log|det dz/dx| of the first x.shape[1] dims."""
+        lib = _lib.load()
+        h = self.handle()
+        src_device = x.device if torch.is_tensor(x) else torch.device("cpu")
+        xd = self._in(x)
+        n, d_in = xd.shape
+        lp = torch.empty((n,), dtype=torch.float32, device=xd.device)
+        _lib.check(lib.nfisam_flow_log_prob(h, xd.data_ptr(), n, d_in, lp.data_ptr(), self._stream()))
+        return lp.to(src_device)
+
+    def _inverse(self, z, x_s, norm=None, want_logdet=False):
+        lib = _lib.load()
+        h = self.handle()
+        src_device = z.device if torch.is_tensor(z) else torch.device("cpu")
+        zd = self._in(z)
+        n, f = zd.shape
+        sep = 0 if x_s is None else int(x_s.shape[1])
+        if sep + f != self.dim:
+            raise ValueError(f"separator dim {sep} + latent dim {f} != flow dim {self.dim}")
+        xs = self._in(x_s) if sep else None
+        out = torch.empty((n, f), dtype=torch.float32, device=zd.device)
+        ld = torch.empty((n,), dtype=torch.float32, device=zd.device) if want_logdet else None
+        aff = None
+        keep = None
+        if norm is not None:
+            mean, std, circ = norm
+            keep = (self._in(mean), self._in(std),
+                    torch.as_tensor(np.asarray(circ, dtype=np.uint8)).to(self._dev()).contiguous())
+            aff = _lib.nf_affine(keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr())
+        _lib.check(lib.nfisam_flow_inverse(h, zd.data_ptr(), xs.data_ptr() if sep else None, n, sep, out.data_ptr(),
+                                           ld.data_ptr() if want_logdet else None,
+                                           ctypes.byref(aff) if aff is not None else None, self._stream()))
+        bad = ctypes.c_int64(0)
+        _lib.check(lib.nfisam_flow_pop_bad_count(h, self._stream(), ctypes.byref(bad)))
+        if bad.value:
+            # the reference asserts (src/flows/utils.py:133)
+            raise AssertionError(f"negative discriminant in the inverse spline for {bad.value} samples")
+        return out.to(src_device), (ld.to(src_device) if want_logdet else None)
+
+    def inverse(self, z):
+        """(x, log_det) like src/flows/flows.py:95-113."""
+        return self._inverse(z, None, want_logdet=True)
+
+    def inverse_given_separator(self, z, x_s, norm=None):
+        """Frontal block given the (normalised) separator columns, src/flows/flows.py:115-137.
+        norm = (mean, std, circular) fuses the solver's normalise / unnormalise into the kernel."""
+        return self._inverse(z, x_s, norm=norm)[0]
+
+    # ------------------------------------------------------------------ training on device
+    def fit(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
+            reset_optimizer=True, pull=True):
+        """Full-batch Adam on -mean(log_prob) with the reference's windowed early stop
+        (src/slam/NFiSAM.py:451-491), entirely on the device.  Returns (loss_history, iters_run);
+        loss_history has `iters` entries, zeros after the stop like the reference's iter_loss."""
+        lib = _lib.load()
+        h = self.handle()
+        xd = self._in(data)
+        n, d = xd.shape
+        if d != self.dim:
+            raise ValueError("training data must have `dim` columns")
+        cfg = _lib.nf_train_cfg(int(iters), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                int(average_window), float(loss_delta_tol), None, 0, 0, 0.0, 1 if reset_optimizer else 0)
+        hist = np.zeros(int(iters), np.float32)
+        ran = ctypes.c_int32(0)
+        _lib.check(lib.nfisam_flow_train(h, xd.data_ptr(), n, ctypes.byref(cfg), hist.ctypes.data_as(ctypes.c_void_p),
+                                         ctypes.byref(ran), self._stream()))
+        if pull:
+            self.pull_parameters()
+        return hist, int(ran.value)
+
+    def loss_and_grad(self, data):
+        """-mean(log_prob) and its gradient (flat, state_dict order) at the current parameters."""
+        lib = _lib.load()
+        h = self.handle()
+        xd = self._in(data)
+        n, d = xd.shape
+        if d != self.dim:
+            raise ValueError("data must have `dim` columns")
+        loss = ctypes.c_float(0.0)
+        g = np.empty(sum(p.numel() for p in self._ordered_params()), np.float32)
+        _lib.check(lib.nfisam_flow_loss_grad(h, xd.data_ptr(), n, ctypes.byref(loss), g.ctypes.data_as(ctypes.c_void_p),
+                                             self._stream()))
+        return float(loss.value), g
+
+
+LOG_2PI = math.log(2.0 * math.pi)

@@ -1,0 +1,303 @@
+"""GPU parity tests of the flow kernels (through the C ABI via the Python drop-ins) against
+ (a) golden vectors produced by the reference's own PyTorch flow (tests/golden/flow_*.npz),
+ (b) the CPU oracle (oracle/nsf_oracle.c) on larger seeded inputs,
+ (c) size-independent properties (forward/inverse round trip, layout permutation, loss invariance).
+
+Tolerances (float32 flow, north_star: 1e-5 relative): max-norm relative error <= 2e-5 plus
+allclose(rtol=1e-5, atol=5e-5) -- see SURVEY.md section 7 "tolerance reality check"."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nsf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _relmax(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def make_flow(c, **kw):
+    from nfisam_b200.flows import NSF_AR
+
+    d, K, H, B = int(c["d"]), int(c["K"]), int(c["H"]), float(c["B"])
+    f = NSF_AR(dim=d, K=K, B=B, hidden_dim=H, **kw)
+    f.load_flat_parameters(c["theta"])
+    return f
+
+
+def test_library_loads_and_sees_device():
+    from nfisam_b200 import _lib
+
+    assert _lib.require_device() >= 1
+
+
+def test_param_roundtrip(flow_cases):
+    for name, c in flow_cases.items():
+        f = make_flow(c)
+        f.handle()
+        f.load_flat_parameters(np.zeros_like(c["theta"]))
+        f._synced = tuple(p._version for p in f._ordered_params())  # pretend in sync, then pull the device copy
+        f.pull_parameters()
+        assert np.array_equal(f.flat_parameters(), c["theta"]), name
+
+
+def test_forward_reference_layout_golden(flow_cases):
+    for name, c in flow_cases.items():
+        f = make_flow(c)
+        z, ld = f.forward(torch.tensor(c["x"]))
+        assert z.shape == c["z_ref"].shape and not z.is_cuda
+        assert _relmax(z.numpy(), c["z_ref"]) < 2e-5, name
+        assert np.allclose(ld.numpy(), c["ld_ref"], rtol=1e-5, atol=1e-4), name
+
+
+def test_forward_per_sample_golden(flow_cases):
+    for name, c in flow_cases.items():
+        f = make_flow(c, reference_layout=False)
+        z, ld = f.forward(torch.tensor(c["x"]).cuda())
+        assert z.is_cuda
+        assert _relmax(z.cpu().numpy(), c["z_col"]) < 2e-5, name
+        assert np.allclose(ld.cpu().numpy(), c["ld_col"], rtol=1e-5, atol=5e-5), name
+
+
+def test_model_forward_golden(flow_cases):
+    from nfisam_b200.flows import CustomMultivariateNormal, NormalizingFlowModel
+
+    for name, c in flow_cases.items():
+        f = make_flow(c)
+        m = NormalizingFlowModel(CustomMultivariateNormal(dim=int(c["d"])), [f])
+        z, plp, ld = m(torch.tensor(c["x"]))
+        assert np.allclose(plp.numpy(), c["prior_lp"], rtol=1e-5, atol=1e-4), name
+        loss = -(plp + ld).double().mean().item()
+        assert abs(loss - float(c["loss"])) < 2e-5 * abs(float(c["loss"])), name
+        lp = m.log_prob(torch.tensor(c["x"]))
+        assert abs(-lp.double().mean().item() - float(c["loss"])) < 2e-5 * abs(float(c["loss"])), name
+
+
+def test_prefix_forward_matches_oracle(flow_cases):
+    c = flow_cases["d11_K9_H8"]
+    f = make_flow(c, reference_layout=False)
+    d, K, H, B = 11, 9, 8, 5.0
+    for d_in in (1, 4, 10):
+        x = c["x"][:, :d_in].copy()
+        z, ld = f.forward(torch.tensor(x))
+        zo, ldo = orc.forward(c["theta"], d, K, H, B, x)
+        assert _relmax(z.numpy(), zo) < 2e-5
+        assert np.allclose(ld.numpy(), ldo, rtol=1e-5, atol=5e-5)
+        lp = f.log_prob(torch.tensor(x))
+        assert np.allclose(lp.numpy(), orc.log_prob(c["theta"], d, K, H, B, x), rtol=1e-5, atol=1e-4)
+
+
+def test_inverse_golden(flow_cases):
+    for name, c in flow_cases.items():
+        f = make_flow(c)
+        x, ld = f.inverse(torch.tensor(c["zin"]))
+        assert _relmax(x.numpy(), c["x_inv"]) < 2e-5, name
+        assert np.allclose(ld.numpy(), c["ld_inv"], rtol=1e-5, atol=1e-4), name
+        sep = int(c["sep"])
+        xc = f.inverse_given_separator(torch.tensor(c["zin_f"]), torch.tensor(c["x_sep"]) if sep else None)
+        assert _relmax(xc.numpy(), c["x_cond"]) < 2e-5, name
+
+
+def test_inverse_fused_normalisation(flow_cases):
+    c = flow_cases["d11_K9_H8"]
+    f = make_flow(c)
+    d, sep = 11, int(c["sep"])
+    rng = np.random.default_rng(3)
+    mean = rng.normal(size=d).astype(np.float32)
+    std = (0.5 + rng.random(d)).astype(np.float32)
+    circ = np.zeros(d, np.uint8)
+    circ[[2, 7]] = 1
+    raw_sep = (c["x_sep"] * std[:sep] + mean[:sep]).astype(np.float32)
+    raw_sep[:, 2] += 2 * np.pi  # wrapped away by the normalisation
+    out = f.inverse_given_separator(torch.tensor(c["zin_f"]), torch.tensor(raw_sep), norm=(mean, std, circ)).numpy()
+    # host restatement of NFiSAM.py:96-118 around the un-normalised kernel
+    def wrap(t):
+        return (t + np.float32(np.pi)) % np.float32(2 * np.pi) - np.float32(np.pi)
+    xs = raw_sep - mean[:sep]
+    xs[:, 2] = wrap(xs[:, 2])
+    xs = xs / std[:sep]
+    plain = f.inverse_given_separator(torch.tensor(c["zin_f"]), torch.tensor(xs)).numpy()
+    exp = plain * std[sep:] + mean[sep:]
+    exp[:, 7 - sep] = wrap(exp[:, 7 - sep])
+    assert np.allclose(out, exp, rtol=1e-5, atol=2e-5)
+
+
+def test_loss_and_gradient_golden(flow_cases):
+    for name, c in flow_cases.items():
+        f = make_flow(c)
+        loss, g = f.loss_and_grad(torch.tensor(c["x"]))
+        assert abs(loss - float(c["loss"])) < 2e-5 * abs(float(c["loss"])), name
+        gr = c["grad"]
+        assert _relmax(g, gr) < 2e-4, (name, _relmax(g, gr))
+        assert np.allclose(g, gr, rtol=1e-3, atol=1e-5 * np.max(np.abs(gr))), name
+
+
+def test_adam_trajectory_golden(flow_cases):
+    for name, c in flow_cases.items():
+        if "adam_loss" not in c:
+            continue
+        f = make_flow(c)
+        steps = len(c["adam_loss"])
+        hist, ran = f.fit(torch.tensor(c["x"]), steps, float(c["adam_lr"]), average_window=0)
+        assert ran == steps
+        assert np.allclose(hist[:10], c["adam_loss"][:10], rtol=2e-5, atol=1e-5), (name, hist, c["adam_loss"])
+        assert np.allclose(hist, c["adam_loss"], rtol=3e-2), (name, hist, c["adam_loss"])
+        assert _relmax(f.flat_parameters(), c["adam_theta"]) < 5e-2, name
+
+
+@pytest.mark.parametrize("n", [1, 7, 33, 2000, 100003])
+def test_ragged_sizes_vs_oracle(flow_cases, n):
+    c = flow_cases["d6_K9_H8"]
+    d, K, H, B = 6, 9, 8, 5.0
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((n, d)) * 1.5).astype(np.float32)
+    x[rng.random((n, d)) < 0.005] *= 8.0
+    f = make_flow(c, reference_layout=False)
+    z, ld = f.forward(torch.tensor(x))
+    zo, ldo = orc.forward(c["theta"], d, K, H, B, x)
+    assert _relmax(z.numpy(), zo) < 2e-5
+    assert np.allclose(ld.numpy(), ldo, rtol=1e-5, atol=5e-5)
+    zin = rng.standard_normal((n, d)).astype(np.float32)
+    xi, ldi = f.inverse(torch.tensor(zin))
+    xo, ldo2, bad = orc.inverse(c["theta"], d, K, H, B, zin)
+    assert bad == 0
+    assert _relmax(xi.numpy(), xo) < 2e-5
+    assert np.allclose(ldi.numpy(), ldo2, rtol=1e-5, atol=1e-4)
+    loss, g = f.loss_and_grad(torch.tensor(x))
+    lo, go = orc.loss_grad(c["theta"], d, K, H, B, x, dtype=np.float64)
+    assert abs(loss - lo) < 2e-5 * abs(lo)
+    assert _relmax(g, go) < 5e-4
+
+
+def test_empty_batch(flow_cases):
+    c = flow_cases["d4_K5_H8"]
+    f = make_flow(c)
+    z, ld = f.forward(torch.zeros((0, 4)))
+    assert z.shape == (0, 4) and ld.shape == (0,)
+
+
+def test_error_vs_f64_oracle_not_worse_than_reference(flow_cases):
+    """kernel-vs-fp64 error <= 2 x (reference fp32-vs-fp64 error) + eps, on the golden inputs."""
+    for name, c in flow_cases.items():
+        d, K, H, B = int(c["d"]), int(c["K"]), int(c["H"]), float(c["B"])
+        z64, ld64 = orc.forward(c["theta"], d, K, H, B, c["x"], dtype=np.float64)
+        f = make_flow(c, reference_layout=False)
+        z, ld = f.forward(torch.tensor(c["x"]))
+        ref_err = max(np.max(np.abs(c["z_col"] - z64)), 1e-7)
+        assert np.max(np.abs(z.numpy() - z64)) <= 2 * ref_err + 2e-6, name
+        ref_err = max(np.max(np.abs(c["ld_col"] - ld64)), 1e-7)
+        assert np.max(np.abs(ld.numpy() - ld64)) <= 2 * ref_err + 1e-5, name
+
+
+def test_round_trip_large():
+    """1e6 samples, d=12: inverse(forward(x)) == x and log-dets cancel (size-independent property)."""
+    from nfisam_b200.flows import NSF_AR
+
+    torch.manual_seed(0)
+    f = NSF_AR(dim=12, K=9, hidden_dim=8, reference_layout=False)
+    n = 1_000_000
+    x = torch.randn(n, 12, device="cuda") * 1.2
+    z, ld = f.forward(x)
+    xb, ldi = f.inverse(z)
+    inside = (x.abs() < 4.99).all(1) & (z.abs() < 4.99).all(1)
+    assert inside.float().mean() > 0.9
+    assert (xb - x)[inside].abs().max().item() < 2e-4
+    assert (ld + ldi)[inside].abs().max().item() < 2e-3
+    # layout permutation property: reference layout is the transpose buffer of the per-sample result
+    zr, ldr = f.forward(x[:1000], reference_layout=True)
+    assert torch.equal(zr, z[:1000].t().contiguous().view(1000, 12))
+    assert abs(ldr.double().sum().item() - ld[:1000].double().sum().item()) < 1e-2
+
+
+def test_host_buffer_api_matches_device_api(flow_cases):
+    import ctypes
+
+    from nfisam_b200 import _lib
+
+    c = flow_cases["d11_K9_H8"]
+    f = make_flow(c, reference_layout=False)
+    n = 300_001
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n, 11)).astype(np.float32)
+    lp_dev = f.log_prob(torch.tensor(x)).numpy()
+    xh = torch.tensor(x).pin_memory()
+    out = torch.empty(n).pin_memory()
+    _lib.check(_lib.load().nfisam_flow_log_prob_host(f.handle(), xh.data_ptr(), n, 11, out.data_ptr()))
+    assert np.array_equal(out.numpy(), lp_dev)
+    z = rng.standard_normal((n, 6)).astype(np.float32)
+    xs = x[:, :5].copy()
+    ref = f.inverse_given_separator(torch.tensor(z), torch.tensor(xs)).numpy()
+    o2 = np.empty((n, 6), np.float32)
+    _lib.check(_lib.load().nfisam_flow_inverse_host(f.handle(), z.ctypes.data_as(ctypes.c_void_p),
+                                                    xs.ctypes.data_as(ctypes.c_void_p), n, 5,
+                                                    o2.ctypes.data_as(ctypes.c_void_p), None, None, None))
+    assert np.array_equal(o2, ref)
+
+
+def test_training_matches_oracle_and_early_stop():
+    """200 Adam iterations on a 2000-sample banana: loss curve tracks the CPU oracle; the windowed
+    early stop fires at the same iteration for a plateaued run."""
+    from nfisam_b200.flows import NSF_AR
+
+    rng = np.random.default_rng(5)
+    d, K, H = 5, 9, 8
+    x = rng.standard_normal((2000, d)).astype(np.float32)
+    x[:, 1] = 0.5 * x[:, 1] + x[:, 0] ** 2 - 1.0
+    x = (x - x.mean(0)) / x.std(0)
+    torch.manual_seed(1)
+    f = NSF_AR(dim=d, K=K, hidden_dim=H)
+    theta0 = f.flat_parameters()
+    hist, ran = f.fit(torch.tensor(x), 200, 0.01, average_window=0)
+    th_o, hist_o, it_o = orc.train(theta0, d, K, H, 5.0, x, 200, 0.01, average_window=0)
+    assert ran == 200 and it_o == 200
+    assert np.allclose(hist[:20], hist_o[:20], rtol=1e-5)
+    assert np.allclose(hist, hist_o, rtol=5e-3), np.max(np.abs(hist - hist_o))
+    assert hist[-1] < hist[0] - 0.1
+    # continuing training keeps the Adam state (bias correction continues)
+    f2 = NSF_AR(dim=d, K=K, hidden_dim=H)
+    f2.load_flat_parameters(theta0)
+    h1, _ = f2.fit(torch.tensor(x), 100, 0.01, average_window=0)
+    h2, _ = f2.fit(torch.tensor(x), 100, 0.01, average_window=0, reset_optimizer=False)
+    assert np.allclose(np.concatenate([h1, h2]), hist, rtol=1e-4)
+    # early stop: tiny lr -> second window mean within tolerance of the first
+    f3 = NSF_AR(dim=d, K=K, hidden_dim=H)
+    f3.load_flat_parameters(theta0)
+    h3, ran3 = f3.fit(torch.tensor(x), 400, 1e-6, average_window=10, loss_delta_tol=1e-2)
+    _, h3o, ran3o = orc.train(theta0, d, K, H, 5.0, x, 400, 1e-6, average_window=10, loss_delta_tol=1e-2)
+    assert ran3 == ran3o == 20
+    assert np.all(h3[20:] == 0)
+    # and a real run with the default window stops where the oracle stops
+    f4 = NSF_AR(dim=d, K=K, hidden_dim=H)
+    f4.load_flat_parameters(theta0)
+    h4, ran4 = f4.fit(torch.tensor(x), 2000, 0.02, average_window=50, loss_delta_tol=1e-2)
+    _, h4o, ran4o = orc.train(theta0, d, K, H, 5.0, x, 2000, 0.02, average_window=50, loss_delta_tol=1e-2)
+    assert ran4 % 50 == 0 and ran4 < 2000
+    assert abs(ran4 - ran4o) <= 50, (ran4, ran4o)
+
+
+def test_training_is_bitwise_reproducible():
+    from nfisam_b200.flows import NSF_AR
+
+    rng = np.random.default_rng(9)
+    x = torch.tensor(rng.standard_normal((1500, 7)).astype(np.float32))
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(3)
+        f = NSF_AR(dim=7, K=9, hidden_dim=8)
+        hist, ran = f.fit(x, 60, 0.02, average_window=0)
+        outs.append((hist.copy(), f.flat_parameters()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_unsupported_configuration_fails_loudly():
+    from nfisam_b200 import _lib
+    from nfisam_b200.flows import NSF_AR
+
+    f = NSF_AR(dim=3, K=7, hidden_dim=8)
+    with pytest.raises(_lib.NfisamError):
+        f.forward(torch.zeros(4, 3))
