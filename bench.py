@@ -51,7 +51,9 @@ def make_inputs(n, d, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled from a thread
+    every ~2 ms (the timed region can be tens of milliseconds, too short for `nvidia-smi -lms`);
+    falls back to the nvidia-smi recipe of B200_PROFILING.md when pynvml is unavailable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -60,19 +62,72 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.mode = None
+
+    def _poll(self, nv, handle):
+        bits = {}
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            v = getattr(nv, attr, None)
+            if v is None:
+                v = getattr(nv, attr.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+            if v is not None:
+                bits[name] = v
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    r = int(get_reasons(handle))
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                ent = vis.split(",")[self.gpu].strip()
+                if ent.isdigit():
+                    idx = int(ent)
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, handle), daemon=True)
+            self.thread.start()
+            self.mode = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
         except OSError:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 2 ms polling"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -93,7 +148,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def measured_peaks():
@@ -257,9 +312,10 @@ def run_gpu(args):
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (nf_forward_kernel<9,8>), live CUDA-event timing
-        fp32_peak = ctypes.c_double(0.0)
-        mufu_peak = ctypes.c_double(0.0)
-        _lib.check(lib.nfisam_probe_pipe_peaks(local_rank, ctypes.byref(fp32_peak), ctypes.byref(mufu_peak)))
+        peaks = (ctypes.c_double * 4)()
+        _lib.check(lib.nfisam_probe_pipe_peaks(local_rank, peaks))
+        fp32_peak = ctypes.c_double(max(peaks[0], peaks[1], peaks[2]))
+        mufu_peak = ctypes.c_double(peaks[3])
         fl = flops_fwd(D, HID, K_BINS)
         achieved_tflops = fl * n / (per_launch_ms * 1e-3) * 1e-12
         alg_bytes = (4 * D + 4) * n
@@ -269,8 +325,10 @@ def run_gpu(args):
             "bound": "fp32_fma", "kernel": "nf_forward_kernel<K=9,H=8> (log_prob mode)",
             "achieved": achieved_tflops, "peak": fp32_peak.value, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak.value if fp32_peak.value > 0 else None,
-            "peak_source": "measured live: FFMA-only probe kernel (nfisam_probe_pipe_peaks); MEASURED_PEAKS.json holds no "
-                           "FP32 figure. The kernel is FMA/MUFU-bound (95 flop/B), not HBM- or tensor-bound (SURVEY.md 8d)",
+            "peak_source": "measured live: best of the FFMA / FFMA2 probe kernels (nfisam_probe_pipe_peaks); "
+                           "MEASURED_PEAKS.json holds no FP32 figure. The kernel is FMA/MUFU-bound (95 flop/B), not HBM- or "
+                           "tensor-bound (SURVEY.md 8d)",
+            "fp32_probe_tflops": {"ffma_reg": peaks[0], "ffma2": peaks[1], "ffma_const": peaks[2]},
             "flops_per_sample": fl, "sfu_ops_per_sample": sfu_fwd(D, HID, K_BINS),
             "mufu": {"achieved_gops": sfu_fwd(D, HID, K_BINS) * n / (per_launch_ms * 1e-3) * 1e-9, "peak_gops": mufu_peak.value},
             "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,

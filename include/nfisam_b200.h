@@ -53,10 +53,11 @@ const char* nfisam_last_error(void);
 int nfisam_device_count(void);
 /* Number of kernels this library launched so far in this process (bench.py's gpu_launches). */
 int64_t nfisam_launch_count(void);
-/* Measured peaks of the FP32 FMA pipe (TFLOP/s, 2 flops per FMA) and of the MUFU/SFU pipe (Gop/s) on
- * `device`, from two register-only probe kernels: the roofline denominators of the flow kernels,
- * which are FMA/MUFU-bound.  Synchronous, ~10 ms. */
-int nfisam_probe_pipe_peaks(int device, double* fp32_tflops, double* mufu_gops);
+/* Measured pipe peaks on `device` from register-only probe kernels -- the roofline denominators of
+ * the flow kernels, which are FMA/MUFU-bound.  peaks4[0] FFMA with register
+ * operands, [1] packed FFMA2 (fma.rn.f32x2), [2] FFMA with constant-bank operands, all in TFLOP/s
+ * (2 flops per FMA); [3] MUFU ex2 in Gop/s.  Synchronous, ~30 ms. */
+int nfisam_probe_pipe_peaks(int device, double* peaks4);
 /* sizeof of an ABI struct, for binding validation: 0 nf_train_cfg, 1 nf_factor_desc, 2 nf_affine. */
 int nfisam_struct_size(int which);
 

@@ -69,7 +69,7 @@ SYMBOLS = {
     "nfisam_device_count": (_INT, []),
     "nfisam_launch_count": (_I64, []),
     "nfisam_struct_size": (_INT, [_INT]),
-    "nfisam_probe_pipe_peaks": (_INT, [_INT, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "nfisam_probe_pipe_peaks": (_INT, [_INT, ctypes.POINTER(ctypes.c_double)]),
     "nfisam_flow_create": (_INT, [_INT, _INT, _INT, ctypes.c_float, _INT, ctypes.POINTER(_P)]),
     "nfisam_flow_destroy": (_INT, [_P]),
     "nfisam_flow_num_params": (_INT, [_P, ctypes.POINTER(_I64)]),

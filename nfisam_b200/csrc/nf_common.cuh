@@ -32,25 +32,126 @@ __host__ __device__ __forceinline__ int nf_block_off(int i, int H, int Pp) {
 __host__ __device__ __forceinline__ int nf_packed_size(int d, int H, int Pp) { return nf_block_off(d, H, Pp); }
 
 // ---------------------------------------------------------------------------------------------
-// Scalar math.  Accurate (non fast-math) paths: the parity bar is 1e-5 relative to the
-// reference's float32 PyTorch results.
+// Scalar math.  The flow kernels are bound by instruction issue (ncu: 83 % issue-active with libm
+// expf/logf/tanhf/IEEE division), so transcendental functions map straight onto the MUFU unit:
+// ex2 / lg2 / rcp approximations are accurate to ~1-2 ulp (relative 1.2e-7..2.4e-7), two orders of
+// magnitude inside the 1e-5 parity bar.  -DNF_ACCURATE_MATH=1 switches back to libm for A/B checks.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float nf_tanh(float v) { return tanhf(v); }
-// torch.nn.functional.softplus(beta=1, threshold=20)
-__device__ __forceinline__ float nf_softplus(float v) { return v > 20.0f ? v : log1pf(expf(v)); }
-__device__ __forceinline__ float nf_sigmoid_sp(float v) { return v > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-v)); }
+#ifndef NF_ACCURATE_MATH
+#define NF_ACCURATE_MATH 0
+#endif
+
+__device__ __forceinline__ float nf_ex2(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float nf_lg2(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float nf_rcp(float v) {
+#if NF_ACCURATE_MATH
+    return 1.0f / v;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#endif
+}
+__device__ __forceinline__ float nf_div(float a, float b) {
+#if NF_ACCURATE_MATH
+    return a / b;
+#else
+    return a * nf_rcp(b);
+#endif
+}
+__device__ __forceinline__ float nf_exp(float v) {
+#if NF_ACCURATE_MATH
+    return expf(v);
+#else
+    return nf_ex2(v * 1.4426950408889634f);
+#endif
+}
+__device__ __forceinline__ float nf_log(float v) {
+#if NF_ACCURATE_MATH
+    return logf(v);
+#else
+    return nf_lg2(v) * 0.6931471805599453f;
+#endif
+}
+__device__ __forceinline__ float nf_sqrt(float v) {
+#if NF_ACCURATE_MATH
+    return sqrtf(v);
+#else
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#endif
+}
+// tanh(v) = 1 - 2 / (exp(2v) + 1): 2 MUFU + 3 FP32 ops, absolute error ~1e-7 (saturates cleanly)
+__device__ __forceinline__ float nf_tanh(float v) {
+#if NF_ACCURATE_MATH
+    return tanhf(v);
+#else
+    const float t = nf_ex2(v * 2.8853900817779268f);
+    return fmaf(-2.0f, nf_rcp(t + 1.0f), 1.0f);
+#endif
+}
+// torch.nn.functional.softplus(beta=1, threshold=20) = log1p(exp(v))
+__device__ __forceinline__ float nf_softplus(float v) {
+#if NF_ACCURATE_MATH
+    return v > 20.0f ? v : log1pf(expf(v));
+#else
+    const float e = nf_exp(fminf(v, 20.0f));
+    // log1p by its alternating series below 0.1 (lg2.approx of 1+e would lose relative accuracy there)
+    const float ser = e * fmaf(e, fmaf(e, fmaf(e, fmaf(e, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
+    const float lg = nf_log(1.0f + e);
+    const float sp = e < 0.1f ? ser : lg;
+    return v > 20.0f ? v : sp;
+#endif
+}
+__device__ __forceinline__ float nf_sigmoid_sp(float v) {
+    return v > 20.0f ? 1.0f : nf_rcp(1.0f + nf_exp(-v));
+}
 
 #define NF_MIN_BIN 1e-3f
 #define NF_MIN_DERIV 1e-3f
 // log(exp(1 - 1e-3) - 1) evaluated in float64 and rounded to float32 (src/flows/utils.py:42)
 #define NF_EDGE_CONST 0.5397424172369522f
+// 1e-3 + softplus(NF_EDGE_CONST) in float32, the reference's boundary derivative (0.99999994)
+#define NF_EDGE_DERIV 0.99999994f
 
-__device__ __forceinline__ float nf_edge_derivative() { return NF_MIN_DERIV + nf_softplus(NF_EDGE_CONST); }
+// packed dual-FP32 FMA (fma.rn.f32x2, new on sm_100): halves the issue slots of the MLP inner products
+__device__ __forceinline__ float2 nf_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
 // ---------------------------------------------------------------------------------------------
 // Conditioner MLP, evaluated by one thread for one sample.  `w` points at block i (i >= 1) in
-// shared memory, `xrow` at the sample's inputs (shared memory, unit stride).
+// shared memory, `xrow` at the sample's inputs (shared memory, unit stride).  Outputs are produced
+// two at a time: one float4 shared-memory broadcast feeds two FFMA2 whose second operand is the
+// duplicated input.
 // ---------------------------------------------------------------------------------------------
+template <int NOUT>
+__device__ __forceinline__ void nf_load_bias(const float* __restrict__ b, float2 (&acc)[NOUT / 2]) {
+#pragma unroll
+    for (int j = 0; j < NOUT; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(b + j);
+        acc[j / 2] = make_float2(v.x, v.y);
+        acc[j / 2 + 1] = make_float2(v.z, v.w);
+    }
+}
+template <int NOUT>
+__device__ __forceinline__ void nf_axpy_row(const float* __restrict__ wrow, float xv, float2 (&acc)[NOUT / 2]) {
+    const float2 xx = make_float2(xv, xv);
+#pragma unroll
+    for (int j = 0; j < NOUT; j += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wrow + j);
+        acc[j / 2] = nf_fma2(make_float2(w4.x, w4.y), xx, acc[j / 2]);
+        acc[j / 2 + 1] = nf_fma2(make_float2(w4.z, w4.w), xx, acc[j / 2 + 1]);
+    }
+}
+
 template <int H>
 __device__ __forceinline__ void nf_mlp_hidden(const float* __restrict__ w, int i, const float* __restrict__ xrow,
                                               float (&h1)[H], float (&h2)[H]) {
@@ -58,45 +159,16 @@ __device__ __forceinline__ void nf_mlp_hidden(const float* __restrict__ w, int i
     const float* b1 = W1t + i * H;
     const float* W2t = b1 + H;
     const float* b2 = W2t + H * H;
-    float a[H];
+    float2 a[H / 2];
+    nf_load_bias<H>(b1, a);
+    for (int k = 0; k < i; ++k) nf_axpy_row<H>(W1t + k * H, xrow[k], a);
 #pragma unroll
-    for (int j = 0; j < H; j += 4) {
-        float4 b = *reinterpret_cast<const float4*>(b1 + j);
-        a[j] = b.x; a[j + 1] = b.y; a[j + 2] = b.z; a[j + 3] = b.w;
-    }
-    for (int k = 0; k < i; ++k) {
-        const float xv = xrow[k];
-        const float4* wr = reinterpret_cast<const float4*>(W1t + k * H);
+    for (int j = 0; j < H / 2; ++j) { h1[2 * j] = nf_tanh(a[j].x); h1[2 * j + 1] = nf_tanh(a[j].y); }
+    nf_load_bias<H>(b2, a);
 #pragma unroll
-        for (int j4 = 0; j4 < H / 4; ++j4) {
-            float4 w4 = wr[j4];
-            a[4 * j4 + 0] = fmaf(w4.x, xv, a[4 * j4 + 0]);
-            a[4 * j4 + 1] = fmaf(w4.y, xv, a[4 * j4 + 1]);
-            a[4 * j4 + 2] = fmaf(w4.z, xv, a[4 * j4 + 2]);
-            a[4 * j4 + 3] = fmaf(w4.w, xv, a[4 * j4 + 3]);
-        }
-    }
+    for (int k = 0; k < H; ++k) nf_axpy_row<H>(W2t + k * H, h1[k], a);
 #pragma unroll
-    for (int j = 0; j < H; ++j) h1[j] = nf_tanh(a[j]);
-#pragma unroll
-    for (int j = 0; j < H; j += 4) {
-        float4 b = *reinterpret_cast<const float4*>(b2 + j);
-        a[j] = b.x; a[j + 1] = b.y; a[j + 2] = b.z; a[j + 3] = b.w;
-    }
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-        const float4* wr = reinterpret_cast<const float4*>(W2t + k * H);
-#pragma unroll
-        for (int j4 = 0; j4 < H / 4; ++j4) {
-            float4 w4 = wr[j4];
-            a[4 * j4 + 0] = fmaf(w4.x, h1[k], a[4 * j4 + 0]);
-            a[4 * j4 + 1] = fmaf(w4.y, h1[k], a[4 * j4 + 1]);
-            a[4 * j4 + 2] = fmaf(w4.z, h1[k], a[4 * j4 + 2]);
-            a[4 * j4 + 3] = fmaf(w4.w, h1[k], a[4 * j4 + 3]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < H; ++j) h2[j] = nf_tanh(a[j]);
+    for (int j = 0; j < H / 2; ++j) { h2[2 * j] = nf_tanh(a[j].x); h2[2 * j + 1] = nf_tanh(a[j].y); }
 }
 
 // Output layer: out[0..Pp) = b3 + W3 h2   (entries >= 3K-1 are padding and stay 0).
@@ -104,23 +176,12 @@ template <int H, int PP>
 __device__ __forceinline__ void nf_mlp_out(const float* __restrict__ w, int i, const float (&h2)[H], float (&out)[PP]) {
     const float* W3t = w + i * H + H + H * H + H;
     const float* b3 = W3t + H * PP;
+    float2 acc[PP / 2];
+    nf_load_bias<PP>(b3, acc);
 #pragma unroll
-    for (int p = 0; p < PP; p += 4) {
-        float4 b = *reinterpret_cast<const float4*>(b3 + p);
-        out[p] = b.x; out[p + 1] = b.y; out[p + 2] = b.z; out[p + 3] = b.w;
-    }
+    for (int k = 0; k < H; ++k) nf_axpy_row<PP>(W3t + k * PP, h2[k], acc);
 #pragma unroll
-    for (int k = 0; k < H; ++k) {
-        const float4* wr = reinterpret_cast<const float4*>(W3t + k * PP);
-#pragma unroll
-        for (int p4 = 0; p4 < PP / 4; ++p4) {
-            float4 w4 = wr[p4];
-            out[4 * p4 + 0] = fmaf(w4.x, h2[k], out[4 * p4 + 0]);
-            out[4 * p4 + 1] = fmaf(w4.y, h2[k], out[4 * p4 + 1]);
-            out[4 * p4 + 2] = fmaf(w4.z, h2[k], out[4 * p4 + 2]);
-            out[4 * p4 + 3] = fmaf(w4.w, h2[k], out[4 * p4 + 3]);
-        }
-    }
+    for (int p = 0; p < PP / 2; ++p) { out[2 * p] = acc[p].x; out[2 * p + 1] = acc[p].y; }
 }
 
 // Conditioner outputs for dim i (i = 0 reads init_param).
@@ -154,8 +215,8 @@ __device__ __forceinline__ void nf_knots(const float* u, float B, float (&c)[K +
     float e[K];
     float s = 0.0f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { e[k] = expf(u[k] - m); s += e[k]; }
-    const float inv = 1.0f / s;
+    for (int k = 0; k < K; ++k) { e[k] = nf_exp(u[k] - m); s += e[k]; }
+    const float inv = nf_rcp(s);
     const float scale = (float)(1.0 - 1e-3 * (double)K);
     float acc = 0.0f;
     c[0] = -B;
@@ -200,8 +261,8 @@ __device__ __forceinline__ void nf_derivs(const float* ud, int bin, float& dk, f
         if (bin == k) uk = ud[k - 1];
         if (bin + 1 == k) uk1 = ud[k - 1];
     }
-    dk = NF_MIN_DERIV + nf_softplus(uk);
-    dk1 = NF_MIN_DERIV + nf_softplus(uk1);
+    dk = bin == 0 ? NF_EDGE_DERIV : NF_MIN_DERIV + nf_softplus(uk);
+    dk1 = bin == K - 1 ? NF_EDGE_DERIV : NF_MIN_DERIV + nf_softplus(uk1);
 }
 
 // Forward spline for one value. out = [uw(K) | uh(K) | ud(K-1)].   src/flows/utils.py:148-164
@@ -217,15 +278,20 @@ __device__ __forceinline__ float nf_rqs_forward(const float* out, float B, float
     nf_select2<K>(chh, bin, yk, yk1);
     nf_derivs<K>(out + 2 * K, bin, dk, dk1, uk, uk1);
     const float wk = xk1 - xk, hk = yk1 - yk;
-    const float delta = hk / wk;
-    const float th = (x - xk) / wk;
+    const float rw = nf_rcp(wk);
+    const float delta = hk * rw;
+    const float th = (x - xk) * rw;
     const float t1 = th * (1.0f - th);
     const float num = hk * (delta * th * th + dk * t1);
     const float den = delta + (dk + dk1 - 2.0f * delta) * t1;
     const float omt = 1.0f - th;
     const float dnum = delta * delta * (dk1 * th * th + 2.0f * delta * t1 + dk * omt * omt);
+#if NF_ACCURATE_MATH
     ld = logf(dnum) - 2.0f * logf(den);
-    return yk + num / den;
+#else
+    ld = 0.6931471805599453f * fmaf(-2.0f, nf_lg2(den), nf_lg2(dnum));
+#endif
+    return yk + nf_div(num, den);
 }
 
 // Inverse spline for one value; ld is what the reference's inverse returns (-logabsdet).
@@ -242,19 +308,23 @@ __device__ __forceinline__ float nf_rqs_inverse(const float* out, float B, float
     nf_select2<K>(cw, bin, xk, xk1);
     nf_derivs<K>(out + 2 * K, bin, dk, dk1, uk, uk1);
     const float wk = xk1 - xk, hk = yk1 - yk;
-    const float delta = hk / wk;
+    const float delta = nf_div(hk, wk);
     const float dy = y - yk, sm = dk + dk1 - 2.0f * delta;
     const float a = dy * sm + hk * (delta - dk);
     const float b = hk * dk - dy * sm;
     const float c = -delta * dy;
     float disc = b * b - 4.0f * a * c;
     if (!(disc >= 0.0f)) { bad = true; disc = 0.0f; }
-    const float root = (2.0f * c) / (-b - sqrtf(disc));
+    const float root = nf_div(2.0f * c, -b - nf_sqrt(disc));
     const float t1 = root * (1.0f - root);
     const float den = delta + sm * t1;
     const float omr = 1.0f - root;
     const float dnum = delta * delta * (dk1 * root * root + 2.0f * delta * t1 + dk * omr * omr);
+#if NF_ACCURATE_MATH
     ld = -(logf(dnum) - 2.0f * logf(den));
+#else
+    ld = -0.6931471805599453f * fmaf(-2.0f, nf_lg2(den), nf_lg2(dnum));
+#endif
     return root * wk + xk;
 }
 

@@ -48,17 +48,21 @@ __device__ __forceinline__ float nf_rqs_grad(float (&o)[((3 * K - 1) + 3) & ~3],
     nf_select2<K>(chh, bin, yk, yk1);
     nf_derivs<K>(o + 2 * K, bin, a, bq, uk, uk1);
     const float wk = xk1 - xk, hk = yk1 - yk;
-    const float rw = 1.0f / wk;
-    const float s = hk / wk;
-    const float t = (x - xk) / wk, u = t * (1.0f - t), omt = 1.0f - t;
+    const float rw = nf_rcp(wk);
+    const float s = hk * rw;
+    const float t = (x - xk) * rw, u = t * (1.0f - t), omt = 1.0f - t;
     const float N = hk * (s * t * t + a * u);
     const float Dn = s + (a + bq - 2.0f * s) * u;
     const float Q = bq * t * t + 2.0f * s * u + a * omt * omt;
     const float M = s * s * Q;
-    const float rD = 1.0f / Dn;
+    const float rD = nf_rcp(Dn);
     const float z = yk + N * rD;
+#if NF_ACCURATE_MATH
     const float f = -0.5f * z * z + logf(M) - 2.0f * logf(Dn);
-    const float cN = -z * rD, cD = z * N * rD * rD - 2.0f * rD, cM = 1.0f / M;
+#else
+    const float f = fmaf(-0.5f * z, z, 0.6931471805599453f * fmaf(-2.0f, nf_lg2(Dn), nf_lg2(M)));
+#endif
+    const float cN = -z * rD, cD = z * N * rD * rD - 2.0f * rD, cM = nf_rcp(M);
     const float N_s = hk * t * t, N_a = hk * u, N_t = hk * (2.0f * s * t + a * (1.0f - 2.0f * t)), N_h = s * t * t + a * u;
     const float D_s = 1.0f - 2.0f * u, D_t = (a + bq - 2.0f * s) * (1.0f - 2.0f * t);
     const float M_s = 2.0f * s * Q + 2.0f * s * s * u, M_a = s * s * omt * omt, M_b = s * s * t * t;
@@ -210,12 +214,13 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
 
     for (int it = it_begin; it < it_end; ++it) {
         // ---------------- local gradient over this warp's tiles ----------------
-        float acc3[NC3][H], accb3[NC3], acc2[N2], accb2 = 0.0f, acc1[M1], accb1 = 0.0f, floss = 0.0f;
+        float2 acc3[NC3][H / 2];
+        float accb3[NC3], acc2[N2], accb2 = 0.0f, acc1[M1], accb1 = 0.0f, floss = 0.0f;
 #pragma unroll
         for (int c = 0; c < NC3; ++c) {
             accb3[c] = 0.0f;
 #pragma unroll
-            for (int k = 0; k < H; ++k) acc3[c][k] = 0.0f;
+            for (int k = 0; k < H / 2; ++k) acc3[c][k] = make_float2(0.0f, 0.0f);
         }
 #pragma unroll
         for (int m = 0; m < N2; ++m) acc2[m] = 0.0f;
@@ -255,33 +260,35 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                 float g2[H], g1[H];
                 const float* W3t = s_w + oW3;
                 const float* W2t = s_w + oW2;
+                float2 o2[PP / 2];
+#pragma unroll
+                for (int p = 0; p < PP / 2; ++p) o2[p] = make_float2(out[2 * p], out[2 * p + 1]);
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
                     const float4* wr = reinterpret_cast<const float4*>(W3t + k * PP);
-                    float acc = 0.0f;
+                    float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
                     for (int p4 = 0; p4 < PP / 4; ++p4) {
                         const float4 w4 = wr[p4];
-                        acc = fmaf(w4.x, out[4 * p4], acc);
-                        acc = fmaf(w4.y, out[4 * p4 + 1], acc);
-                        acc = fmaf(w4.z, out[4 * p4 + 2], acc);
-                        acc = fmaf(w4.w, out[4 * p4 + 3], acc);
+                        acc = nf_fma2(make_float2(w4.x, w4.y), o2[2 * p4], acc);
+                        acc = nf_fma2(make_float2(w4.z, w4.w), o2[2 * p4 + 1], acc);
                     }
-                    g2[k] = acc * (1.0f - h2[k] * h2[k]);
+                    g2[k] = (acc.x + acc.y) * fmaf(-h2[k], h2[k], 1.0f);
                 }
+                float2 g22[H / 2];
+#pragma unroll
+                for (int k = 0; k < H / 2; ++k) g22[k] = make_float2(g2[2 * k], g2[2 * k + 1]);
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
                     const float4* wr = reinterpret_cast<const float4*>(W2t + k * H);
-                    float acc = 0.0f;
+                    float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
                     for (int j4 = 0; j4 < H / 4; ++j4) {
                         const float4 w4 = wr[j4];
-                        acc = fmaf(w4.x, g2[4 * j4], acc);
-                        acc = fmaf(w4.y, g2[4 * j4 + 1], acc);
-                        acc = fmaf(w4.z, g2[4 * j4 + 2], acc);
-                        acc = fmaf(w4.w, g2[4 * j4 + 3], acc);
+                        acc = nf_fma2(make_float2(w4.x, w4.y), g22[2 * j4], acc);
+                        acc = nf_fma2(make_float2(w4.z, w4.w), g22[2 * j4 + 1], acc);
                     }
-                    g1[k] = acc * (1.0f - h1[k] * h1[k]);
+                    g1[k] = (acc.x + acc.y) * fmaf(-h1[k], h1[k], 1.0f);
                 }
 #pragma unroll
                 for (int k = 0; k < H; k += 4) {
@@ -306,11 +313,12 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
             } else {
                 for (int ss = 0; ss < 32; ++ss) {
                     const float* rw_ = stage + ss * STG;
-                    float hv[H];
+                    float2 hv[H / 2];
 #pragma unroll
                     for (int k = 0; k < H; k += 4) {
                         const float4 v = *reinterpret_cast<const float4*>(rw_ + PP + k);
-                        hv[k] = v.x; hv[k + 1] = v.y; hv[k + 2] = v.z; hv[k + 3] = v.w;
+                        hv[k / 2] = make_float2(v.x, v.y);
+                        hv[k / 2 + 1] = make_float2(v.z, v.w);
                     }
 #pragma unroll
                     for (int c = 0; c < NC3; ++c) {
@@ -318,8 +326,9 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                         if (p < PP) {
                             const float g = rw_[p];
                             accb3[c] += g;
+                            const float2 gg = make_float2(g, g);
 #pragma unroll
-                            for (int k = 0; k < H; ++k) acc3[c][k] = fmaf(g, hv[k], acc3[c][k]);
+                            for (int k = 0; k < H / 2; ++k) acc3[c][k] = nf_fma2(gg, hv[k], acc3[c][k]);
                         }
                     }
                     const float g2j = rw_[PP + H + jl];
@@ -348,7 +357,10 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                     wg[ob3 + p] = accb3[c];
                     if (i > 0) {
 #pragma unroll
-                        for (int k = 0; k < H; ++k) wg[oW3 + k * PP + p] = acc3[c][k];
+                        for (int k = 0; k < H / 2; ++k) {
+                            wg[oW3 + (2 * k) * PP + p] = acc3[c][k].x;
+                            wg[oW3 + (2 * k + 1) * PP + p] = acc3[c][k].y;
+                        }
                     }
                 }
             }

@@ -1,0 +1,89 @@
+"""GPU parity of the float64 factor kernels (through nfisam_factor_logpdf /
+nfisam_mixture_posterior_weights) against the golden vectors of the reference's own factor classes and
+against the numpy oracle on larger seeded inputs.  Tolerance: |diff| <= 1e-6 (north_star), written below."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import factor_oracle as fo
+from tests.test_oracle_factors import build_factors, check
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def g():
+    return dict(np.load(os.path.join(HERE, "golden", "factors.npz")))
+
+
+def test_single_factors_golden(g):
+    for key, f in build_factors(g).items():
+        got = f.log_pdf(g[key + "_x"])
+        # values reach 2e6 in magnitude: 1e-6 absolute there is 5e-13 relative
+        ref = g[key + "_lp"]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin), key
+        assert np.max(np.abs(got[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]) * 1e-3)) <= TOL, key
+        pdf = f.pdf(g[key + "_x"][:8])
+        assert np.allclose(pdf, np.exp(ref[:8]), rtol=1e-9, atol=0)
+
+
+def test_posterior_weights_golden(g):
+    fs = build_factors(g)
+    from nfisam_b200.slam import R2Variable, SE2Variable
+
+    X0, L1, L2, L3 = SE2Variable("X0"), R2Variable("L1"), R2Variable("L2"), R2Variable("L3")
+    x = g["ada2_x"]
+    w = fs["ada2"].posterior_weights({X0: x[:, :3], L1: x[:, 3:5], L2: x[:, 5:7]})
+    assert np.allclose(w, g["ada2_post_w"], atol=1e-9)
+    x = g["ada3_x"]
+    w = fs["ada3"].posterior_weights({X0: x[:, :3], L1: x[:, 3:5], L2: x[:, 5:7], L3: x[:, 7:9]})
+    assert np.allclose(w, g["ada3_post_w"], atol=1e-9)
+
+
+@pytest.mark.parametrize("tag,path", [("joint", "small_case1.fg"), ("joint_da", "small_case1_da.fg")])
+def test_fused_joint_golden(g, tag, path):
+    from nfisam_b200.factors import JointFactor
+    from nfisam_b200.slam.graph_io import read_factor_graph_from_file
+
+    nodes, truth, factors = read_factor_graph_from_file(os.path.join(HERE, "data", path))
+    jf = JointFactor(factors, nodes)
+    total, per = jf.log_pdf(g[tag + "_x"], per_factor=True)
+    assert np.max(np.abs(total - g[tag + "_lp"]) / np.maximum(1.0, np.abs(g[tag + "_lp"]) * 1e-3)) <= TOL
+    assert np.max(np.abs(per - g[tag + "_per_factor"]) / np.maximum(1.0, np.abs(g[tag + "_per_factor"]) * 1e-3)) <= TOL
+
+
+@pytest.mark.parametrize("n", [1, 127, 100_000])
+def test_joint_vs_oracle_sizes(n):
+    from nfisam_b200.factors import JointFactor, oracle_descriptor
+    from nfisam_b200.slam.graph_io import read_factor_graph_from_file
+
+    nodes, truth, factors = read_factor_graph_from_file(os.path.join(HERE, "data", "small_case1_da.fg"))
+    jf = JointFactor(factors, nodes)
+    rng = np.random.default_rng(n)
+    center = np.concatenate([truth[v] for v in nodes])
+    x = center + rng.standard_normal((n, center.size)) * np.tile([0.5, 0.5, 0.05], 8)[:center.size]
+    x[:, 2] += 2 * np.pi * rng.integers(-2, 3, n)          # unwrapped angles must not matter
+    got = jf.log_pdf(x)
+    exp = fo.joint_logpdf([oracle_descriptor(f, jf._col_of) for f in factors], x)
+    assert np.max(np.abs(got - exp) / np.maximum(1.0, np.abs(exp) * 1e-3)) <= TOL
+
+
+def test_device_tensor_input_and_bad_descriptor():
+    import torch
+
+    from nfisam_b200 import _lib
+    from nfisam_b200.factors import SE2R2RangeGaussianLikelihoodFactor, _gpu
+    from nfisam_b200.slam import R2Variable, SE2Variable
+
+    f = SE2R2RangeGaussianLikelihoodFactor(SE2Variable("X"), R2Variable("L"), 5.0, 1.0)
+    x = torch.randn(1000, 5, dtype=torch.float64, device="cuda")
+    out = _gpu.logpdf([f.components({f.vars[0]: 0, f.vars[1]: 3})], x)
+    assert out.is_cuda and out.shape == (1000,)
+    r = (x[:, :2] - x[:, 3:5]).norm(dim=1)
+    assert torch.allclose(out, -0.5 * (r - 5.0) ** 2 - 0.5 * np.log(2 * np.pi), atol=1e-12)
+    with pytest.raises(_lib.NfisamError):
+        _gpu.logpdf([[dict(type="range", cols=[0, 1, 2, 9], obs=[1.0], info=[1.0], lnorm=0.0)]], x)
