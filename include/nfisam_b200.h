@@ -104,12 +104,14 @@ typedef struct nf_affine {
 } nf_affine;
 
 /* NSF_AR.inverse (sep_dim = 0, src/flows/flows.py:95-113) and NSF_AR.inverse_given_separator
- * (src/flows/flows.py:115-137):
- *   z_dev (n, dim - sep_dim) latent draws, x_sep_dev (n, sep_dim) or NULL when sep_dim = 0,
- *   x_out_dev (n, dim - sep_dim), logdet_dev (n) or NULL (the value NSF_AR.inverse returns).
+ * (src/flows/flows.py:115-137).  Generates the out_dim columns that follow the sep_dim given ones,
+ * sep_dim + out_dim <= dim (the reference's loop runs over range(sep_dim, sep_dim + z.shape[1]): a
+ * separator factor draws only the separator block of a clique flow, a prefix of the autoregression):
+ *   z_dev (n, out_dim) latent draws, x_sep_dev (n, sep_dim) or NULL when sep_dim = 0,
+ *   x_out_dev (n, out_dim), logdet_dev (n) or NULL (the value NSF_AR.inverse returns).
  * Samples whose discriminant is negative are counted in the handle; query with
  * nfisam_flow_pop_bad_count (synchronises the stream). */
-int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim,
+int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim, int out_dim,
                         float* x_out_dev, float* logdet_dev, const nf_affine* norm, void* stream);
 int nfisam_flow_pop_bad_count(nf_flow_t* f, void* stream, int64_t* count);
 
@@ -117,7 +119,7 @@ int nfisam_flow_pop_bad_count(nf_flow_t* f, void* stream, int64_t* count);
  * H2D -> kernel -> D2H pipelining on two internal streams.  Synchronous. */
 int nfisam_flow_log_prob_host(nf_flow_t* f, const float* x_host, int64_t n, int d_in, float* logp_host);
 int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_sep_host, int64_t n, int sep_dim,
-                             float* x_out_host, const float* mean_host, const float* std_host,
+                             int out_dim, float* x_out_host, const float* mean_host, const float* std_host,
                              const uint8_t* circular_host);
 
 /* ------------------------------------------------------------------------------------------

@@ -254,10 +254,11 @@ int nfisam_flow_log_prob(nf_flow_t* f, const float* x_dev, int64_t n, int d_in, 
                              (cudaStream_t)stream);
 }
 
-int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim,
+int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim, int out_dim,
                         float* x_out_dev, float* logdet_dev, const nf_affine* norm, void* stream) {
     if (!f || ((!z_dev || !x_out_dev) && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
-    if (n < 0 || sep_dim < 0 || sep_dim >= f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / sep_dim");
+    if (n < 0 || sep_dim < 0 || out_dim < 1 || sep_dim + out_dim > f->fd.d)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad n / sep_dim / out_dim (sep_dim + out_dim must be <= dim)");
     if (sep_dim > 0 && !x_sep_dev && n > 0) return nf_set_error(NF_ERR_BAD_ARG, "x_sep_dev is NULL");
     const float* mean = nullptr; const float* stdv = nullptr; const uint8_t* circ = nullptr;
     if (norm) {
@@ -265,7 +266,7 @@ int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev
         mean = norm->mean_dev; stdv = norm->std_dev; circ = norm->circular_dev;
     }
     DeviceGuard g(f->device);
-    return nf_launch_inverse(f->fd, f->d_pk, z_dev, x_sep_dev, n, sep_dim, x_out_dev, logdet_dev, mean, stdv, circ,
+    return nf_launch_inverse(f->fd, f->d_pk, z_dev, x_sep_dev, n, sep_dim, out_dim, x_out_dev, logdet_dev, mean, stdv, circ,
                              f->d_bad, f->device, (cudaStream_t)stream);
 }
 
@@ -326,13 +327,14 @@ int nfisam_flow_log_prob_host(nf_flow_t* f, const float* x_host, int64_t n, int 
 }
 
 int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_sep_host, int64_t n, int sep_dim,
-                             float* x_out_host, const float* mean_host, const float* std_host,
+                             int out_dim, float* x_out_host, const float* mean_host, const float* std_host,
                              const uint8_t* circular_host) {
     if (!f || ((!z_host || !x_out_host) && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
-    if (n < 0 || sep_dim < 0 || sep_dim >= f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / sep_dim");
+    if (n < 0 || sep_dim < 0 || out_dim < 1 || sep_dim + out_dim > f->fd.d)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad n / sep_dim / out_dim (sep_dim + out_dim must be <= dim)");
     if (sep_dim > 0 && !x_sep_host && n > 0) return nf_set_error(NF_ERR_BAD_ARG, "x_sep_host is NULL");
     if (n == 0) return NF_OK;
-    const int d = f->fd.d, fr = d - sep_dim;
+    const int d = f->fd.d, fr = out_dim;
     DeviceGuard g(f->device);
     int rc = ensure_streams(f);
     if (rc != NF_OK) return rc;
@@ -356,7 +358,7 @@ int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_s
             NF_CUDA(cudaMemcpyAsync(f->d_stage_aux[s], x_sep_host + o * sep_dim, sizeof(float) * (size_t)m * sep_dim,
                                     cudaMemcpyHostToDevice, st));
         rc = nf_launch_inverse(f->fd, f->d_pk, f->d_stage_in[s], sep_dim > 0 ? f->d_stage_aux[s] : nullptr, m, sep_dim,
-                               f->d_stage_out[s], nullptr, has_norm ? f->d_norm : nullptr, has_norm ? f->d_norm + d : nullptr,
+                               out_dim, f->d_stage_out[s], nullptr, has_norm ? f->d_norm : nullptr, has_norm ? f->d_norm + d : nullptr,
                                has_norm ? f->d_circ : nullptr, f->d_bad, f->device, st);
         if (rc != NF_OK) return rc;
         NF_CUDA(cudaMemcpyAsync(x_out_host + o * fr, f->d_stage_out[s], sizeof(float) * (size_t)m * fr, cudaMemcpyDeviceToHost, st));

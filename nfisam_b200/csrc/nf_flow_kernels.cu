@@ -87,7 +87,7 @@ __global__ void nf_rowsum_kernel(const float* __restrict__ ws, int64_t n, int d_
 
 template <int K, int H>
 __global__ void __launch_bounds__(TPB)
-nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, float B, const float* __restrict__ zin,
+nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, float B, const float* __restrict__ zin,  // d = sep + generated dims
                   const float* __restrict__ xsep, int64_t n, float* __restrict__ xout, float* __restrict__ logdet,
                   const float* __restrict__ mean, const float* __restrict__ stdv, const uint8_t* __restrict__ circ,
                   unsigned long long* __restrict__ bad_count) {
@@ -182,10 +182,11 @@ int launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_
 
 template <int K, int H>
 int launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep,
-                   float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
+                   int out_dim, float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
                    unsigned long long* bad, int device, cudaStream_t st) {
-    const int wcount = nf_block_off(fd.d, H, fd.Pp);
-    const int dp = fd.d | 1;
+    const int d_end = sep + out_dim;
+    const int wcount = nf_block_off(d_end, H, fd.Pp);
+    const int dp = d_end | 1;
     const size_t smem = sizeof(float) * ((size_t)wcount + 2 * (size_t)TPB * dp);
     auto kern = nf_inverse_kernel<K, H>;
     if (smem > 48 * 1024) {
@@ -194,7 +195,7 @@ int launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, cons
     }
     const int64_t tiles = (n + TPB - 1) / TPB;
     const int grid = grid_for(kern, smem, tiles, device);
-    kern<<<grid, TPB, smem, st>>>(pk, wcount, fd.d, sep, fd.B, zin, xsep, n, xout, logdet, mean, stdv, circ, bad);
+    kern<<<grid, TPB, smem, st>>>(pk, wcount, d_end, sep, fd.B, zin, xsep, n, xout, logdet, mean, stdv, circ, bad);
     nf_count_launch();
     return nf_check_launch("nf_inverse_kernel");
 }
@@ -213,12 +214,12 @@ int nf_launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int
 }
 
 int nf_launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep,
-                      float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
+                      int out_dim, float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
                       unsigned long long* bad, int device, cudaStream_t st) {
     if (n == 0) return NF_OK;
 #define NF_CASE(KK, HH) \
     if (fd.K == KK && fd.H == HH) \
-        return launch_inverse<KK, HH>(fd, pk, zin, xsep, n, sep, xout, logdet, mean, stdv, circ, bad, device, st);
+        return launch_inverse<KK, HH>(fd, pk, zin, xsep, n, sep, out_dim, xout, logdet, mean, stdv, circ, bad, device, st);
     NF_FOREACH_KH(NF_CASE)
 #undef NF_CASE
     return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");

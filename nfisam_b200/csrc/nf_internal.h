@@ -33,7 +33,7 @@ int nf_sm_count(int device);
 int nf_launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_t n, int d_in, float* z,
                       float* logdet, float* logp, float* ws, int layout, int device, cudaStream_t st);
 int nf_launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep,
-                      float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
+                      int out_dim, float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
                       unsigned long long* bad, int device, cudaStream_t st);
 
 // nf_train_kernel.cu

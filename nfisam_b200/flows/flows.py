@@ -72,6 +72,7 @@ class NSF_AR(nn.Module):
         self._device_index = device
         self._h = None
         self._synced = None
+        self._pending = None
 
     def reset_parameters(self):
         init.uniform_(self.init_param, -1 / 2, 1 / 2)
@@ -184,8 +185,8 @@ class NSF_AR(nn.Module):
         zd = self._in(z)
         n, f = zd.shape
         sep = 0 if x_s is None else int(x_s.shape[1])
-        if sep + f != self.dim:
-            raise ValueError(f"separator dim {sep} + latent dim {f} != flow dim {self.dim}")
+        if sep + f > self.dim:
+            raise ValueError(f"separator dim {sep} + latent dim {f} > flow dim {self.dim}")
         xs = self._in(x_s) if sep else None
         out = torch.empty((n, f), dtype=torch.float32, device=zd.device)
         ld = torch.empty((n,), dtype=torch.float32, device=zd.device) if want_logdet else None
@@ -196,7 +197,7 @@ class NSF_AR(nn.Module):
             keep = (self._in(mean), self._in(std),
                     torch.as_tensor(np.asarray(circ, dtype=np.uint8)).to(self._dev()).contiguous())
             aff = _lib.nf_affine(keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr())
-        _lib.check(lib.nfisam_flow_inverse(h, zd.data_ptr(), xs.data_ptr() if sep else None, n, sep, out.data_ptr(),
+        _lib.check(lib.nfisam_flow_inverse(h, zd.data_ptr(), xs.data_ptr() if sep else None, n, sep, f, out.data_ptr(),
                                            ld.data_ptr() if want_logdet else None,
                                            ctypes.byref(aff) if aff is not None else None, self._stream()))
         bad = ctypes.c_int64(0)
@@ -211,16 +212,17 @@ class NSF_AR(nn.Module):
         return self._inverse(z, None, want_logdet=True)
 
     def inverse_given_separator(self, z, x_s, norm=None):
-        """Frontal block given the (normalised) separator columns, src/flows/flows.py:115-137.
+        """The z.shape[1] columns that follow the given (normalised) separator columns, src/flows/flows.py:115-137
+        (sep + z.shape[1] may be smaller than dim: a prefix of the autoregression).
         norm = (mean, std, circular) fuses the solver's normalise / unnormalise into the kernel."""
         return self._inverse(z, x_s, norm=norm)[0]
 
     # ------------------------------------------------------------------ training on device
-    def fit(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
-            reset_optimizer=True, pull=True):
-        """Full-batch Adam on -mean(log_prob) with the reference's windowed early stop
-        (src/slam/NFiSAM.py:451-491), entirely on the device.  Returns (loss_history, iters_run);
-        loss_history has `iters` entries, zeros after the stop like the reference's iter_loss."""
+    def fit_launch(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
+                   reset_optimizer=True, stream=None):
+        """Enqueue the whole Adam loop (src/slam/NFiSAM.py:451-491) on `stream` (a torch.cuda.Stream, default:
+        the current one) and return immediately; several flows launched on different streams / devices train
+        concurrently.  Call fit_finish() to collect the loss history."""
         lib = _lib.load()
         h = self.handle()
         xd = self._in(data)
@@ -229,13 +231,32 @@ class NSF_AR(nn.Module):
             raise ValueError("training data must have `dim` columns")
         cfg = _lib.nf_train_cfg(int(iters), float(lr), float(betas[0]), float(betas[1]), float(eps),
                                 int(average_window), float(loss_delta_tol), None, 0, 0, 0.0, 1 if reset_optimizer else 0)
-        hist = np.zeros(int(iters), np.float32)
+        st = stream if stream is not None else torch.cuda.current_stream(self._dev())
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(self._dev()))   # data upload happened on the current stream
+        _lib.check(lib.nfisam_flow_train_launch(h, xd.data_ptr(), n, ctypes.byref(cfg), ctypes.c_void_p(st.cuda_stream)))
+        self._pending = (xd, int(iters), st)
+
+    def fit_finish(self, pull=True):
+        """Wait for fit_launch; returns (loss_history, iters_run) -- history has `iters` entries, zeros after the
+        early stop like the reference's preallocated iter_loss."""
+        lib = _lib.load()
+        xd, iters, st = self._pending
+        self._pending = None
+        hist = np.zeros(iters, np.float32)
         ran = ctypes.c_int32(0)
-        _lib.check(lib.nfisam_flow_train(h, xd.data_ptr(), n, ctypes.byref(cfg), hist.ctypes.data_as(ctypes.c_void_p),
-                                         ctypes.byref(ran), self._stream()))
+        _lib.check(lib.nfisam_flow_train_finish(self._h, hist.ctypes.data_as(ctypes.c_void_p), iters, ctypes.byref(ran),
+                                                ctypes.c_void_p(st.cuda_stream)))
         if pull:
             self.pull_parameters()
         return hist, int(ran.value)
+
+    def fit(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
+            reset_optimizer=True, pull=True):
+        """Full-batch Adam on -mean(log_prob) with the reference's windowed early stop, entirely on the device.
+        Returns (loss_history, iters_run)."""
+        self.fit_launch(data, iters, lr, betas, eps, average_window, loss_delta_tol, reset_optimizer)
+        return self.fit_finish(pull=pull)
 
     def loss_and_grad(self, data):
         """-mean(log_prob) and its gradient (flat, state_dict order) at the current parameters."""

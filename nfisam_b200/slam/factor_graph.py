@@ -1,0 +1,88 @@
+"""Factor graph + symbolic elimination into a Bayes tree (reference: src/slam/FactorGraph.py)."""
+from typing import Dict, Iterable, List, Set
+
+from ..factors.factors import Factor
+from .bayes_tree import BayesTree, BayesTreeNode
+from .variables import Variable
+
+
+class FactorGraph:
+    def __init__(self):
+        self._vars: List[Variable] = []
+        self._factors: List[Factor] = []
+        self._neighbors: Dict[Variable, Set[Variable]] = {}
+
+    vars = property(lambda self: self._vars)
+    factors = property(lambda self: self._factors)
+
+    def add_node(self, var: Variable) -> "FactorGraph":
+        if var in self._neighbors:
+            raise KeyError("The node has already existed in the graph")
+        self._vars.append(var)
+        self._neighbors[var] = set()
+        return self
+
+    def add_factor(self, factor: Factor) -> "FactorGraph":
+        self._factors.append(factor)
+        vs = list(factor.vars)
+        for a in vs:
+            for b in vs:
+                if a != b:
+                    self._neighbors[a].add(b)
+        return self
+
+    def get_neighbors_in_factor_graph(self, key: Variable) -> Set[Variable]:
+        return self._neighbors[key]
+
+    def get_bayes_tree(self, ordering: List[Variable]) -> BayesTree:
+        """Symbolic elimination along `ordering`: the separator of a variable is its neighbour set at
+        elimination time, which then becomes a clique (FactorGraph.py:70-92, 172-202)."""
+        adj = {v: set(n) for v, n in self._neighbors.items()}
+        parents = {}
+        for v in ordering:
+            sep = set(adj[v])
+            for u in sep:
+                adj[u].discard(v)
+                adj[u] |= sep - {u}
+            adj[v] = set()
+            parents[v] = sep
+        tree = BayesTree(frontal=ordering[-1])
+        tree.reverse_elimination_order = ordering[::-1]
+        for v in ordering[:-1][::-1]:
+            tree.add_node(frontal=v, parents=parents[v])
+        return tree
+
+    def _subgraph(self, keep_var, keep_factor, extra: Iterable[Factor] = ()) -> "FactorGraph":
+        g = FactorGraph()
+        for v in self._vars:
+            if keep_var(v):
+                g.add_node(v)
+        for f in self._factors:
+            if keep_factor(f):
+                g.add_factor(f)
+        for f in extra:
+            if f is not None:
+                g.add_factor(f)
+        return g
+
+    def get_sub_factor_graph_with_prior(self, variables: Set[Variable], sub_trees: List[BayesTree],
+                                        clique_prior_dict: Dict[BayesTreeNode, Factor]) -> "FactorGraph":
+        """Factors among `variables` that are not already summarised by an untouched subtree, plus the
+        separator factors of those subtrees (FactorGraph.py:204-228)."""
+        roots = [t.root.vars for t in sub_trees]
+
+        def keep(f):
+            fv = set(f.vars)
+            return fv.issubset(variables) and not any(fv.issubset(r) for r in roots)
+
+        return self._subgraph(lambda v: v in variables, keep, [clique_prior_dict[t.root] for t in sub_trees])
+
+    def eliminate_clique_variables(self, clique: BayesTreeNode, new_factor: Factor) -> "FactorGraph":
+        """Drop the clique's frontal variables and every factor inside the clique; add its separator
+        factor (FactorGraph.py:230-247)."""
+        cv = clique.vars
+        return self._subgraph(lambda v: v not in clique.frontal, lambda f: not set(f.vars).issubset(cv), [new_factor])
+
+    def get_clique_factor_graph(self, clique: BayesTreeNode) -> "FactorGraph":
+        cv = clique.vars
+        return self._subgraph(lambda v: v in cv, lambda f: set(f.vars).issubset(cv))

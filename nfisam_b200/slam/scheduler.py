@@ -1,0 +1,223 @@
+"""Clique scheduler: trains mutually independent cliques of the working Bayes tree concurrently.
+
+Replaces the two serial loops of the reference solver (FactorGraphSolver.fit_tree_density_models,
+src/slam/FactorGraphSolver.py:409-477, and sample_posterior, :497-550) with a level-synchronous
+schedule:
+
+  up-pass    levels of the working tree, leaves first.  All cliques of a level only depend on
+             separator factors of lower levels, so they are simulated and trained concurrently:
+             on one GPU every clique's persistent training kernel is enqueued on its own CUDA stream;
+             under torch.distributed (one process per GPU) the cliques of a level are dealt
+             round-robin to the ranks and each owner broadcasts the trained flow (parameters,
+             normalisation, loss curve: a few tens of KB) to the other ranks over NCCL.
+  down-pass  root first: the owner of a clique draws its frontal variables given the separator
+             samples and broadcasts them (n x frontal_dim float32) to the ranks that own the children.
+
+There is no collective on the training data path itself (cliques are independent): NCCL only moves
+parameters up and separator samples down, as the north star prescribes.  With
+`deterministic_cliques` every clique seeds its own RNG streams from (seed, step, clique name), which
+makes the result independent of the number of GPUs.
+"""
+import time
+import zlib
+from typing import List
+
+import numpy as np
+import torch
+
+from .simulation_sampler import SimulationBasedSampler
+
+
+def _clique_name(clique) -> str:
+    return "".join(sorted(str(v.name) for v in clique.frontal)) + "|" + "".join(sorted(str(v.name) for v in clique.separator))
+
+
+class CliqueScheduler:
+    def __init__(self, solver):
+        self.solver = solver
+        self._streams = {}
+
+    # -- distributed plumbing -----------------------------------------------------------------------
+    @property
+    def distributed(self) -> bool:
+        import torch.distributed as dist
+
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _world(self):
+        import torch.distributed as dist
+
+        if self.distributed:
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def _comm_device(self):
+        import torch.distributed as dist
+
+        if self.distributed and dist.get_backend() == "nccl":
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device("cpu")
+
+    def _bcast(self, array: np.ndarray, src: int, dtype=torch.float32) -> np.ndarray:
+        """Broadcast a (pre-shaped) array from rank `src`; every rank passes an array of the same shape."""
+        import torch.distributed as dist
+
+        t = torch.as_tensor(np.ascontiguousarray(array)).to(dtype).to(self._comm_device())
+        dist.broadcast(t, src=src)
+        return t.cpu().numpy()
+
+    def _stream(self, slot: int):
+        if not torch.cuda.is_available():
+            return None                     # host-logic tests with the oracle backend
+        dev = torch.cuda.current_device()
+        key = (dev, slot)
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=dev)
+        return self._streams[key]
+
+    def _seed_for(self, clique, salt: int) -> int:
+        a = self.solver._args
+        return (zlib.crc32(_clique_name(clique).encode()) + 7919 * self.solver._step_counter + 104729 * salt + int(a.seed)) % (2 ** 31 - 1)
+
+    # -- up-pass --------------------------------------------------------------------------------------
+    def fit_tree(self, timer: List[float] = None, clique_dim_timer=None):
+        s = self.solver
+        a = s._args
+        rank, world = self._world()
+        reseed = a.deterministic_cliques or world > 1
+        s._temp_training_loss = {}
+        t_begin = time.time()
+        sim_time, train_time = 0.0, 0.0
+        for level in s._working_bayes_tree.levels():
+            todo = [c for c in level if c not in s._clique_density_model]
+            plans = {}
+            for c in todo:
+                # deterministic part, identical on every rank: which factors the clique consumes (claimed one
+                # clique at a time, so a factor on variables shared by sibling cliques is used exactly once,
+                # as in the reference's serial loop), column order and observation vector
+                graph = s._working_graph.get_clique_factor_graph(c)
+                s._working_graph = s._working_graph.eliminate_clique_variables(clique=c, new_factor=None)
+                pattern = s._working_bayes_tree.clique_variable_pattern(c)
+                sampler = SimulationBasedSampler(factors=graph.factors, vars=pattern)
+                _, var_order, true_obs = sampler.plan()
+                plans[id(c)] = (sampler, var_order, true_obs)
+            mine = [(k, c) for k, c in enumerate(todo) if k % world == rank]
+            launched = []
+            t0 = time.time()
+            for slot, (k, c) in enumerate(mine):
+                sampler, var_order, true_obs = plans[id(c)]
+                if reseed:
+                    seed = self._seed_for(c, 1)
+                    np.random.seed(seed)
+                    torch.manual_seed(seed)
+                samples, _, _ = sampler.sample(a.local_sample_num)
+                if a.store_clique_samples:
+                    s._clique_samples[c] = samples
+                model, data = s._prepare_clique_model(c, samples, var_order)
+                t1 = time.time()
+                sim_time += t1 - t0
+                model.flows[0].fit_launch(data, a.flow_iterations, a.learning_rate, average_window=a.average_window,
+                                          loss_delta_tol=a.loss_delta_tol, stream=self._stream(slot))
+                launched.append((k, c, model))
+                t0 = time.time()
+            results = {}
+            t1 = time.time()
+            for k, c, model in launched:
+                hist, ran = model.flows[0].fit_finish(pull=True)
+                results[k] = (model, hist)
+            train_time += time.time() - t1
+            for k, c in enumerate(todo):
+                sampler, var_order, true_obs = plans[id(c)]
+                owner = k % world
+                if world > 1:
+                    model, hist = self._exchange_model(c, var_order, results.get(k), owner)
+                else:
+                    model, hist = results[k]
+                s._clique_true_obs[c] = true_obs
+                s._record_loss(c, hist)
+                s._finish_clique(c, model, true_obs, already_eliminated=True)
+            if clique_dim_timer is not None:
+                for c in level:
+                    clique_dim_timer.append([c.dim, time.time() - t_begin])
+        if timer is not None:
+            timer.append(sim_time)      # same slots as the reference's [sampler_i, train_i] pairs, aggregated per step
+            timer.append(train_time)
+
+    def _exchange_model(self, clique, var_order, local, owner):
+        """Owner -> everyone: flow parameters, normalisation constants and loss curve of one clique."""
+        from ..flows import NSF_AR, CustomMultivariateNormal
+        from .nfisam import NormalizingFlowModelWithSeparator
+
+        s = self.solver
+        a = s._args
+        rank, world = self._world()
+        d = sum(v.dim for v in var_order)
+        circular = []
+        for v in var_order:
+            circular += v.circular_dim_list
+        if rank == owner:
+            model, hist = local
+            theta = model.flows[0].flat_parameters()
+            payload = np.concatenate([theta, np.asarray(model.samples_mean, np.float32), np.asarray(model.samples_std, np.float32),
+                                      np.asarray(hist, np.float32)])
+        else:
+            flow = NSF_AR(dim=d, K=a.num_knots, hidden_dim=a.hidden_dim, device=a.device)
+            n_theta = flow.flat_parameters().size
+            payload = np.zeros(n_theta + 2 * d + a.flow_iterations, np.float32)
+        payload = self._bcast(payload, owner)
+        if rank == owner:
+            return local
+        theta, rest = payload[:n_theta], payload[n_theta:]
+        flow.load_flat_parameters(theta)
+        sep_dim = d - clique.frontal_dim
+        model = NormalizingFlowModelWithSeparator([flow], CustomMultivariateNormal(dim=d),
+                                                  CustomMultivariateNormal(dim=sep_dim) if sep_dim > 0 else None, circular,
+                                                  torch.tensor(rest[:d]), torch.tensor(rest[d:2 * d]))
+        return model, rest[2 * d:]
+
+    # -- down-pass ------------------------------------------------------------------------------------
+    def sample_posterior(self, timer: List[float] = None):
+        """Root -> leaves with per-clique seeded latent draws; under torch.distributed the owner of a clique
+        draws and broadcasts its frontal samples (the separator samples of its children)."""
+        s = self.solver
+        a = s._args
+        n = a.posterior_sample_num
+        rank, world = self._world()
+        start = time.time()
+        samples = {}
+        queue = [s._physical_bayes_tree.root]
+        k = 0
+        while queue:
+            clique = queue.pop(0)
+            frontal = sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v])
+            separator = sorted(clique.separator, key=lambda v: s._reverse_ordering_map[v])
+            model = s._clique_density_model[clique]
+            owner = zlib.crc32(_clique_name(clique).encode()) % world
+            if rank == owner:
+                obs = s._clique_true_obs[clique]
+                blocks = [np.tile(obs, (n, 1))] if len(obs) else []
+                blocks += [samples[v] for v in separator]
+                gen = torch.Generator()
+                gen.manual_seed(self._seed_for(clique, 2))
+                model.rng = gen
+                try:
+                    if blocks:
+                        drawn = model.conditional_sample_given_observation(conditional_dim=clique.frontal_dim,
+                                                                           obs_samples=np.hstack(blocks))
+                    else:
+                        drawn = model.conditional_sample_given_observation(conditional_dim=clique.frontal_dim, sample_number=n)
+                finally:
+                    model.rng = None
+            else:
+                drawn = np.zeros((n, clique.frontal_dim), np.float32)
+            if world > 1:
+                drawn = self._bcast(drawn, owner)
+            col = 0
+            for v in frontal:
+                samples[v] = drawn[:, col:col + v.dim]
+                col += v.dim
+            queue.extend(clique.children)
+            k += 1
+        if timer is not None:
+            timer.append(time.time() - start)
+        return samples

@@ -233,7 +233,7 @@ def test_host_buffer_api_matches_device_api(flow_cases):
     ref = f.inverse_given_separator(torch.tensor(z), torch.tensor(xs)).numpy()
     o2 = np.empty((n, 6), np.float32)
     _lib.check(_lib.load().nfisam_flow_inverse_host(f.handle(), z.ctypes.data_as(ctypes.c_void_p),
-                                                    xs.ctypes.data_as(ctypes.c_void_p), n, 5,
+                                                    xs.ctypes.data_as(ctypes.c_void_p), n, 5, 6,
                                                     o2.ctypes.data_as(ctypes.c_void_p), None, None, None))
     assert np.array_equal(o2, ref)
 
