@@ -28,10 +28,10 @@ from factors.Factors import BinaryFactorMixture  # noqa: E402
 ITERS = 600
 
 
-def run(case):
-    random.seed(0)
-    np.random.seed(0)
-    torch.manual_seed(0)
+def run(case, seed=0):
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
     nodes, truth, factors = graph_file_parser(os.path.join(HERE, "..", "data", case + ".fg"), "fg", 0.1)
     steps = group_nodes_factors_incrementally(nodes=nodes, factors=factors, incremental_step=1)
     args = NFiSAMArgs(num_knots=9, flow_iterations=ITERS, local_sample_num=2000, learning_rate=.025, hidden_dim=8,
@@ -61,9 +61,11 @@ def run(case):
         if mixtures:
             out[f"step{i}_hypo"] = np.array([f.posterior_weights(cur) for f in mixtures if set(f.vars).issubset(cur.keys())])
         print(case, "step", i, "%.1f s" % (time.time() - t0), [round(t, 2) for t in timer], flush=True)
-    np.savez_compressed(os.path.join(HERE, f"solve_{case}.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, f"solve_{case}.npz" if seed == 0 else f"solve_{case}_seed{seed}.npz"), **out)
 
 
 if __name__ == "__main__":
-    for case in sys.argv[1:] or ["small_case1", "small_case1_da"]:
-        run(case)
+    # `case` or `case:seed`; a second seed of the same case calibrates the reference's own run-to-run spread
+    for spec in sys.argv[1:] or ["small_case1", "small_case1_da", "small_case1:1"]:
+        case, _, seed = spec.partition(":")
+        run(case, int(seed or 0))

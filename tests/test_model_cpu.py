@@ -1,0 +1,68 @@
+"""Host-side parity of the solver-facing wrapper against the reference's own outputs (tests/golden/model.npz):
+parameter initialisation draw-for-draw, training-sample normalisation, and -- through the oracle backend --
+the RNG consumption / column slicing of conditional sampling.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.oracle_backend import oracle_backend
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def g():
+    return dict(np.load(os.path.join(HERE, "golden", "model.npz")))
+
+
+def test_initialisation_matches_reference_draw_for_draw(g):
+    from nfisam_b200.flows import NSF_AR
+
+    for (d, K, H, seed) in ((5, 9, 8, 11), (14, 12, 8, 12)):
+        torch.manual_seed(seed)
+        f = NSF_AR(dim=d, K=K, hidden_dim=H)
+        assert np.array_equal(f.flat_parameters(), g[f"init_d{d}_K{K}_H{H}_s{seed}"])
+
+
+def test_normalize_training_samples(g):
+    from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
+
+    data, means, stds = NFiSAM(NFiSAMArgs()).normalize_training_samples(g["norm_raw"].copy(), list(g["norm_circ"]), "NSF_AR")
+    assert np.array_equal(means.numpy(), g["norm_means"]) and np.array_equal(stds.numpy(), g["norm_stds"])
+    assert np.array_equal(data.numpy(), g["norm_data"])
+    assert stds.numpy()[6] == np.float32(1e-5)                  # clipped std of the collapsed column
+
+
+def build_model(g):
+    from nfisam_b200.flows import NSF_AR, CustomMultivariateNormal
+    from nfisam_b200.slam.nfisam import NormalizingFlowModelWithSeparator
+
+    d = 9
+    flow = NSF_AR(dim=d, K=9, hidden_dim=8)
+    flow.load_flat_parameters(g["wrap_theta"])
+    return NormalizingFlowModelWithSeparator([flow], CustomMultivariateNormal(dim=d), CustomMultivariateNormal(dim=6),
+                                             list(g["norm_circ"]), torch.tensor(g["norm_means"]), torch.tensor(g["norm_stds"]))
+
+
+def check_wrapper(g, rtol):
+    model = build_model(g)
+    torch.manual_seed(21)
+    got = model.conditional_sample_given_observation(conditional_dim=3, obs_samples=g["wrap_obs"].copy())
+    assert got.dtype == np.float32 and np.allclose(got, g["wrap_cond"], rtol=rtol, atol=2e-4)
+    torch.manual_seed(22)
+    got = model.conditional_sample_given_observation(conditional_dim=2, obs_samples=g["wrap_obs"][:, :4].copy())
+    assert np.allclose(got, g["wrap_cond_prefix"], rtol=rtol, atol=2e-4)
+    torch.manual_seed(23)
+    got = model.conditional_sample_given_observation(conditional_dim=5, sample_number=32)
+    assert np.allclose(got, g["wrap_uncond"], rtol=rtol, atol=2e-4)
+    z, plp, ld = model.separator_forward(torch.tensor(np.float32(g["wrap_obs"])))
+    assert np.allclose(z.numpy(), g["wrap_sepfwd_z"], rtol=rtol, atol=1e-4)
+    assert np.allclose(plp.numpy(), g["wrap_sepfwd_plp"], rtol=rtol, atol=1e-3)
+    assert np.allclose(ld.numpy(), g["wrap_sepfwd_ld"], rtol=rtol, atol=1e-3)
+
+
+def test_wrapper_host_logic_with_oracle_backend(g):
+    with oracle_backend():
+        check_wrapper(g, rtol=1e-4)

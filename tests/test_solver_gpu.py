@@ -1,0 +1,134 @@
+"""GPU tests of the solver-facing layer: wrapper parity with the reference's outputs (same weights, same
+torch seed => same draws), and full incremental solves compared with posterior samples of the REFERENCE
+solver (tests/golden/solve_*.npz, tests/golden/make_solve_golden.py).
+
+Posterior tolerance (Monte-Carlo + model-fitting variance: two runs of the REFERENCE with different seeds
+differ by up to 0.52 sigma on pose means, 1.3 sigma on landmark means and 1.8x on stds,
+tests/golden/solve_small_case1_seed1.npz): per-variable mean within 0.75 sigma_ref + 0.5 (poses) /
+1.5 sigma_ref + 0.5 (landmarks) of the reference's mean, std ratio within [0.4, 2.5]; the biased MMD (RBF kernel,
+sigma = sqrt(dim), the reference's post-processing metric) between our samples and the reference's is
+reported and bounded."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.test_model_cpu import check_wrapper
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def mmd_b(x, y, sigma):
+    """Biased MMD^2 estimate with an RBF kernel (reference: src/utils/Statistics.py:68-84)."""
+    def k(a, b):
+        d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2 * a @ b.T
+        return np.exp(-d2 / (2 * sigma * sigma))
+    return float(np.sqrt(max(k(x, x).mean() + k(y, y).mean() - 2 * k(x, y).mean(), 0.0)))
+
+
+def test_wrapper_matches_reference_outputs():
+    g = dict(np.load(os.path.join(HERE, "golden", "model.npz")))
+    check_wrapper(g, rtol=2e-5)
+
+
+def solve(case, **kw):
+    from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
+    from nfisam_b200.slam.run_batch import graph_file_parser, group_nodes_factors_incrementally
+
+    nodes, truth, factors = graph_file_parser(os.path.join(HERE, "data", case + ".fg"))
+    steps = group_nodes_factors_incrementally(nodes, factors, incremental_step=1)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    args = dict(num_knots=9, flow_iterations=600, local_sample_num=2000, learning_rate=.025, hidden_dim=8,
+                elimination_method="pose_first", loss_delta_tol=.01, posterior_sample_num=1000)
+    args.update(kw)
+    solver = NFiSAM(NFiSAMArgs(**args))
+    per_step = []
+    for sn, sf in steps:
+        for v in sn:
+            solver.add_node(v)
+        for f in sf:
+            solver.add_factor(f)
+        timer = []
+        solver.update_physical_and_working_graphs(timer=timer)
+        cur = solver.incremental_inference(timer=timer)
+        order = solver.elimination_ordering
+        per_step.append(([v.name for v in order], np.hstack([cur[v] for v in order]), timer, solver))
+    return per_step
+
+
+@pytest.mark.parametrize("case", ["small_case1", "small_case1_da"])
+def test_incremental_solve_matches_reference_posterior(case):
+    path = os.path.join(HERE, "golden", f"solve_{case}.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden posterior not generated")
+    g = dict(np.load(path))
+    steps = solve(case)
+    report = []
+    for i, (names, x, timer, solver) in enumerate(steps):
+        ref = g[f"step{i}_samples"]
+        assert names == list(g[f"step{i}_order"])
+        assert x.shape == ref.shape
+        tree = sorted("".join(sorted(v.name for v in c.frontal)) + "|" + "".join(sorted(v.name for v in c.separator))
+                      for c in solver.physical_bayes_tree.clique_nodes)
+        if i == len(steps) - 1:
+            assert tree == list(g[f"step{i}_tree"]), (tree, list(g[f"step{i}_tree"]))
+        m, mr = x.mean(0), ref.mean(0)
+        s, sr = x.std(0), ref.std(0)
+        # Range-only landmark marginals are multi-modal (mirror solutions) until enough poses have seen them:
+        # compare means / stds per VARIABLE only where the reference's own marginal is concentrated (every dim
+        # std < 5); the multi-modal ones are covered by the MMD below.
+        col = 0
+        for nm in names:
+            w = 2 if nm.startswith("L") else 3
+            sl = slice(col, col + w)
+            col += w
+            if np.all(sr[sl] < 5.0):
+                # calibrated on two runs of the REFERENCE itself (seeds 0 / 1, tests/golden/solve_small_case1*.npz):
+                # pose means differ by up to 0.52 sigma, landmark means by up to 1.3 sigma, std ratios reach 1.8
+                tol = (1.5 if nm.startswith("L") else 0.75) * sr[sl] + 0.5
+                assert np.all(np.abs(m[sl] - mr[sl]) <= tol), (i, nm, m[sl], mr[sl], tol)
+                ratio = s[sl] / np.maximum(sr[sl], 1e-9)
+                assert np.all((ratio > 0.4) & (ratio < 2.5)), (i, nm, s[sl], sr[sl])
+        d = x.shape[1]
+        report.append(mmd_b(x[:500].astype(np.float64), ref[:500].astype(np.float64), np.sqrt(d)))
+    print(f"\n[{case}] joint MMD_b vs reference per step:", np.round(report, 4))
+    # the reference's own run-to-run MMD against a nested-sampling posterior is .015-.125
+    assert max(report) < 0.25, report
+
+
+def test_clique_parallel_equals_serial_loop_statistically():
+    """Level-synchronous schedule on streams vs the serial reference-order loop: same posterior up to MC noise."""
+    a = solve("small_case1", flow_iterations=300, clique_parallel=True)[-1][1]
+    b = solve("small_case1", flow_iterations=300, clique_parallel=False)[-1][1]
+    assert np.all(np.abs(a.mean(0) - b.mean(0)) < np.maximum(0.25 * b.std(0) + 0.5, 0.1))
+
+
+def test_multi_robot_graph_runs_cliques_concurrently():
+    from nfisam_b200 import _lib
+    from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
+    from nfisam_b200.slam.run_batch import group_nodes_factors_incrementally
+    from nfisam_b200.slam.synthetic import make_manhattan_range_graph
+
+    nodes, truth, factors = make_manhattan_range_graph(robots=4, poses=4, landmarks=3, seed=2)
+    steps = group_nodes_factors_incrementally(nodes, factors, incremental_step=1)
+    np.random.seed(1)
+    torch.manual_seed(1)
+    solver = NFiSAM(NFiSAMArgs(num_knots=9, flow_iterations=200, local_sample_num=1000, learning_rate=.02,
+                               posterior_sample_num=500, deterministic_cliques=True))
+    widths = []
+    for sn, sf in steps:
+        for v in sn:
+            solver.add_node(v)
+        for f in sf:
+            solver.add_factor(f)
+        solver.update_physical_and_working_graphs()
+        widths.append(max(len(l) for l in solver.working_bayes_tree.levels()))
+        cur = solver.incremental_inference()
+    assert max(widths) >= 4
+    for var, val in truth.items():
+        if var.type.value == "Pose":
+            assert np.linalg.norm(cur[var].mean(0)[:2] - val[:2]) < 5.0, (var.name, cur[var].mean(0), val)
+    assert _lib.launch_count() > 0
