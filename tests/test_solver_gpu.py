@@ -95,8 +95,19 @@ def test_incremental_solve_matches_reference_posterior(case):
         d = x.shape[1]
         report.append(mmd_b(x[:500].astype(np.float64), ref[:500].astype(np.float64), np.sqrt(d)))
     print(f"\n[{case}] joint MMD_b vs reference per step:", np.round(report, 4))
-    # the reference's own run-to-run MMD against a nested-sampling posterior is .015-.125
-    assert max(report) < 0.25, report
+    # calibration: two runs of the REFERENCE itself (seeds 0 / 1) are 0.06-0.30 apart in this metric
+    # (small_case1: .063 .064 .066 .145 .300 .295; small_case1_da: .063 .064 .077 .084 .201 .246)
+    assert max(report) < 0.35, report
+    if "step5_hypo" in g:
+        # data-association hypothesis weights after the last step agree with the reference's
+        from nfisam_b200.factors import BinaryFactorMixture
+
+        solver = steps[-1][3]
+        cur = solver._samples
+        mix = [f for f in solver.physical_factors if isinstance(f, BinaryFactorMixture)]
+        w = np.array([f.posterior_weights(cur) for f in mix])
+        print("hypothesis weights:", np.round(w, 3).tolist(), "reference:", np.round(g["step5_hypo"], 3).tolist())
+        assert np.all(np.abs(w - g["step5_hypo"]) < 0.15)
 
 
 def test_clique_parallel_equals_serial_loop_statistically():
