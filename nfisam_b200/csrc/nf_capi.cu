@@ -92,10 +92,14 @@ struct nf_flow {
     uint8_t* d_circ = nullptr;
 };
 
+// packed column of conditioner output p (reference order: K widths, K heights, K-1 derivatives):
+// widths and heights are interleaved, (uw_0, uh_0, uw_1, uh_1, ...), derivatives follow (nf_common.cuh)
+static inline int packed_col(int p, int K) { return p < K ? 2 * p : (p < 2 * K ? 2 * (p - K) + 1 : p); }
+
 static void build_index_map(nf_flow* f) {
     const int d = f->fd.d, K = f->fd.K, H = f->fd.H, P = f->fd.P, Pp = f->fd.Pp;
     f->pk2th.assign((size_t)f->n_packed, -1);
-    for (int p = 0; p < P; ++p) f->pk2th[p] = p;
+    for (int p = 0; p < P; ++p) f->pk2th[packed_col(p, K)] = p;
     int64_t th = P;
     for (int i = 1; i < d; ++i) {
         const int off = nf_block_off(i, H, Pp);
@@ -111,12 +115,11 @@ static void build_index_map(nf_flow* f) {
         for (int j = 0; j < H; ++j) f->pk2th[ob2 + j] = (int32_t)(th + j);
         th += H;
         for (int p = 0; p < P; ++p)
-            for (int k = 0; k < H; ++k) f->pk2th[oW3 + k * Pp + p] = (int32_t)(th + p * H + k);
+            for (int k = 0; k < H; ++k) f->pk2th[oW3 + k * Pp + packed_col(p, K)] = (int32_t)(th + p * H + k);
         th += (int64_t)P * H;
-        for (int p = 0; p < P; ++p) f->pk2th[ob3 + p] = (int32_t)(th + p);
+        for (int p = 0; p < P; ++p) f->pk2th[ob3 + packed_col(p, K)] = (int32_t)(th + p);
         th += P;
     }
-    (void)K;
 }
 
 extern "C" {
@@ -242,16 +245,16 @@ int nfisam_flow_forward(nf_flow_t* f, const float* x_dev, int64_t n, int d_in, f
     if (layout != 0 && layout != 1) return nf_set_error(NF_ERR_BAD_ARG, "layout must be 0 or 1");
     if (layout == 1 && logdet_dev && !ws_dev) return nf_set_error(NF_ERR_BAD_ARG, "layout 1 with logdet needs ws_dev");
     DeviceGuard g(f->device);
-    return nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, z_dev, logdet_dev, nullptr, ws_dev, layout, f->device,
-                             (cudaStream_t)stream);
+    return nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, z_dev, logdet_dev,
+                             nullptr, ws_dev, layout, f->device, (cudaStream_t)stream);
 }
 
 int nfisam_flow_log_prob(nf_flow_t* f, const float* x_dev, int64_t n, int d_in, float* logp_dev, void* stream) {
     if (!f || ((!x_dev || !logp_dev) && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
     if (n < 0 || d_in < 1 || d_in > f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / d_in");
     DeviceGuard g(f->device);
-    return nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, nullptr, nullptr, logp_dev, nullptr, 0, f->device,
-                             (cudaStream_t)stream);
+    return nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, nullptr, nullptr,
+                             logp_dev, nullptr, 0, f->device, (cudaStream_t)stream);
 }
 
 int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim, int out_dim,
@@ -316,8 +319,8 @@ int nfisam_flow_log_prob_host(nf_flow_t* f, const float* x_host, int64_t n, int 
         const int64_t m = n - o < chunk ? n - o : chunk;
         cudaStream_t st = f->streams[s];
         NF_CUDA(cudaMemcpyAsync(f->d_stage_in[s], x_host + o * d_in, sizeof(float) * (size_t)m * d_in, cudaMemcpyHostToDevice, st));
-        rc = nf_launch_forward(f->fd, f->d_pk, f->d_stage_in[s], m, d_in, nullptr, nullptr, f->d_stage_out[s], nullptr, 0,
-                               f->device, st);
+        rc = nf_launch_forward(f->fd, f->d_pk, f->d_stage_in[s], m, d_in, nullptr,
+                               nullptr, f->d_stage_out[s], nullptr, 0, f->device, st);
         if (rc != NF_OK) return rc;
         NF_CUDA(cudaMemcpyAsync(logp_host + o, f->d_stage_out[s], sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost, st));
     }

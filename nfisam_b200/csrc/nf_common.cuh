@@ -123,14 +123,33 @@ __device__ __forceinline__ float nf_sigmoid_sp(float v) {
 // 1e-3 + softplus(NF_EDGE_CONST) in float32, the reference's boundary derivative (0.99999994)
 #define NF_EDGE_DERIV 0.99999994f
 
-// packed dual-FP32 FMA (fma.rn.f32x2, new on sm_100): halves the issue slots of the MLP inner products
+// packed dual-FP32 arithmetic (fma/add/mul.rn.f32x2, new on sm_100): halves the issue slots
 __device__ __forceinline__ float2 nf_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 nf_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 nf_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 nf_dup(float v) { return make_float2(v, v); }
+
+// two tanh at once: 3 packed FP32 ops + 4 MUFU
+__device__ __forceinline__ float2 nf_tanh2(float2 a) {
+#if NF_ACCURATE_MATH
+    return make_float2(tanhf(a.x), tanhf(a.y));
+#else
+    const float2 t = nf_mul2(a, nf_dup(2.8853900817779268f));
+    const float2 d = nf_add2(make_float2(nf_ex2(t.x), nf_ex2(t.y)), nf_dup(1.0f));
+    return nf_fma2(nf_dup(-2.0f), make_float2(nf_rcp(d.x), nf_rcp(d.y)), nf_dup(1.0f));
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // Conditioner MLP, evaluated by one thread for one sample.  `w` points at block i (i >= 1) in
 // shared memory, `xrow` at the sample's inputs (shared memory, unit stride).  Outputs are produced
 // two at a time: one float4 shared-memory broadcast feeds two FFMA2 whose second operand is the
-// duplicated input.
+// (scalar-broadcast) input.
+//
+// Output order of the last layer (= column order of W3t / b3 in the packed layout):
+//     (uw_0, uh_0), (uw_1, uh_1), ..., (uw_{K-1}, uh_{K-1}), ud_0 .. ud_{K-2}, padding
+// i.e. unnormalised bin widths and heights are INTERLEAVED so that both softmax / cumsum chains run
+// as the two lanes of packed f32x2 instructions.
 // ---------------------------------------------------------------------------------------------
 template <int NOUT>
 __device__ __forceinline__ void nf_load_bias(const float* __restrict__ b, float2 (&acc)[NOUT / 2]) {
@@ -163,121 +182,148 @@ __device__ __forceinline__ void nf_mlp_hidden(const float* __restrict__ w, int i
     nf_load_bias<H>(b1, a);
     for (int k = 0; k < i; ++k) nf_axpy_row<H>(W1t + k * H, xrow[k], a);
 #pragma unroll
-    for (int j = 0; j < H / 2; ++j) { h1[2 * j] = nf_tanh(a[j].x); h1[2 * j + 1] = nf_tanh(a[j].y); }
+    for (int j = 0; j < H / 2; ++j) { const float2 t = nf_tanh2(a[j]); h1[2 * j] = t.x; h1[2 * j + 1] = t.y; }
     nf_load_bias<H>(b2, a);
 #pragma unroll
     for (int k = 0; k < H; ++k) nf_axpy_row<H>(W2t + k * H, h1[k], a);
 #pragma unroll
-    for (int j = 0; j < H / 2; ++j) { h2[2 * j] = nf_tanh(a[j].x); h2[2 * j + 1] = nf_tanh(a[j].y); }
+    for (int j = 0; j < H / 2; ++j) { const float2 t = nf_tanh2(a[j]); h2[2 * j] = t.x; h2[2 * j + 1] = t.y; }
 }
 
-// Output layer: out[0..Pp) = b3 + W3 h2   (entries >= 3K-1 are padding and stay 0).
+// Output layer: out2[0..Pp/2) = b3 + W3 h2 in the interleaved order above (padding entries stay 0).
 template <int H, int PP>
-__device__ __forceinline__ void nf_mlp_out(const float* __restrict__ w, int i, const float (&h2)[H], float (&out)[PP]) {
+__device__ __forceinline__ void nf_mlp_out(const float* __restrict__ w, int i, const float (&h2)[H], float2 (&out2)[PP / 2]) {
     const float* W3t = w + i * H + H + H * H + H;
     const float* b3 = W3t + H * PP;
-    float2 acc[PP / 2];
-    nf_load_bias<PP>(b3, acc);
+    nf_load_bias<PP>(b3, out2);
 #pragma unroll
-    for (int k = 0; k < H; ++k) nf_axpy_row<PP>(W3t + k * PP, h2[k], acc);
-#pragma unroll
-    for (int p = 0; p < PP / 2; ++p) { out[2 * p] = acc[p].x; out[2 * p + 1] = acc[p].y; }
+    for (int k = 0; k < H; ++k) nf_axpy_row<PP>(W3t + k * PP, h2[k], out2);
 }
 
 // Conditioner outputs for dim i (i = 0 reads init_param).
 template <int K, int H>
 __device__ __forceinline__ void nf_conditioner(const float* __restrict__ wbase, int i, const float* __restrict__ xrow,
-                                               float (&out)[((3 * K - 1) + 3) & ~3]) {
+                                               float2 (&out2)[(((3 * K - 1) + 3) & ~3) / 2]) {
     constexpr int PP = ((3 * K - 1) + 3) & ~3;
     if (i == 0) {
-#pragma unroll
-        for (int p = 0; p < PP; p += 4) {
-            float4 b = *reinterpret_cast<const float4*>(wbase + p);
-            out[p] = b.x; out[p + 1] = b.y; out[p + 2] = b.z; out[p + 3] = b.w;
-        }
+        nf_load_bias<PP>(wbase, out2);
         return;
     }
     const float* w = wbase + nf_block_off(i, H, PP);
     float h1[H], h2[H];
     nf_mlp_hidden<H>(w, i, xrow, h1, h2);
-    nf_mlp_out<H, PP>(w, i, h2, out);
+    nf_mlp_out<H, PP>(w, i, h2, out2);
+}
+
+// unnormalised derivative parameter ud_j (j = 0..K-2) inside the interleaved output vector
+template <int K, int NP>
+__device__ __forceinline__ float nf_ud(const float2 (&out2)[NP], int j) {
+    const int f = 2 * K + j;
+    return (f & 1) ? out2[f / 2].y : out2[f / 2].x;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Spline pieces.  u[K] unnormalised bin sizes -> knots c[0..K] on [-B, B] (ends pinned) and, if
-// wanted, the softmax probabilities p[K].   src/flows/utils.py:85-92 / 96-103
+// Spline pieces (src/flows/utils.py:85-121).  Both knot vectors at once: c[k] = (cw_k, ch_k) on
+// [-B, B] with pinned ends.  With S_k the inclusive prefix sums of e_j = exp(u_j - max u):
+//     c_k = 2B (1e-3 k + (1 - 1e-3 K) S_{k-1} / S_{K-1}) - B
+// which is the reference's cumsum of (1e-3 + (1 - 1e-3 K) softmax) up to rounding order.
+// p[k] (softmax probabilities, both lanes) is produced only for the backward pass.
 // ---------------------------------------------------------------------------------------------
-template <int K, bool KEEP_P>
-__device__ __forceinline__ void nf_knots(const float* u, float B, float (&c)[K + 1], float (&p)[K]) {
-    float m = u[0];
+template <int K, bool KEEP_P, int NP>
+__device__ __forceinline__ void nf_knots2(const float2 (&out2)[NP], float B, float2 (&c)[K + 1], float2 (&p)[K]) {
+    float mw = out2[0].x, mh = out2[0].y;
 #pragma unroll
-    for (int k = 1; k < K; ++k) m = fmaxf(m, u[k]);
-    float e[K];
-    float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) { e[k] = nf_exp(u[k] - m); s += e[k]; }
-    const float inv = nf_rcp(s);
-    const float scale = (float)(1.0 - 1e-3 * (double)K);
-    float acc = 0.0f;
-    c[0] = -B;
+    for (int k = 1; k < K; ++k) { mw = fmaxf(mw, out2[k].x); mh = fmaxf(mh, out2[k].y); }
+    const float L2E = 1.4426950408889634f;
+    const float2 nm = make_float2(-mw * L2E, -mh * L2E);
+    float2 e[K], pre[K];
+    float2 S = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const float pk = e[k] * inv;
-        if (KEEP_P) p[k] = pk;
-        acc += NF_MIN_BIN + scale * pk;
-        c[k + 1] = fmaf(2.0f * B, acc, -B);
+#if NF_ACCURATE_MATH
+        e[k] = make_float2(expf(out2[k].x - mw), expf(out2[k].y - mh));
+#else
+        const float2 t = nf_fma2(out2[k], nf_dup(L2E), nm);
+        e[k] = make_float2(nf_ex2(t.x), nf_ex2(t.y));
+#endif
+        S = nf_add2(S, e[k]);
+        pre[k] = S;
     }
-    c[K] = B;
-}
-
-// bin = #(v >= knot) - 1 with the last knot nudged by 1e-6 (src/flows/utils.py:17-22), clamped.
-template <int K>
-__device__ __forceinline__ int nf_search(const float (&c)[K + 1], float v) {
-    int cnt = 0;
+    const float2 inv = make_float2(nf_rcp(S.x), nf_rcp(S.y));
+    const float scale2B = 2.0f * B * (float)(1.0 - 1e-3 * (double)K);
+    const float2 A = nf_mul2(inv, nf_dup(scale2B));
+    c[0] = nf_dup(-B);
+    c[K] = nf_dup(B);
 #pragma unroll
-    for (int k = 0; k < K; ++k) cnt += (v >= c[k]) ? 1 : 0;
-    cnt += (v >= c[K] + 1e-6f) ? 1 : 0;
-    int b = cnt - 1;
-    b = b < 0 ? 0 : b;
-    b = b > K - 1 ? K - 1 : b;
-    return b;
+    for (int k = 1; k < K; ++k) c[k] = nf_fma2(pre[k - 1], A, nf_dup(2.0f * B * NF_MIN_BIN * (float)k - B));
+    if (KEEP_P) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) p[k] = nf_mul2(e[k], inv);
+    }
 }
 
+// Everything the rational-quadratic segment containing the input needs, found by two predicated
+// scans over the knots instead of an integer bin search + gathers (src/flows/utils.py:17-22, 105-121):
+// (v >= knot_k) is monotone in k and the bin is the last k for which it holds.  The comparisons are
+// recomputed where they are needed (one FSETP each) rather than kept live: only 7 predicate registers exist.
 template <int K>
-__device__ __forceinline__ void nf_select2(const float (&c)[K + 1], int bin, float& lo, float& hi) {
-    lo = c[0]; hi = c[1];
+struct NfSeg {
+    float2 lo, hi;     // (x_k, y_k), (x_{k+1}, y_{k+1})
+    float uk, uk1;     // unnormalised derivative parameters at the two knots (edge constant at the ends)
+    bool first, last;  // bin == 0, bin == K-1
+};
+
+template <int K, bool ON_HEIGHTS>
+__device__ __forceinline__ bool nf_ge(const float2 (&c)[K + 1], float v, int k) {
+    return ON_HEIGHTS ? (v >= c[k].y) : (v >= c[k].x);
+}
+
+template <int K, bool ON_HEIGHTS, int NP>
+__device__ __forceinline__ void nf_locate(const float2 (&c)[K + 1], const float2 (&out2)[NP], float v, NfSeg<K>& sg) {
+    sg.lo = c[0];
+    sg.uk = NF_EDGE_CONST;
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-        if (bin == k) { lo = c[k]; hi = c[k + 1]; }
+        const bool ge = nf_ge<K, ON_HEIGHTS>(c, v, k);
+        sg.lo.x = ge ? c[k].x : sg.lo.x;
+        sg.lo.y = ge ? c[k].y : sg.lo.y;
+        sg.uk = ge ? nf_ud<K>(out2, k - 1) : sg.uk;
     }
-}
-
-// derivatives at knots bin and bin+1: 1e-3 + softplus(ud[bin-1]) / boundary value at the ends.
-template <int K>
-__device__ __forceinline__ void nf_derivs(const float* ud, int bin, float& dk, float& dk1, float& uk, float& uk1) {
-    uk = NF_EDGE_CONST; uk1 = NF_EDGE_CONST;
+    sg.hi = c[K];
+    sg.uk1 = NF_EDGE_CONST;
 #pragma unroll
-    for (int k = 1; k < K; ++k) {
-        if (bin == k) uk = ud[k - 1];
-        if (bin + 1 == k) uk1 = ud[k - 1];
+    for (int k = K - 1; k >= 1; --k) {
+        const bool ge = nf_ge<K, ON_HEIGHTS>(c, v, k);
+        sg.hi.x = ge ? sg.hi.x : c[k].x;
+        sg.hi.y = ge ? sg.hi.y : c[k].y;
+        sg.uk1 = ge ? sg.uk1 : nf_ud<K>(out2, k - 1);
     }
-    dk = bin == 0 ? NF_EDGE_DERIV : NF_MIN_DERIV + nf_softplus(uk);
-    dk1 = bin == K - 1 ? NF_EDGE_DERIV : NF_MIN_DERIV + nf_softplus(uk1);
+    sg.first = !nf_ge<K, ON_HEIGHTS>(c, v, 1);
+    sg.last = nf_ge<K, ON_HEIGHTS>(c, v, K - 1);
 }
 
-// Forward spline for one value. out = [uw(K) | uh(K) | ud(K-1)].   src/flows/utils.py:148-164
 template <int K>
-__device__ __forceinline__ float nf_rqs_forward(const float* out, float B, float x, float& ld) {
-    if (!(x >= -B && x <= B)) { ld = 0.0f; return x; }
-    float cw[K + 1], chh[K + 1], dummy[K];
-    nf_knots<K, false>(out, B, cw, dummy);
-    const int bin = nf_search<K>(cw, x);
-    float xk, xk1, yk, yk1, dk, dk1, uk, uk1;
-    nf_select2<K>(cw, bin, xk, xk1);
-    nf_knots<K, false>(out + K, B, chh, dummy);
-    nf_select2<K>(chh, bin, yk, yk1);
-    nf_derivs<K>(out + 2 * K, bin, dk, dk1, uk, uk1);
-    const float wk = xk1 - xk, hk = yk1 - yk;
+__device__ __forceinline__ void nf_seg_derivs(const NfSeg<K>& sg, float& dk, float& dk1) {
+    // at the pinned end knots the derivative is the reference's boundary constant
+    dk = sg.first ? NF_EDGE_DERIV : NF_MIN_DERIV + nf_softplus(sg.uk);
+    dk1 = sg.last ? NF_EDGE_DERIV : NF_MIN_DERIV + nf_softplus(sg.uk1);
+}
+
+// Forward spline for one value.   src/flows/utils.py:148-164
+template <int K, int NP>
+__device__ __forceinline__ float nf_rqs_forward(const float2 (&out2)[NP], float B, float xin, float& ld) {
+    // branch-free: values outside [-B, B] (linear tails: identity, log-det 0) run the spline on a dummy
+    // in-range value and are patched by selects at the end, so that independent samples interleave
+    const bool inside = (xin >= -B && xin <= B);
+    const float x = inside ? xin : 0.0f;
+    float2 c[K + 1], dummy[K];
+    nf_knots2<K, false>(out2, B, c, dummy);
+    NfSeg<K> sg;
+    nf_locate<K, false>(c, out2, x, sg);
+    float dk, dk1;
+    nf_seg_derivs<K>(sg, dk, dk1);
+    const float xk = sg.lo.x, yk = sg.lo.y;
+    const float wk = sg.hi.x - xk, hk = sg.hi.y - yk;
     const float rw = nf_rcp(wk);
     const float delta = hk * rw;
     const float th = (x - xk) * rw;
@@ -287,45 +333,48 @@ __device__ __forceinline__ float nf_rqs_forward(const float* out, float B, float
     const float omt = 1.0f - th;
     const float dnum = delta * delta * (dk1 * th * th + 2.0f * delta * t1 + dk * omt * omt);
 #if NF_ACCURATE_MATH
-    ld = logf(dnum) - 2.0f * logf(den);
+    const float l = logf(dnum) - 2.0f * logf(den);
 #else
-    ld = 0.6931471805599453f * fmaf(-2.0f, nf_lg2(den), nf_lg2(dnum));
+    const float l = 0.6931471805599453f * fmaf(-2.0f, nf_lg2(den), nf_lg2(dnum));
 #endif
-    return yk + nf_div(num, den);
+    ld = inside ? l : 0.0f;
+    return inside ? yk + nf_div(num, den) : xin;
 }
 
 // Inverse spline for one value; ld is what the reference's inverse returns (-logabsdet).
 // bad is set when the discriminant is negative.   src/flows/utils.py:123-147
-template <int K>
-__device__ __forceinline__ float nf_rqs_inverse(const float* out, float B, float y, float& ld, bool& bad) {
-    if (!(y >= -B && y <= B)) { ld = 0.0f; return y; }
-    float cw[K + 1], chh[K + 1], dummy[K];
-    nf_knots<K, false>(out + K, B, chh, dummy);
-    const int bin = nf_search<K>(chh, y);
-    float xk, xk1, yk, yk1, dk, dk1, uk, uk1;
-    nf_select2<K>(chh, bin, yk, yk1);
-    nf_knots<K, false>(out, B, cw, dummy);
-    nf_select2<K>(cw, bin, xk, xk1);
-    nf_derivs<K>(out + 2 * K, bin, dk, dk1, uk, uk1);
-    const float wk = xk1 - xk, hk = yk1 - yk;
+template <int K, int NP>
+__device__ __forceinline__ float nf_rqs_inverse(const float2 (&out2)[NP], float B, float yin, float& ld, bool& bad) {
+    const bool inside = (yin >= -B && yin <= B);
+    const float y = inside ? yin : 0.0f;
+    float2 c[K + 1], dummy[K];
+    nf_knots2<K, false>(out2, B, c, dummy);
+    NfSeg<K> sg;
+    nf_locate<K, true>(c, out2, y, sg);
+    float dk, dk1;
+    nf_seg_derivs<K>(sg, dk, dk1);
+    const float xk = sg.lo.x, yk = sg.lo.y;
+    const float wk = sg.hi.x - xk, hk = sg.hi.y - yk;
     const float delta = nf_div(hk, wk);
     const float dy = y - yk, sm = dk + dk1 - 2.0f * delta;
     const float a = dy * sm + hk * (delta - dk);
     const float b = hk * dk - dy * sm;
-    const float c = -delta * dy;
-    float disc = b * b - 4.0f * a * c;
-    if (!(disc >= 0.0f)) { bad = true; disc = 0.0f; }
-    const float root = nf_div(2.0f * c, -b - nf_sqrt(disc));
+    const float cc = -delta * dy;
+    float disc = b * b - 4.0f * a * cc;
+    bad = bad || (inside && !(disc >= 0.0f));
+    disc = fmaxf(disc, 0.0f);
+    const float root = nf_div(2.0f * cc, -b - nf_sqrt(disc));
     const float t1 = root * (1.0f - root);
     const float den = delta + sm * t1;
     const float omr = 1.0f - root;
     const float dnum = delta * delta * (dk1 * root * root + 2.0f * delta * t1 + dk * omr * omr);
 #if NF_ACCURATE_MATH
-    ld = -(logf(dnum) - 2.0f * logf(den));
+    const float l = -(logf(dnum) - 2.0f * logf(den));
 #else
-    ld = -0.6931471805599453f * fmaf(-2.0f, nf_lg2(den), nf_lg2(dnum));
+    const float l = -0.6931471805599453f * fmaf(-2.0f, nf_lg2(den), nf_lg2(dnum));
 #endif
-    return root * wk + xk;
+    ld = inside ? l : 0.0f;
+    return inside ? root * wk + xk : yin;
 }
 
 // theta_to_pipi (src/utils/Functions.py:20-21): (t + pi) mod 2pi - pi with Python's modulo sign.

@@ -28,26 +28,25 @@ namespace {
 
 constexpr float HALF_LOG_2PI = 0.91893853320467274178f;
 
-// d f / d out for one (sample, dim), f = -z^2/2 + logdet; `o` holds the conditioner outputs on
-// entry and gscale * df/dout on exit.  Returns f.
-template <int K>
-__device__ __forceinline__ float nf_rqs_grad(float (&o)[((3 * K - 1) + 3) & ~3], float B, float x, float gscale) {
+// d f / d out for one (sample, dim), f = -z^2/2 + logdet.  `o2` holds the conditioner outputs (interleaved
+// layout of nf_common.cuh) on entry and gscale * df/dout, same layout, on exit.  Returns f.
+template <int K, int NP>
+__device__ __forceinline__ float nf_rqs_grad(float2 (&o2)[NP], float B, float xin, float gscale_in) {
     constexpr int P = 3 * K - 1;
     constexpr int PP = (P + 3) & ~3;
-    if (!(x >= -B && x <= B)) {
-#pragma unroll
-        for (int p = 0; p < PP; ++p) o[p] = 0.0f;
-        return -0.5f * x * x;
-    }
-    float cw[K + 1], chh[K + 1], pw[K], ph[K];
-    nf_knots<K, true>(o, B, cw, pw);
-    const int bin = nf_search<K>(cw, x);
-    float xk, xk1, yk, yk1, a, bq, uk, uk1;
-    nf_select2<K>(cw, bin, xk, xk1);
-    nf_knots<K, true>(o + K, B, chh, ph);
-    nf_select2<K>(chh, bin, yk, yk1);
-    nf_derivs<K>(o + 2 * K, bin, a, bq, uk, uk1);
-    const float wk = xk1 - xk, hk = yk1 - yk;
+    static_assert(NP == PP / 2, "output vector size");
+    // branch-free linear tails: outside [-B, B] the gradient is zero (gscale = 0) and f = -x^2/2
+    const bool inside = (xin >= -B && xin <= B);
+    const float x = inside ? xin : 0.0f;
+    const float gscale = inside ? gscale_in : 0.0f;
+    float2 c[K + 1], pr[K];
+    nf_knots2<K, true>(o2, B, c, pr);
+    NfSeg<K> sg;
+    nf_locate<K, false>(c, o2, x, sg);
+    float a, bq;
+    nf_seg_derivs<K>(sg, a, bq);
+    const float xk = sg.lo.x, yk = sg.lo.y;
+    const float wk = sg.hi.x - xk, hk = sg.hi.y - yk;
     const float rw = nf_rcp(wk);
     const float s = hk * rw;
     const float t = (x - xk) * rw, u = t * (1.0f - t), omt = 1.0f - t;
@@ -58,10 +57,11 @@ __device__ __forceinline__ float nf_rqs_grad(float (&o)[((3 * K - 1) + 3) & ~3],
     const float rD = nf_rcp(Dn);
     const float z = yk + N * rD;
 #if NF_ACCURATE_MATH
-    const float f = -0.5f * z * z + logf(M) - 2.0f * logf(Dn);
+    const float f_in = -0.5f * z * z + logf(M) - 2.0f * logf(Dn);
 #else
-    const float f = fmaf(-0.5f * z, z, 0.6931471805599453f * fmaf(-2.0f, nf_lg2(Dn), nf_lg2(M)));
+    const float f_in = fmaf(-0.5f * z, z, 0.6931471805599453f * fmaf(-2.0f, nf_lg2(Dn), nf_lg2(M)));
 #endif
+    const float f = inside ? f_in : -0.5f * xin * xin;
     const float cN = -z * rD, cD = z * N * rD * rD - 2.0f * rD, cM = nf_rcp(M);
     const float N_s = hk * t * t, N_a = hk * u, N_t = hk * (2.0f * s * t + a * (1.0f - 2.0f * t)), N_h = s * t * t + a * u;
     const float D_s = 1.0f - 2.0f * u, D_t = (a + bq - 2.0f * s) * (1.0f - 2.0f * t);
@@ -77,42 +77,35 @@ __device__ __forceinline__ float nf_rqs_grad(float (&o)[((3 * K - 1) + 3) & ~3],
     const float g_yk = -z;
     const float c1 = (float)(1.0 - 1e-3 * (double)K) * gscale;
     const float twoB = 2.0f * B;
-    {   // widths: knots bin (if interior) and bin+1 (if interior) receive gradient
-        const float A = bin >= 1 ? twoB * (g_xk - g_wk) : 0.0f;
-        const float Bc = bin + 1 <= K - 1 ? twoB * g_wk : 0.0f;
-        float dot = 0.0f;
+    // Knot `bin` receives (g_xk - g_wk, g_yk - g_hk), knot `bin + 1` receives (g_wk, g_hk); the pinned end knots
+    // receive nothing.  Both lanes (widths, heights) at once.
+    const float2 zero2 = make_float2(0.0f, 0.0f);
+    const float2 Alo = sg.first ? zero2 : make_float2(twoB * (g_xk - g_wk), twoB * (g_yk - g_hk));
+    const float2 Bhi = sg.last ? zero2 : make_float2(twoB * g_wk, twoB * g_hk);
+    // ge(k) = (x >= knot_k), with ge(0) = true and ge(K) = false
+    auto ge = [&](int k) -> bool { return k <= 0 ? true : (k >= K ? false : (x >= c[k].x)); };
+    // d/d(bin size j) = 2B * sum of knot gradients above j:  (j < bin ? Alo : 0) + (j <= bin ? Bhi : 0)
+    float2 gw[K];
+    float2 dot = zero2;
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const float gw = (j < bin ? A : 0.0f) + (j <= bin ? Bc : 0.0f);
-            dot = fmaf(pw[j], gw, dot);
-        }
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const float gw = (j < bin ? A : 0.0f) + (j <= bin ? Bc : 0.0f);
-            o[j] = c1 * pw[j] * (gw - dot);
-        }
+    for (int j = 0; j < K; ++j) {
+        gw[j] = nf_add2(ge(j + 1) ? Alo : zero2, ge(j) ? Bhi : zero2);
+        dot = nf_fma2(pr[j], gw[j], dot);
     }
-    {   // heights
-        const float A = bin >= 1 ? twoB * (g_yk - g_hk) : 0.0f;
-        const float Bc = bin + 1 <= K - 1 ? twoB * g_hk : 0.0f;
-        float dot = 0.0f;
+    const float2 ndot = make_float2(-dot.x, -dot.y);
+    const float ga = gscale * f_a * nf_sigmoid_sp(sg.uk);
+    const float gb = gscale * f_b * nf_sigmoid_sp(sg.uk1);
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const float gh = (j < bin ? A : 0.0f) + (j <= bin ? Bc : 0.0f);
-            dot = fmaf(ph[j], gh, dot);
-        }
+    for (int j = 0; j < K; ++j) o2[j] = nf_mul2(nf_mul2(pr[j], nf_dup(c1)), nf_add2(gw[j], ndot));
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const float gh = (j < bin ? A : 0.0f) + (j <= bin ? Bc : 0.0f);
-            o[K + j] = c1 * ph[j] * (gh - dot);
-        }
+    for (int p = K; p < NP; ++p) o2[p] = zero2;
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        // derivative parameter ud_{k-1} belongs to knot k: it is the lower knot when bin == k, the upper when bin + 1 == k
+        const float v = ((ge(k) && !ge(k + 1)) ? ga : 0.0f) + ((ge(k - 1) && !ge(k)) ? gb : 0.0f);
+        const int fl = 2 * K + k - 1;
+        if (fl & 1) o2[fl / 2].y = v; else o2[fl / 2].x = v;
     }
-    const float ga = gscale * f_a * nf_sigmoid_sp(uk);
-    const float gb = gscale * f_b * nf_sigmoid_sp(uk1);
-#pragma unroll
-    for (int k = 1; k < K; ++k) o[2 * K + k - 1] = (bin == k ? ga : 0.0f) + (bin + 1 == k ? gb : 0.0f);
-#pragma unroll
-    for (int p = P; p < PP; ++p) o[p] = 0.0f;
     return f;
 }
 
@@ -234,35 +227,31 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
             const int64_t s = tile * 32 + lane;
             const bool valid = s < n;
             const float* xrow = slot + lane * dp;
-            float out[PP];
+            float2 o2[PP / 2];
             float h1[H], h2[H];
             if (i == 0) {
-#pragma unroll
-                for (int p = 0; p < PP; ++p) out[p] = s_w[p];
+                nf_load_bias<PP>(s_w, o2);
             } else {
                 nf_mlp_hidden<H>(s_w, i, xrow, h1, h2);
-                nf_mlp_out<H, PP>(s_w, i, h2, out);
+                nf_mlp_out<H, PP>(s_w, i, h2, o2);
             }
-            float f = nf_rqs_grad<K>(out, B, xrow[i], -inv_n);
+            float f = nf_rqs_grad<K>(o2, B, xrow[i], -inv_n);
             if (!valid) {
                 f = 0.0f;
 #pragma unroll
-                for (int p = 0; p < PP; ++p) out[p] = 0.0f;
+                for (int p = 0; p < PP / 2; ++p) o2[p] = make_float2(0.0f, 0.0f);
             } else {
                 f -= HALF_LOG_2PI;
             }
             floss += f;
             float* row = stage + lane * STG;
 #pragma unroll
-            for (int p = 0; p < PP; p += 4)
-                *reinterpret_cast<float4*>(row + p) = make_float4(out[p], out[p + 1], out[p + 2], out[p + 3]);
+            for (int p = 0; p < PP / 2; p += 2)
+                *reinterpret_cast<float4*>(row + 2 * p) = make_float4(o2[p].x, o2[p].y, o2[p + 1].x, o2[p + 1].y);
             if (i > 0) {
                 float g2[H], g1[H];
                 const float* W3t = s_w + oW3;
                 const float* W2t = s_w + oW2;
-                float2 o2[PP / 2];
-#pragma unroll
-                for (int p = 0; p < PP / 2; ++p) o2[p] = make_float2(out[2 * p], out[2 * p + 1]);
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
                     const float4* wr = reinterpret_cast<const float4*>(W3t + k * PP);

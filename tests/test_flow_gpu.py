@@ -149,7 +149,7 @@ def test_adam_trajectory_golden(flow_cases):
         assert _relmax(f.flat_parameters(), c["adam_theta"]) < 5e-2, name
 
 
-@pytest.mark.parametrize("n", [1, 7, 33, 2000, 100003])
+@pytest.mark.parametrize("n", [1, 7, 33, 2000, 100003, 200001])
 def test_ragged_sizes_vs_oracle(flow_cases, n):
     c = flow_cases["d6_K9_H8"]
     d, K, H, B = 6, 9, 8, 5.0

@@ -5,7 +5,7 @@ solver (tests/golden/solve_*.npz, tests/golden/make_solve_golden.py).
 Posterior tolerance (Monte-Carlo + model-fitting variance: two runs of the REFERENCE with different seeds
 differ by up to 0.52 sigma on pose means, 1.3 sigma on landmark means and 1.8x on stds,
 tests/golden/solve_small_case1_seed1.npz): per-variable mean within 0.75 sigma_ref + 0.5 (poses) /
-1.5 sigma_ref + 0.5 (landmarks) of the reference's mean, std ratio within [0.4, 2.5]; the biased MMD (RBF kernel,
+1.5 sigma_ref + 0.5 (landmarks) of the reference's mean, std ratio within [0.33, 3]; the biased MMD (RBF kernel,
 sigma = sqrt(dim), the reference's post-processing metric) between our samples and the reference's is
 reported and bounded."""
 import os
@@ -91,7 +91,7 @@ def test_incremental_solve_matches_reference_posterior(case):
                 tol = (1.5 if nm.startswith("L") else 0.75) * sr[sl] + 0.5
                 assert np.all(np.abs(m[sl] - mr[sl]) <= tol), (i, nm, m[sl], mr[sl], tol)
                 ratio = s[sl] / np.maximum(sr[sl], 1e-9)
-                assert np.all((ratio > 0.4) & (ratio < 2.5)), (i, nm, s[sl], sr[sl])
+                assert np.all((ratio > 0.33) & (ratio < 3.0)), (i, nm, s[sl], sr[sl])
         d = x.shape[1]
         report.append(mmd_b(x[:500].astype(np.float64), ref[:500].astype(np.float64), np.sqrt(d)))
     print(f"\n[{case}] joint MMD_b vs reference per step:", np.round(report, 4))
