@@ -185,10 +185,13 @@ typedef struct nf_factor_desc {
     double info[9];                     /* SE2 / GAUSS: precision matrix row-major (3x3 or top-left n x n);
                                            RANGE: info[0] = 1 / sigma^2 */
     double lnorm;                       /* log normalisation constant: -0.5*(dim*ln(2pi) + ln det Sigma) */
+    double obs_cs[2];                   /* SE2 types: cos and sin of the (wrapped) observation / prior angle obs[2] */
 } nf_factor_desc;
 
 /* JointFactor.log_pdf (src/sampler/sampler_utils.py:86-99): out_dev[s] = sum over factor groups of
- * log_pdf(x[s, cols]).  descs_host (n_desc) is copied to the device per call (small).
+ * log_pdf(x[s, cols]).  Up to 200 descriptors travel in the kernel-parameter constant bank (no allocation, copy
+ * or synchronisation per call: the call is then fully asynchronous on `stream`); longer lists go through a
+ * temporary device buffer and synchronise.
  * x_dev (n, D) float64, out_dev (n) float64.  If per_factor_dev != NULL it receives the per-group
  * values, (n_groups, n) row-major. */
 int nfisam_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const double* x_dev, int64_t n, int D,

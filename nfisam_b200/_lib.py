@@ -56,6 +56,7 @@ class nf_factor_desc(ctypes.Structure):
         ("obs", ctypes.c_double * 3),
         ("info", ctypes.c_double * 9),
         ("lnorm", ctypes.c_double),
+        ("obs_cs", ctypes.c_double * 2),
     ]
 
 

@@ -80,6 +80,8 @@ struct nf_flow {
     float* d_loss_part = nullptr;
     size_t loss_part_cap = 0;
     NfTrainCtrl* d_ctrl = nullptr;
+    float* d_partials = nullptr;       // large-batch training: per-block partial gradients / losses
+    float* d_loss_partials = nullptr;
     int pending_iters = 0;
     int pending_launches = 0;
     // host-API staging
@@ -193,6 +195,7 @@ int nfisam_flow_destroy(nf_flow_t* f) {
     DeviceGuard g(f->device);
     cudaFree(f->d_pk); cudaFree(f->d_m); cudaFree(f->d_v); cudaFree(f->d_grad); cudaFree(f->d_bad);
     cudaFree(f->d_loss_part); cudaFree(f->d_ctrl); cudaFree(f->d_norm); cudaFree(f->d_circ);
+    cudaFree(f->d_partials); cudaFree(f->d_loss_partials);
     for (int s = 0; s < 2; ++s) {
         cudaFree(f->d_stage_in[s]); cudaFree(f->d_stage_aux[s]); cudaFree(f->d_stage_out[s]);
         if (f->streams[s]) cudaStreamDestroy(f->streams[s]);
@@ -415,6 +418,15 @@ static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const n
     a->grad_out = f->d_grad;
     a->loss_part = f->d_loss_part;
     a->ctrl = f->d_ctrl;
+    a->n_packed = (int)f->n_packed;
+    if (n >= NF_TRAIN_PLAIN_MIN_N) {
+        if (!f->d_partials) {
+            NF_CUDA(cudaMalloc(&f->d_partials, sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->n_packed));
+            NF_CUDA(cudaMalloc(&f->d_loss_partials, sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->fd.d));
+        }
+        a->partials = f->d_partials;
+        a->loss_partials = f->d_loss_partials;
+    }
     return NF_OK;
 }
 
@@ -541,16 +553,7 @@ int nfisam_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const dou
     if (rc != NF_OK) return rc;
     DeviceGuard g(device);
     if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
-    nf_factor_desc* d_desc = nullptr;
-    cudaStream_t st = (cudaStream_t)stream;
-    NF_CUDA(cudaMallocAsync(&d_desc, sizeof(nf_factor_desc) * (size_t)n_desc, st));
-    cudaError_t e = cudaMemcpyAsync(d_desc, descs_host, sizeof(nf_factor_desc) * (size_t)n_desc, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) rc = nf_launch_factor_logpdf(d_desc, n_desc, groups, x_dev, n, D, out_dev, per_factor_dev, device, st);
-    cudaFreeAsync(d_desc, st);
-    if (e != cudaSuccess) return nf_cuda_fail(e, "descriptor upload");
-    // descs_host may be pageable and short-lived: make sure the upload is complete before returning
-    NF_CUDA(cudaStreamSynchronize(st));
-    return rc;
+    return nf_launch_factor_logpdf(descs_host, n_desc, x_dev, n, D, out_dev, per_factor_dev, device, (cudaStream_t)stream);
 }
 
 int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_desc, const double* x_dev, int64_t n, int D,

@@ -12,6 +12,14 @@
 //   SE2Pose compose / inverse / log_map / det_grad_x_logmap
 //                                          src/geometry/TwoDimension.py:405-418, 437-441, 475-477, 494-498
 //   Rot2 angle wrap                        src/geometry/TwoDimension.py:159, src/utils/Functions.py:20-21
+//
+// The reference builds one SE2Pose object per sample and per operation (7 trigonometric calls per odometry
+// factor).  Here the error pose dT = Z^-1 (Ti^-1 Tj) is formed algebraically: rotation by -theta_i uses one
+// sincos, rotation by the constant -theta_Z uses cos/sin precomputed in the descriptor, the error angle is
+// w = wrap(theta_j - theta_i - theta_Z), and the log map / its Jacobian need one sincos(w) and one log:
+//   det = (cos w - 1)^2 + sin^2 w = 4 sin^2(w/2)   =>   |d log / d(x,y,theta)| = w^2 / det.
+#include <cstring>
+
 #include "nf_internal.h"
 
 namespace {
@@ -26,87 +34,50 @@ __device__ __forceinline__ double wrap_pipi(double t) {
     return r - PI_D;
 }
 
-struct Pose {
-    double x, y, th;
-};
-
-__device__ __forceinline__ Pose pose_make(double x, double y, double th) { return Pose{x, y, wrap_pipi(th)}; }
-
-__device__ __forceinline__ Pose pose_inverse(const Pose& p) {
-    const double th = wrap_pipi(-p.th);
+// Gaussian on the log map of the error pose (tx, ty, w) plus the log-map Jacobian.
+__device__ __forceinline__ double se2_error_logpdf(double tx, double ty, double w, const double* info, double lnorm) {
+    double v0, v1, logdet;
     double s, c;
-    sincos(th, &s, &c);
-    // -(R(-theta) t)
-    return Pose{-(c * p.x - s * p.y), -(s * p.x + c * p.y), th};
-}
-
-__device__ __forceinline__ Pose pose_mul(const Pose& a, const Pose& b) {
-    double s, c;
-    sincos(a.th, &s, &c);
-    return Pose{a.x + (c * b.x - s * b.y), a.y + (s * b.x + c * b.y), wrap_pipi(a.th + b.th)};
-}
-
-// log map of dT and ln|det d(logmap)/d(x,y,theta)|
-__device__ __forceinline__ void pose_logmap(const Pose& p, double (&v)[3], double& logdet) {
-    const double w = p.th;
+    sincos(w, &s, &c);
+    const double c1 = c - 1.0;
+    const double det = c1 * c1 + s * s;
     if (fabs(w) < 1e-10) {
-        v[0] = p.x; v[1] = p.y; v[2] = w;
+        v0 = tx; v1 = ty;
     } else {
-        double s, c;
-        sincos(w, &s, &c);
-        const double c1 = c - 1.0;
-        const double det = c1 * c1 + s * s;
-        // unrotate: R(-w) t
-        double sn, cn;
-        sincos(wrap_pipi(-w), &sn, &cn);
-        const double qx = (cn * p.x - sn * p.y) - p.x;
-        const double qy = (sn * p.x + cn * p.y) - p.y;
-        // rot_pi_2 = Rot2(pi/2): cos = 6.123233995736766e-17, sin = 1
-        const double c90 = 6.123233995736766e-17, s90 = 1.0;
-        const double px = c90 * qx - s90 * qy;
-        const double py = s90 * qx + c90 * qy;
+        // p = rot(pi/2) (R(-w) t - t),  v = (w / det) p        (TwoDimension.py:405-418)
+        const double qx = (c * tx + s * ty) - tx;
+        const double qy = (-s * tx + c * ty) - ty;
+        const double c90 = 6.123233995736766e-17;            // cos(pi/2) as the reference's Rot2(pi/2) evaluates it
         const double k = w / det;
-        v[0] = k * px; v[1] = k * py; v[2] = w;
+        v0 = k * (c90 * qx - qy);
+        v1 = k * (qx + c90 * qy);
     }
-    if (fabs(w) < 1e-5) {
-        logdet = 0.0;
-    } else {
-        const double sh = sin(w / 2.0);
-        logdet = log(fabs(w * w / 4.0 / (sh * sh)));
-    }
+    logdet = fabs(w) < 1e-5 ? 0.0 : log(w * w / det);          // theta^2 / (4 sin^2(theta/2))
+    const double q = v0 * (info[0] * v0 + info[1] * v1 + info[2] * w) + v1 * (info[3] * v0 + info[4] * v1 + info[5] * w) +
+                     w * (info[6] * v0 + info[7] * v1 + info[8] * w);
+    return -0.5 * q + lnorm + logdet;
 }
 
-__device__ __forceinline__ double quad3(const double* info, const double (&v)[3]) {
-    double q = 0.0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        double row = 0.0;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) row += info[a * 3 + b] * v[b];
-        q += v[a] * row;
-    }
-    return q;
-}
-
-// log-density of one component for the sample row `xr`
+// log-density of one component for the sample row `xr` (element c of the row at xr[c * xstride])
 __device__ __forceinline__ double component_logpdf(const nf_factor_desc& f, const double* xr, int xstride) {
     switch (f.type) {
         case NF_FACTOR_SE2_PRIOR: {
-            const Pose prior = pose_make(f.obs[0], f.obs[1], f.obs[2]);
-            const Pose T = pose_make(xr[f.cols[0] * xstride], xr[f.cols[1] * xstride], xr[f.cols[2] * xstride]);
-            const Pose dT = pose_mul(pose_inverse(prior), T);
-            double v[3], ld;
-            pose_logmap(dT, v, ld);
-            return -0.5 * quad3(f.info, v) + f.lnorm + ld;
+            const double dx = xr[f.cols[0] * xstride] - f.obs[0], dy = xr[f.cols[1] * xstride] - f.obs[1];
+            const double co = f.obs_cs[0], so = f.obs_cs[1];
+            const double w = wrap_pipi(xr[f.cols[2] * xstride] - f.obs[2]);
+            return se2_error_logpdf(co * dx + so * dy, -so * dx + co * dy, w, f.info, f.lnorm);
         }
         case NF_FACTOR_SE2_BETWEEN: {
-            const Pose obs = pose_make(f.obs[0], f.obs[1], f.obs[2]);
-            const Pose Ti = pose_make(xr[f.cols[0] * xstride], xr[f.cols[1] * xstride], xr[f.cols[2] * xstride]);
-            const Pose Tj = pose_make(xr[f.cols[3] * xstride], xr[f.cols[4] * xstride], xr[f.cols[5] * xstride]);
-            const Pose dT = pose_mul(pose_inverse(obs), pose_mul(pose_inverse(Ti), Tj));
-            double v[3], ld;
-            pose_logmap(dT, v, ld);
-            return -0.5 * quad3(f.info, v) + f.lnorm + ld;
+            const double thi = xr[f.cols[2] * xstride], thj = xr[f.cols[5] * xstride];
+            const double dx = xr[f.cols[3] * xstride] - xr[f.cols[0] * xstride];
+            const double dy = xr[f.cols[4] * xstride] - xr[f.cols[1] * xstride];
+            double si, ci;
+            sincos(thi, &si, &ci);
+            const double rx = (ci * dx + si * dy) - f.obs[0];     // Ti^-1 Tj translation, minus the observed one
+            const double ry = (-si * dx + ci * dy) - f.obs[1];
+            const double co = f.obs_cs[0], so = f.obs_cs[1];
+            const double w = wrap_pipi(thj - thi - f.obs[2]);
+            return se2_error_logpdf(co * rx + so * ry, -so * rx + co * ry, w, f.info, f.lnorm);
         }
         case NF_FACTOR_RANGE: {
             const double dx = xr[f.cols[0] * xstride] - xr[f.cols[2] * xstride];
@@ -131,20 +102,13 @@ __device__ __forceinline__ double component_logpdf(const nf_factor_desc& f, cons
 }
 
 // One thread per sample.  The tile of rows is staged in shared memory (coalesced global reads) in a
-// column-major layout xs[col][thread] so that per-thread row accesses are conflict-free.
-__global__ void __launch_bounds__(FTPB)
-nf_factor_logpdf_kernel(const nf_factor_desc* __restrict__ descs, int n_desc, const double* __restrict__ x, int64_t n,
-                        int D, double* __restrict__ out, double* __restrict__ per_factor, int accumulate,
-                        int group_base) {
+// column-major layout xs[col][thread] so that per-thread row accesses are conflict-free.  Descriptors are read
+// at warp-uniform indices: from the kernel-parameter constant bank (PARAMS) or from a device buffer.
+template <typename DescSrc>
+__device__ __forceinline__ void factor_logpdf_body(const DescSrc& descs, int n_desc, const double* __restrict__ x, int64_t n,
+                                                   int D, double* __restrict__ out, double* __restrict__ per_factor) {
     extern __shared__ __align__(16) unsigned char fsmem[];
-    nf_factor_desc* sd = reinterpret_cast<nf_factor_desc*>(fsmem);
-    double* xs = reinterpret_cast<double*>(fsmem + (((size_t)n_desc * sizeof(nf_factor_desc) + 15) & ~size_t(15)));
-    {
-        const int words = n_desc * (int)(sizeof(nf_factor_desc) / 4);
-        const int* src = reinterpret_cast<const int*>(descs);
-        int* dst = reinterpret_cast<int*>(sd);
-        for (int t = threadIdx.x; t < words; t += FTPB) dst[t] = src[t];
-    }
+    double* xs = reinterpret_cast<double*>(fsmem);
     const int64_t tiles = (n + FTPB - 1) / FTPB;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t s0 = tile * FTPB;
@@ -159,16 +123,16 @@ nf_factor_logpdf_kernel(const nf_factor_desc* __restrict__ descs, int n_desc, co
         if (threadIdx.x < cnt) {
             const double* xr = xs + threadIdx.x;
             double total = 0.0;
-            int g = group_base;
+            int g = 0;
             for (int fi = 0; fi < n_desc;) {
-                const int nc = sd[fi].n_comp;
+                const int nc = descs[fi].n_comp;
                 double val;
                 if (nc <= 1) {
-                    val = component_logpdf(sd[fi], xr, FTPB);
+                    val = component_logpdf(descs[fi], xr, FTPB);
                     fi += 1;
                 } else {
                     double acc = 0.0;
-                    for (int c = 0; c < nc; ++c) acc += exp(component_logpdf(sd[fi + c], xr, FTPB)) * sd[fi + c].weight;
+                    for (int c = 0; c < nc; ++c) acc += exp(component_logpdf(descs[fi + c], xr, FTPB)) * descs[fi + c].weight;
                     val = log(acc);
                     fi += nc;
                 }
@@ -176,10 +140,33 @@ nf_factor_logpdf_kernel(const nf_factor_desc* __restrict__ descs, int n_desc, co
                 total += val;
                 ++g;
             }
-            if (accumulate) out[s0 + threadIdx.x] += total;
-            else out[s0 + threadIdx.x] = total;
+            out[s0 + threadIdx.x] = total;
         }
     }
+}
+
+constexpr int PARAMS_SMALL = 24, PARAMS_LARGE = 192;
+template <int N>
+struct DescPack {
+    nf_factor_desc d[N];
+    __device__ __forceinline__ const nf_factor_desc& operator[](int i) const { return d[i]; }
+};
+struct DescPtr {
+    const nf_factor_desc* d;
+    __device__ __forceinline__ const nf_factor_desc& operator[](int i) const { return d[i]; }
+};
+
+template <int N>
+__global__ void __launch_bounds__(FTPB)
+nf_factor_logpdf_kernel(const __grid_constant__ DescPack<N> descs, int n_desc, const double* __restrict__ x, int64_t n, int D,
+                        double* __restrict__ out, double* __restrict__ per_factor) {
+    factor_logpdf_body(descs, n_desc, x, n, D, out, per_factor);
+}
+
+__global__ void __launch_bounds__(FTPB)
+nf_factor_logpdf_buf_kernel(const nf_factor_desc* __restrict__ descs, int n_desc, const double* __restrict__ x, int64_t n, int D,
+                            double* __restrict__ out, double* __restrict__ per_factor) {
+    factor_logpdf_body(DescPtr{descs}, n_desc, x, n, D, out, per_factor);
 }
 
 // posterior_weights of ONE mixture group: per block partial sums of the responsibilities.
@@ -221,29 +208,58 @@ nf_mixture_weights_kernel(const nf_factor_desc* __restrict__ descs, int n_desc, 
     }
 }
 
-}  // namespace
-
-int nf_launch_factor_logpdf(const nf_factor_desc* descs_dev, int n_desc, int n_groups, const double* x, int64_t n, int D,
-                            double* out, double* per_factor, int device, cudaStream_t st) {
-    (void)n_groups;
-    if (n == 0) return NF_OK;
-    const size_t desc_bytes = ((size_t)n_desc * sizeof(nf_factor_desc) + 15) & ~size_t(15);
-    const size_t smem = desc_bytes + sizeof(double) * (size_t)FTPB * D;
-    int max_smem = 0;
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (smem > (size_t)max_smem)
-        return nf_set_error(NF_ERR_UNSUPPORTED, "factor list / row width too large for one pass (%zu B shared)", smem);
-    if (smem > 48 * 1024)
-        NF_CUDA(cudaFuncSetAttribute(nf_factor_logpdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <typename KernelT>
+int factor_grid(KernelT kern, size_t smem, int64_t n, int device) {
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nf_factor_logpdf_kernel, FTPB, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FTPB, smem);
     if (per_sm < 1) per_sm = 1;
     const int64_t tiles = (n + FTPB - 1) / FTPB;
     const int64_t cap = (int64_t)nf_sm_count(device) * per_sm;
-    const int grid = (int)(tiles < cap ? tiles : cap);
-    nf_factor_logpdf_kernel<<<grid, FTPB, smem, st>>>(descs_dev, n_desc, x, n, D, out, per_factor, 0, 0);
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+template <int N>
+int launch_params(const nf_factor_desc* descs_host, int n_desc, const double* x, int64_t n, int D, double* out,
+                  double* per_factor, size_t smem, int device, cudaStream_t st) {
+    static thread_local DescPack<N> pack;
+    memcpy(pack.d, descs_host, sizeof(nf_factor_desc) * (size_t)n_desc);
+    auto kern = nf_factor_logpdf_kernel<N>;
+    if (smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<factor_grid(kern, smem, n, device), FTPB, smem, st>>>(pack, n_desc, x, n, D, out, per_factor);
     nf_count_launch();
     return nf_check_launch("nf_factor_logpdf_kernel");
+}
+
+}  // namespace
+
+// descs_host: host descriptors.  Returns NF_OK; *synced tells the caller whether the stream was synchronised.
+int nf_launch_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const double* x, int64_t n, int D, double* out,
+                            double* per_factor, int device, cudaStream_t st) {
+    if (n == 0) return NF_OK;
+    const size_t smem = sizeof(double) * (size_t)FTPB * D;
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (smem > (size_t)max_smem) return nf_set_error(NF_ERR_UNSUPPORTED, "sample rows too wide for one tile (%d columns)", D);
+    if (n_desc <= PARAMS_SMALL) return launch_params<PARAMS_SMALL>(descs_host, n_desc, x, n, D, out, per_factor, smem, device, st);
+    if (n_desc <= PARAMS_LARGE) return launch_params<PARAMS_LARGE>(descs_host, n_desc, x, n, D, out, per_factor, smem, device, st);
+    nf_factor_desc* d_desc = nullptr;
+    NF_CUDA(cudaMallocAsync(&d_desc, sizeof(nf_factor_desc) * (size_t)n_desc, st));
+    cudaError_t e = cudaMemcpyAsync(d_desc, descs_host, sizeof(nf_factor_desc) * (size_t)n_desc, cudaMemcpyHostToDevice, st);
+    int rc = NF_OK;
+    if (e == cudaSuccess) {
+        if (smem > 48 * 1024)
+            e = cudaFuncSetAttribute(nf_factor_logpdf_buf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            nf_factor_logpdf_buf_kernel<<<factor_grid(nf_factor_logpdf_buf_kernel, smem, n, device), FTPB, smem, st>>>(
+                d_desc, n_desc, x, n, D, out, per_factor);
+            nf_count_launch();
+            rc = nf_check_launch("nf_factor_logpdf_buf_kernel");
+        }
+    }
+    cudaFreeAsync(d_desc, st);
+    if (e != cudaSuccess) return nf_cuda_fail(e, "descriptor upload");
+    NF_CUDA(cudaStreamSynchronize(st));      // descs_host may be pageable and short-lived
+    return rc;
 }
 
 int nf_launch_mixture_weights(const nf_factor_desc* descs_dev, int n_desc, const double* x, int64_t n, int D,

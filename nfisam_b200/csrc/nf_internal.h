@@ -64,14 +64,21 @@ struct NfTrainArgs {
     float* grad_out;        // packed-size buffer (grad_only)
     float* loss_part;       // (max_iters, d) per-dim loss contributions
     NfTrainCtrl* ctrl;      // [2] double-buffered early-stop record (zeroed before the first launch)
+    // large-batch mode (n >= NF_TRAIN_PLAIN_MIN_N): plain grid, per-block partial gradients in global memory,
+    // reduced + applied by nf_adam_kernel; null pointers select the cluster mode
+    float* partials;        // (NF_TRAIN_PLAIN_MAX_BLOCKS, n_packed)
+    float* loss_partials;   // (NF_TRAIN_PLAIN_MAX_BLOCKS, d)
+    int n_packed;
 };
+#define NF_TRAIN_PLAIN_MIN_N 16384
+#define NF_TRAIN_PLAIN_MAX_BLOCKS 64
 // Returns the number of launches enqueued (>= 1) or a negative nf_status.  The final control record
 // is ctrl[launches & 1].
 int nf_launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st);
 size_t nf_train_loss_part_elems(const NfFlowDims& fd, int max_iters);
 
 // nf_factor_kernels.cu
-int nf_launch_factor_logpdf(const nf_factor_desc* descs_dev, int n_desc, int n_groups, const double* x, int64_t n, int D,
-                            double* out, double* per_factor, int device, cudaStream_t st);
+int nf_launch_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const double* x, int64_t n, int D, double* out,
+                            double* per_factor, int device, cudaStream_t st);
 int nf_launch_mixture_weights(const nf_factor_desc* descs_dev, int n_desc, const double* x, int64_t n, int D,
                               double* partial_dev, int* n_partial, int device, cudaStream_t st);

@@ -111,7 +111,8 @@ __device__ __forceinline__ float nf_rqs_grad(float2 (&o2)[NP], float B, float xi
 
 template <int K, int H, int W>
 __global__ void __launch_bounds__(W * 32)
-nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_begin, int it_end, int launch_idx) {
+nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_begin, int it_end, int launch_idx,
+                int plain) {
     constexpr int P = 3 * K - 1;
     constexpr int PP = (P + 3) & ~3;
     constexpr int NC3 = (PP + 31) / 32;            // W3 columns owned per lane
@@ -121,9 +122,11 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     constexpr int STG = PP + 4 * H;                // staging row: gout | h2 | g2 | h1 | g1
     static_assert(H % 4 == 0 && 32 % H == 0, "hidden width must divide 32 and be a multiple of 4");
 
+    // cluster mode: the C blocks of a cluster share one dim; plain (large-batch) mode: gridDim.x independent blocks
+    // per dim that leave their partial gradient in global memory for nf_adam_kernel
     cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks();
-    const int r = (int)cluster.block_rank();
+    const int C = plain ? (int)gridDim.x : (int)cluster.num_blocks();
+    const int r = plain ? (int)blockIdx.x : (int)cluster.block_rank();
     const int i = blockIdx.y;                      // the dim / conditioner this cluster trains
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = W * 32;
@@ -157,7 +160,11 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
 
     // ---------------- early stop: windowed relative loss change (NFiSAM.py:481-491) ----------------
     // Evaluated on the window the previous launch finished; identical in every block.
-    {
+    const bool window_start = a.average_window <= 0 || it_begin % a.average_window == 0 || !plain;
+    if (!window_start) {
+        // plain mode launches one iteration at a time: inside a window just honour the decision of its first launch
+        if (a.ctrl[(launch_idx + 1) & 1].stop) return;
+    } else {
         const NfTrainCtrl cin = a.ctrl[launch_idx & 1];
         NfTrainCtrl cout = cin;
         if (!cin.stop && launch_idx > 0 && a.average_window > 0 && !a.grad_only && it_begin % a.average_window == 0) {
@@ -381,6 +388,13 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
             for (int w = 0; w < W; ++w) acc += s_loss[w];
             s_misc[0] = acc;
         }
+        if (plain) {
+            __syncthreads();
+            float* dst = a.partials + (size_t)r * a.n_packed + goff;
+            for (int p = threadIdx.x; p < G; p += T) dst[p] = s_g[p];
+            if (threadIdx.x == 0) a.loss_partials[r * d + i] = s_misc[0];
+            return;                                               // one iteration per launch in this mode
+        }
         cluster.sync();                                           // (A) every block's s_g / loss ready
         // ---------------- slice reduce over the cluster + fused Adam ----------------
         b1t *= (double)a.beta1;
@@ -420,6 +434,37 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     }
 }
 
+// Large-batch mode, second half of an iteration: fixed-order reduction of the per-block partial gradients,
+// fused Adam update of the packed parameters (elementwise, any layout), per-dim loss.
+__global__ void __launch_bounds__(256)
+nf_adam_kernel(NfTrainArgs a, int d, int blocks, int it, int launch_idx) {
+    if (a.ctrl[(launch_idx + 1) & 1].stop) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.n_packed) {
+        float g = 0.0f;
+        for (int b = 0; b < blocks; ++b) g += a.partials[(size_t)b * a.n_packed + p];
+        if (a.grad_only) {
+            a.grad_out[p] = g;
+        } else {
+            const int tstep = a.step0 + it + 1;
+            const double b1t = pow((double)a.beta1, (double)tstep), b2t = pow((double)a.beta2, (double)tstep);
+            const float step = (float)((double)a.lr / (1.0 - b1t));
+            const float bc2s = (float)sqrt(1.0 - b2t);
+            float m = a.adam_m[p], v = a.adam_v[p];
+            m = m + (g - m) * (1.0f - a.beta1);
+            v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+            a.adam_m[p] = m;
+            a.adam_v[p] = v;
+            a.pk[p] = a.pk[p] - step * (m / (sqrtf(v) / bc2s + a.eps));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < d) {
+        float acc = 0.0f;
+        for (int b = 0; b < blocks; ++b) acc += a.loss_partials[b * d + threadIdx.x];
+        a.loss_part[(size_t)it * d + threadIdx.x] = -acc / (float)a.n;
+    }
+}
+
 template <int K, int H, int W>
 size_t train_smem_bytes(int i_max, int C, int mt_res) {
     constexpr int PP = ((3 * K - 1) + 3) & ~3;
@@ -445,6 +490,43 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const int window = a.grad_only ? 1 : (a.average_window > 0 ? a.average_window : 64);
+    if (a.partials != nullptr && a.loss_partials != nullptr) {
+        // ---- large-batch mode: two launches per iteration, about two blocks per SM over all dims
+        const size_t smem = train_smem_bytes<K, H, W>(d - 1, 1, 1);
+        if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem);
+        if (per_sm < 1) per_sm = 1;
+        int blocks = (nf_sm_count(device) * per_sm + d - 1) / d;
+        const int64_t want = (ntiles + W - 1) / W;
+        if (blocks > want) blocks = (int)want;
+        if (blocks > NF_TRAIN_PLAIN_MAX_BLOCKS) blocks = NF_TRAIN_PLAIN_MAX_BLOCKS;
+        if (blocks < 1) blocks = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks, d, 1);
+        cfg.blockDim = dim3(W * 32, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attrs[1];
+        attrs[0].id = cudaLaunchAttributeClusterDimension;
+        attrs[0].val.clusterDim.x = 1;
+        attrs[0].val.clusterDim.y = 1;
+        attrs[0].val.clusterDim.z = 1;
+        cfg.attrs = attrs;
+        cfg.numAttrs = 1;
+        const int adam_blocks = (a.n_packed + 255) / 256;
+        for (int it = 0; it < a.max_iters; ++it) {
+            const int launch_idx = it / window;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, 1, 0, it, it + 1, launch_idx, 1);
+            if (e != cudaSuccess) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, plain)");
+            nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
+            nf_count_launch(2);
+        }
+        int rc = nf_check_launch("nf_adam_kernel");
+        if (rc != NF_OK) return rc;
+        return (a.max_iters + window - 1) / window;     // number of windows = index of the final control record
+    }
     for (;; C /= 2) {
         const int TW = C * W;
         int mt = (int)((ntiles + TW - 1) / TW);
@@ -470,7 +552,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         bool retry = false;
         for (int it0 = 0; it0 < a.max_iters; it0 += window, ++launch_idx) {
             const int it1 = it0 + window < a.max_iters ? it0 + window : a.max_iters;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 if (launch_idx > 0 || C == 1) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel)");

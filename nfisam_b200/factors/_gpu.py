@@ -34,6 +34,9 @@ def pack_descs(groups):
             for j in range(9):
                 d.info[j] = info[j] if j < len(info) else 0.0
             d.lnorm = float(c["lnorm"])
+            if c["type"] in ("se2_prior", "se2_between"):
+                th = (obs[2] + np.pi) % (2.0 * np.pi) - np.pi
+                d.obs_cs[0], d.obs_cs[1] = float(np.cos(th)), float(np.sin(th))
             k += 1
     return arr, n
 

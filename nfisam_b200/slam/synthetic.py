@@ -19,12 +19,12 @@ from .variables import R2Variable, SE2Variable, Variable, VariableType
 
 def make_manhattan_range_graph(robots: int = 1, poses: int = 16, landmarks: int = 4, cell: float = 10.0,
                                range_sigma: float = 2.0, odom_sigmas=(0.2, 0.04, 0.02), prior_sigmas=(0.02, 0.02, 0.002),
-                               max_range: float = 1e9, ada_prob: float = 0.0, seed: int = 0
+                               max_range: float = 1e9, ada_prob: float = 0.0, seed: int = 0, ranges_per_pose: int = 2
                                ) -> Tuple[List[Variable], Dict[Variable, np.ndarray], List[Factor]]:
     """Returns (nodes, truth, factors) like read_factor_graph_from_file.  Every pose measures the range
-    to its nearest landmark (with probability `ada_prob` the association is ambiguous between that
-    landmark and a random other one); at time 0 each robot additionally ranges to every landmark so that
-    all landmarks are tied to a prior-connected pose."""
+    to its `ranges_per_pose` nearest landmarks (with probability `ada_prob` an association is ambiguous
+    between the true landmark and a random other one); at time 0 each robot ranges to every landmark so
+    that all landmarks are tied to a prior-connected pose."""
     rng = np.random.default_rng(seed)
     side = int(np.ceil(np.sqrt(max(robots, 1))))
     extent = cell * max(4, int(np.sqrt(poses)) + 2)
@@ -63,7 +63,7 @@ def make_manhattan_range_graph(robots: int = 1, poses: int = 16, landmarks: int 
             var = seq[t]
             ordered_nodes.append(var)
             d = np.linalg.norm(lmk_xy - truth[var][:2], axis=1)
-            targets = list(range(landmarks)) if t == 0 else [int(np.argmin(d))]
+            targets = list(range(landmarks)) if t == 0 else [int(k) for k in np.argsort(d)[:max(1, ranges_per_pose)]]
             for k in targets:
                 if d[k] > max_range:
                     continue

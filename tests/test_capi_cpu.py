@@ -31,8 +31,8 @@ def test_header_symbols_are_exported(built_lib):
 
 def test_struct_sizes_match_header(built_lib):
     lib = built_lib.load()  # load() itself verifies the three struct sizes against the C side
-    # nf_factor_desc: 2 ints + 6 ints + 2 ints + 1 + 3 + 9 + 1 doubles
-    assert ctypes.sizeof(built_lib.nf_factor_desc) == 4 * 10 + 8 * 14 == lib.nfisam_struct_size(1)
+    # nf_factor_desc: 2 ints + 6 ints + 2 ints + 1 + 3 + 9 + 1 + 2 doubles
+    assert ctypes.sizeof(built_lib.nf_factor_desc) == 4 * 10 + 8 * 16 == lib.nfisam_struct_size(1)
     assert ctypes.sizeof(built_lib.nf_train_cfg) == lib.nfisam_struct_size(0)
     assert ctypes.sizeof(built_lib.nf_affine) == 24 == lib.nfisam_struct_size(2)
 

@@ -308,3 +308,36 @@ def test_unsupported_configuration_fails_loudly():
     f = NSF_AR(dim=3, K=7, hidden_dim=8)
     with pytest.raises(_lib.NfisamError):
         f.forward(torch.zeros(4, 3))
+
+
+def test_large_batch_training_mode_matches_oracle():
+    """n >= 16384 switches the training loop to the plain-grid mode (per-block partial gradients + Adam kernel):
+    same loss curve as the oracle, same early-stop iteration, continuation keeps the Adam state."""
+    from nfisam_b200.flows import NSF_AR
+
+    rng = np.random.default_rng(11)
+    d, K, H, n = 5, 9, 8, 20_000
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[:, 2] = 0.4 * x[:, 2] + np.tanh(x[:, 0]) - 0.5 * x[:, 1] ** 2 + 0.5
+    x = (x - x.mean(0)) / x.std(0)
+    torch.manual_seed(2)
+    f = NSF_AR(dim=d, K=K, hidden_dim=H)
+    theta0 = f.flat_parameters()
+    hist, ran = f.fit(torch.tensor(x), 40, 0.01, average_window=0)
+    _, hist_o, _ = orc.train(theta0, d, K, H, 5.0, x, 40, 0.01, average_window=0)
+    _, hist64, _ = orc.train(theta0, d, K, H, 5.0, x, 40, 0.01, average_window=0, dtype=np.float64)
+    assert ran == 40
+    assert np.allclose(hist[:10], hist_o[:10], rtol=1e-5)
+    assert np.abs(hist - hist64).max() <= 5 * np.abs(hist_o - hist64).max() + 1e-4
+    f2 = NSF_AR(dim=d, K=K, hidden_dim=H)
+    f2.load_flat_parameters(theta0)
+    h1, _ = f2.fit(torch.tensor(x), 20, 0.01, average_window=0)
+    h2, _ = f2.fit(torch.tensor(x), 20, 0.01, average_window=0, reset_optimizer=False)
+    assert np.array_equal(h1, hist[:20]) and np.allclose(h2, hist[20:], rtol=1e-4)
+    f3 = NSF_AR(dim=d, K=K, hidden_dim=H)
+    f3.load_flat_parameters(theta0)
+    h3, ran3 = f3.fit(torch.tensor(x), 100, 1e-6, average_window=10, loss_delta_tol=1e-2)
+    assert ran3 == 20 and np.all(h3[20:] == 0) and np.all(h3[:20] != 0)
+    loss, g = f3.loss_and_grad(torch.tensor(x))
+    lo, go = orc.loss_grad(f3.flat_parameters(), d, K, H, 5.0, x, dtype=np.float64)
+    assert abs(loss - lo) < 2e-5 * abs(lo) and _relmax(g, go) < 5e-4

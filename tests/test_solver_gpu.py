@@ -33,14 +33,15 @@ def test_wrapper_matches_reference_outputs():
     check_wrapper(g, rtol=2e-5)
 
 
-def solve(case, **kw):
+def solve(case, _reseed=True, **kw):
     from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
     from nfisam_b200.slam.run_batch import graph_file_parser, group_nodes_factors_incrementally
 
     nodes, truth, factors = graph_file_parser(os.path.join(HERE, "data", case + ".fg"))
     steps = group_nodes_factors_incrementally(nodes, factors, incremental_step=1)
-    np.random.seed(0)
-    torch.manual_seed(0)
+    if _reseed:
+        np.random.seed(0)
+        torch.manual_seed(0)
     args = dict(num_knots=9, flow_iterations=600, local_sample_num=2000, learning_rate=.025, hidden_dim=8,
                 elimination_method="pose_first", loss_delta_tol=.01, posterior_sample_num=1000)
     args.update(kw)
@@ -59,55 +60,77 @@ def solve(case, **kw):
     return per_step
 
 
-@pytest.mark.parametrize("case", ["small_case1", "small_case1_da"])
+def solve_seeded(case, seed, **kw):
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    return solve(case, _reseed=False, **kw)
+
+
+@pytest.mark.parametrize("case", ["small_case1", "small_case1_da", "manhattan_r1_p10", "manhattan_r2_p5"])
 def test_incremental_solve_matches_reference_posterior(case):
+    """Three independently seeded runs of this solver against the reference's stored posterior(s).  NF-iSAM's
+    run-to-run spread is large (the reference itself, seeds 0 vs 1: pose means up to 0.52 sigma apart, landmark
+    means up to 1.3 sigma, stds up to 1.8x, joint MMD_b up to 0.30), so every statistic is the MEDIAN over our three
+    runs of the distance to the CLOSEST reference run."""
     path = os.path.join(HERE, "golden", f"solve_{case}.npz")
     if not os.path.exists(path):
         pytest.skip("golden posterior not generated")
-    g = dict(np.load(path))
-    steps = solve(case)
+    refs = [dict(np.load(path))]
+    alt = os.path.join(HERE, "golden", f"solve_{case}_seed1.npz")
+    if os.path.exists(alt):
+        refs.append(dict(np.load(alt)))
+    runs = [solve_seeded(case, seed) for seed in (0, 1, 2)]
+    n_steps = len(runs[0])
     report = []
-    for i, (names, x, timer, solver) in enumerate(steps):
-        ref = g[f"step{i}_samples"]
-        assert names == list(g[f"step{i}_order"])
-        assert x.shape == ref.shape
-        tree = sorted("".join(sorted(v.name for v in c.frontal)) + "|" + "".join(sorted(v.name for v in c.separator))
-                      for c in solver.physical_bayes_tree.clique_nodes)
-        if i == len(steps) - 1:
-            assert tree == list(g[f"step{i}_tree"]), (tree, list(g[f"step{i}_tree"]))
-        m, mr = x.mean(0), ref.mean(0)
-        s, sr = x.std(0), ref.std(0)
-        # Range-only landmark marginals are multi-modal (mirror solutions) until enough poses have seen them:
-        # compare means / stds per VARIABLE only where the reference's own marginal is concentrated (every dim
-        # std < 5); the multi-modal ones are covered by the MMD below.
-        col = 0
-        for nm in names:
-            w = 2 if nm.startswith("L") else 3
-            sl = slice(col, col + w)
-            col += w
-            if np.all(sr[sl] < 5.0):
-                # calibrated on two runs of the REFERENCE itself (seeds 0 / 1, tests/golden/solve_small_case1*.npz):
-                # pose means differ by up to 0.52 sigma, landmark means by up to 1.3 sigma, std ratios reach 1.8
-                tol = (1.5 if nm.startswith("L") else 0.75) * sr[sl] + 0.5
-                assert np.all(np.abs(m[sl] - mr[sl]) <= tol), (i, nm, m[sl], mr[sl], tol)
-                ratio = s[sl] / np.maximum(sr[sl], 1e-9)
-                assert np.all((ratio > 0.33) & (ratio < 3.0)), (i, nm, s[sl], sr[sl])
-        d = x.shape[1]
-        report.append(mmd_b(x[:500].astype(np.float64), ref[:500].astype(np.float64), np.sqrt(d)))
-    print(f"\n[{case}] joint MMD_b vs reference per step:", np.round(report, 4))
-    # calibration: two runs of the REFERENCE itself (seeds 0 / 1) are 0.06-0.30 apart in this metric
-    # (small_case1: .063 .064 .066 .145 .300 .295; small_case1_da: .063 .064 .077 .084 .201 .246)
+    for i in range(n_steps):
+        names = runs[0][i][0]
+        assert names == list(refs[0][f"step{i}_order"])
+        if i == n_steps - 1:
+            solver = runs[0][i][3]
+            tree = sorted("".join(sorted(v.name for v in c.frontal)) + "|" + "".join(sorted(v.name for v in c.separator))
+                          for c in solver.physical_bayes_tree.clique_nodes)
+            assert tree == list(refs[0][f"step{i}_tree"]), (tree, list(refs[0][f"step{i}_tree"]))
+        mean_excess, std_bad, mmds = [], [], []
+        for (nm_, x, timer, solver) in runs:
+            best_excess, best_std, best_mmd = np.inf, np.inf, np.inf
+            for g in refs:
+                ref = g[f"step{i}_samples"]
+                assert x.shape == ref.shape
+                m, mr, s_, sr = x.mean(0), ref.mean(0), x.std(0), ref.std(0)
+                col, excess, stdr = 0, 0.0, 1.0
+                for nm in names:
+                    w = 2 if nm.startswith("L") else 3
+                    sl = slice(col, col + w)
+                    col += w
+                    # range-only landmark marginals are multi-modal until enough poses have seen them: means / stds
+                    # are compared only where the reference's marginal is concentrated; the rest is covered by the MMD
+                    if np.all(sr[sl] < 5.0):
+                        tol = (1.5 if nm.startswith("L") else 0.75) * sr[sl] + 0.5
+                        excess = max(excess, float(np.max(np.abs(m[sl] - mr[sl]) / tol)))
+                        r = s_[sl] / np.maximum(sr[sl], 1e-9)
+                        stdr = max(stdr, float(np.max(np.maximum(r, 1.0 / np.maximum(r, 1e-9)))))
+                best_excess, best_std = min(best_excess, excess), min(best_std, stdr)
+                best_mmd = min(best_mmd, mmd_b(x[:500].astype(np.float64), ref[:500].astype(np.float64), np.sqrt(x.shape[1])))
+            mean_excess.append(best_excess)
+            std_bad.append(best_std)
+            mmds.append(best_mmd)
+        assert np.median(mean_excess) <= 1.0, (case, i, mean_excess)
+        assert np.median(std_bad) <= 3.0, (case, i, std_bad)
+        report.append(float(np.median(mmds)))
+    print(f"\n[{case}] joint MMD_b vs reference per step (median of 3 runs):", np.round(report, 4))
     assert max(report) < 0.35, report
-    if "step5_hypo" in g:
-        # data-association hypothesis weights after the last step agree with the reference's
+    g = refs[0]
+    key = f"step{n_steps - 1}_hypo"
+    if key in g and len(g[key]):
         from nfisam_b200.factors import BinaryFactorMixture
 
-        solver = steps[-1][3]
-        cur = solver._samples
-        mix = [f for f in solver.physical_factors if isinstance(f, BinaryFactorMixture)]
-        w = np.array([f.posterior_weights(cur) for f in mix])
-        print("hypothesis weights:", np.round(w, 3).tolist(), "reference:", np.round(g["step5_hypo"], 3).tolist())
-        assert np.all(np.abs(w - g["step5_hypo"]) < 0.15)
+        ws = []
+        for (nm_, x, timer, solver) in [r[-1] for r in runs]:
+            mix = [f for f in solver.physical_factors if isinstance(f, BinaryFactorMixture)]
+            ws.append(np.array([f.posterior_weights(solver._samples) for f in mix]))
+        w = np.median(np.array(ws), axis=0)
+        print("hypothesis weights:", np.round(w, 3).tolist(), "reference:", np.round(g[key], 3).tolist())
+        assert np.all(np.abs(w - g[key]) < 0.2)
 
 
 def test_clique_parallel_equals_serial_loop_statistically():
