@@ -91,7 +91,8 @@ def test_incremental_solve_matches_reference_posterior(case):
                           for c in solver.physical_bayes_tree.clique_nodes)
             assert tree == list(refs[0][f"step{i}_tree"]), (tree, list(refs[0][f"step{i}_tree"]))
         mean_excess, std_bad, mmds = [], [], []
-        for (nm_, x, timer, solver) in runs:
+        for run in runs:
+            x = run[i][1]
             best_excess, best_std, best_mmd = np.inf, np.inf, np.inf
             for g in refs:
                 ref = g[f"step{i}_samples"]
@@ -125,7 +126,7 @@ def test_incremental_solve_matches_reference_posterior(case):
         from nfisam_b200.factors import BinaryFactorMixture
 
         ws = []
-        for (nm_, x, timer, solver) in [r[-1] for r in runs]:
+        for solver in [r[-1][3] for r in runs]:
             mix = [f for f in solver.physical_factors if isinstance(f, BinaryFactorMixture)]
             ws.append(np.array([f.posterior_weights(solver._samples) for f in mix]))
         w = np.median(np.array(ws), axis=0)
