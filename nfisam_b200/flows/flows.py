@@ -55,6 +55,13 @@ class NSF_AR(nn.Module):
       reference_layout  True (default): ``forward`` returns exactly what the reference returns,
                         including its dim-major output permutation for n > 1 (SURVEY.md 0.2);
                         False: mathematically per-sample rows.
+
+    The parameters are drawn exactly like the reference draws them (same torch RNG consumption: per
+    conditioner Linear weights / biases ~ U(+-1/sqrt(fan_in)) in module order, then init_param ~ U(+-1/2)),
+    but kept as ONE flat host vector in state_dict order.  The reference's module tree (``init_param``,
+    ``layers[i].network[0|2|4]``) is materialised lazily, the first time ``layers`` / ``init_param`` /
+    ``parameters()`` / ``state_dict()`` is touched: building 3 (dim-1) nn.Linear modules costs ~13 ms per
+    flow, more than a whole on-device training run of a clique.
     """
 
     def __init__(self, dim, K=5, B=5.0, hidden_dim=8, base_network=FCNN, device=None, reference_layout=True):
@@ -64,21 +71,80 @@ class NSF_AR(nn.Module):
         self.B = B
         self.hidden_dim = hidden_dim
         self.reference_layout = reference_layout
-        self.layers = nn.ModuleList()
-        self.init_param = nn.Parameter(torch.Tensor(3 * K - 1))
-        for i in range(1, dim):
-            self.layers += [base_network(i, 3 * K - 1, hidden_dim)]
-        self.reset_parameters()
+        self._base_network = base_network
+        self._materialized = False
+        self._flat_version = 0
+        self._theta = self._draw_initial_parameters()
         self._device_index = device
         self._h = None
         self._synced = None
         self._pending = None
 
-    def reset_parameters(self):
-        init.uniform_(self.init_param, -1 / 2, 1 / 2)
+    # ------------------------------------------------------------------ parameters
+    def _shapes(self):
+        """(shape, fan_in) of every tensor in state_dict order."""
+        P, H = 3 * self.K - 1, self.hidden_dim
+        out = [((P,), None)]
+        for i in range(1, self.dim):
+            out += [((H, i), i), ((H,), i), ((H, H), H), ((H,), H), ((P, H), H), ((P,), H)]
+        return out
 
-    # ------------------------------------------------------------------ handle / parameter mirror
+    def _draw_initial_parameters(self):
+        """Same draws, in the same order, as constructing the reference module tree (src/flows/flows.py:51-63):
+        nn.Linear.reset_parameters for every conditioner layer, then reset_parameters() on init_param."""
+        shapes = self._shapes()
+        parts = [None]
+        for shape, fan_in in shapes[1:]:
+            bound = 1.0 / math.sqrt(fan_in)
+            parts.append(torch.empty(shape).uniform_(-bound, bound).numpy().ravel())
+        parts[0] = torch.empty(shapes[0][0]).uniform_(-0.5, 0.5).numpy().ravel()
+        return np.concatenate(parts).astype(np.float32)
+
+    def reset_parameters(self):
+        if self._materialized:
+            init.uniform_(self.init_param, -1 / 2, 1 / 2)
+        else:
+            P = 3 * self.K - 1
+            self._theta[:P] = torch.empty(P).uniform_(-0.5, 0.5).numpy()
+            self._flat_version += 1
+
+    def _materialize(self):
+        if self._materialized:
+            return
+        self._materialized = True
+        P = 3 * self.K - 1
+        layers = nn.ModuleList()
+        init_param = nn.Parameter(torch.Tensor(P))
+        for i in range(1, self.dim):
+            layers.append(self._base_network(i, P, self.hidden_dim))
+        # register without going through our own __getattr__ hook
+        self._parameters["init_param"] = init_param
+        self._modules["layers"] = layers
+        self._load_into_modules(self._theta)
+
+    def __getattr__(self, name):
+        if name in ("layers", "init_param") and not self.__dict__.get("_materialized", True):
+            self._materialize()
+        return super().__getattr__(name)
+
+    def parameters(self, recurse=True):
+        self._materialize()
+        return super().parameters(recurse)
+
+    def named_parameters(self, *args, **kwargs):
+        self._materialize()
+        return super().named_parameters(*args, **kwargs)
+
+    def state_dict(self, *args, **kwargs):
+        self._materialize()
+        return super().state_dict(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._materialize()
+        return super().load_state_dict(*args, **kwargs)
+
     def _ordered_params(self):
+        self._materialize()
         ps = [self.init_param]
         for layer in self.layers:
             for j in (0, 2, 4):
@@ -86,12 +152,18 @@ class NSF_AR(nn.Module):
                 ps.append(layer.network[j].bias)
         return ps
 
+    def _param_version(self):
+        if self._materialized:
+            return ("m",) + tuple(p._version for p in self._ordered_params())
+        return ("f", self._flat_version)
+
     def flat_parameters(self) -> np.ndarray:
         """state_dict order, float32 (the order of the C ABI's parameter vector)."""
+        if not self._materialized:
+            return self._theta.copy()
         return np.concatenate([p.detach().cpu().numpy().astype(np.float32).ravel() for p in self._ordered_params()])
 
-    def load_flat_parameters(self, theta):
-        theta = np.asarray(theta, dtype=np.float32)
+    def _load_into_modules(self, theta):
         off = 0
         with torch.no_grad():
             for p in self._ordered_params():
@@ -99,6 +171,16 @@ class NSF_AR(nn.Module):
                 p.copy_(torch.from_numpy(theta[off:off + k].reshape(tuple(p.shape)).copy()))
                 off += k
         assert off == theta.size
+
+    def load_flat_parameters(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float32).ravel()
+        if theta.size != self._theta.size:
+            raise ValueError(f"expected {self._theta.size} parameters, got {theta.size}")
+        if self._materialized:
+            self._load_into_modules(theta)
+        else:
+            self._theta = theta.copy()
+            self._flat_version += 1
 
     @property
     def device_index(self):
@@ -115,7 +197,7 @@ class NSF_AR(nn.Module):
                                               int(self.device_index), ctypes.byref(h)))
             self._h = h
             self._synced = None
-        ver = tuple(p._version for p in self._ordered_params())
+        ver = self._param_version()
         if ver != self._synced:
             theta = self.flat_parameters()
             _lib.check(lib.nfisam_flow_set_params(self._h, theta.ctypes.data_as(ctypes.c_void_p), theta.size))
@@ -125,11 +207,11 @@ class NSF_AR(nn.Module):
     def pull_parameters(self):
         """Copy the device parameters (e.g. after on-device training) back into the nn.Parameters."""
         lib = _lib.load()
-        n = sum(p.numel() for p in self._ordered_params())
+        n = self._theta.size
         theta = np.empty(n, np.float32)
         _lib.check(lib.nfisam_flow_get_params(self._h, theta.ctypes.data_as(ctypes.c_void_p), n))
         self.load_flat_parameters(theta)
-        self._synced = tuple(p._version for p in self._ordered_params())
+        self._synced = self._param_version()
 
     def __del__(self):
         try:
@@ -191,11 +273,16 @@ class NSF_AR(nn.Module):
         out = torch.empty((n, f), dtype=torch.float32, device=zd.device)
         ld = torch.empty((n,), dtype=torch.float32, device=zd.device) if want_logdet else None
         aff = None
-        keep = None
         if norm is not None:
-            mean, std, circ = norm
-            keep = (self._in(mean), self._in(std),
-                    torch.as_tensor(np.asarray(circ, dtype=np.uint8)).to(self._dev()).contiguous())
+            # device copies of (mean, std, circular) are cached per norm tuple (same object => same constants)
+            cache = self.__dict__.setdefault("_norm_dev", {})
+            keep = cache.get(id(norm))
+            if keep is None or keep[3] is not norm:
+                mean, std, circ = norm
+                keep = (self._in(mean), self._in(std),
+                        torch.as_tensor(np.asarray(circ, dtype=np.uint8)).to(self._dev()).contiguous(), norm)
+                cache.clear()
+                cache[id(norm)] = keep
             aff = _lib.nf_affine(keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr())
         _lib.check(lib.nfisam_flow_inverse(h, zd.data_ptr(), xs.data_ptr() if sep else None, n, sep, f, out.data_ptr(),
                                            ld.data_ptr() if want_logdet else None,
@@ -267,7 +354,7 @@ class NSF_AR(nn.Module):
         if d != self.dim:
             raise ValueError("data must have `dim` columns")
         loss = ctypes.c_float(0.0)
-        g = np.empty(sum(p.numel() for p in self._ordered_params()), np.float32)
+        g = np.empty(self._theta.size, np.float32)
         _lib.check(lib.nfisam_flow_loss_grad(h, xd.data_ptr(), n, ctypes.byref(loss), g.ctypes.data_as(ctypes.c_void_p),
                                              self._stream()))
         return float(loss.value), g
