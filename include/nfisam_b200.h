@@ -114,6 +114,10 @@ typedef struct nf_affine {
 int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim, int out_dim,
                         float* x_out_dev, float* logdet_dev, const nf_affine* norm, void* stream);
 int nfisam_flow_pop_bad_count(nf_flow_t* f, void* stream, int64_t* count);
+/* Redirect the handle's negative-discriminant counter to a caller-owned device counter (uint64, must stay
+ * valid while attached; NULL restores the internal one).  Lets a scheduler run many flows' inverses without a
+ * per-call synchronisation and check one shared counter at the end of a pass. */
+int nfisam_flow_set_bad_counter(nf_flow_t* f, unsigned long long* counter_dev);
 
 /* Host-buffer convenience used for the end-to-end numbers: pinned staging, chunked
  * H2D -> kernel -> D2H pipelining on two internal streams.  Synchronous. */

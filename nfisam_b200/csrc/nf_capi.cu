@@ -76,6 +76,7 @@ struct nf_flow {
     float* d_grad = nullptr;
     int adam_steps = 0;
     unsigned long long* d_bad = nullptr;
+    unsigned long long* d_bad_ext = nullptr;   // caller-owned counter (nfisam_flow_set_bad_counter)
     // training scratch
     float* d_loss_part = nullptr;
     size_t loss_part_cap = 0;
@@ -273,7 +274,13 @@ int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev
     }
     DeviceGuard g(f->device);
     return nf_launch_inverse(f->fd, f->d_pk, z_dev, x_sep_dev, n, sep_dim, out_dim, x_out_dev, logdet_dev, mean, stdv, circ,
-                             f->d_bad, f->device, (cudaStream_t)stream);
+                             f->d_bad_ext ? f->d_bad_ext : f->d_bad, f->device, (cudaStream_t)stream);
+}
+
+int nfisam_flow_set_bad_counter(nf_flow_t* f, unsigned long long* counter_dev) {
+    if (!f) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    f->d_bad_ext = counter_dev;
+    return NF_OK;
 }
 
 int nfisam_flow_pop_bad_count(nf_flow_t* f, void* stream, int64_t* count) {

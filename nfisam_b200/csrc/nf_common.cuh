@@ -124,7 +124,16 @@ __device__ __forceinline__ float nf_sigmoid_sp(float v) {
 #define NF_EDGE_DERIV 0.99999994f
 
 // packed dual-FP32 arithmetic (fma/add/mul.rn.f32x2, new on sm_100): halves the issue slots
-__device__ __forceinline__ float2 nf_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#ifndef NF_SCALAR_FMA
+#define NF_SCALAR_FMA 0
+#endif
+__device__ __forceinline__ float2 nf_fma2(float2 a, float2 b, float2 c) {
+#if NF_SCALAR_FMA
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
+    return __ffma2_rn(a, b, c);
+#endif
+}
 __device__ __forceinline__ float2 nf_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 nf_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 nf_dup(float v) { return make_float2(v, v); }

@@ -294,6 +294,35 @@ class NSF_AR(nn.Module):
             raise AssertionError(f"negative discriminant in the inverse spline for {bad.value} samples")
         return out.to(src_device), (ld.to(src_device) if want_logdet else None)
 
+    def inverse_device(self, z_dev, x_s_dev, norm=None, counter=None):
+        """Asynchronous device-to-device variant of inverse_given_separator for schedulers: float32 CUDA tensors in,
+        CUDA tensor out, no host synchronisation.  `counter` is a CUDA int64 tensor of one element that accumulates
+        the number of negative discriminants (checked by the caller at the end of its pass)."""
+        lib = _lib.load()
+        h = self.handle()
+        n, f = z_dev.shape
+        sep = 0 if x_s_dev is None else int(x_s_dev.shape[1])
+        out = torch.empty((n, f), dtype=torch.float32, device=z_dev.device)
+        aff = None
+        if norm is not None:
+            cache = self.__dict__.setdefault("_norm_dev", {})
+            keep = cache.get(id(norm))
+            if keep is None or keep[3] is not norm:
+                mean, std, circ = norm
+                keep = (self._in(mean), self._in(std),
+                        torch.as_tensor(np.asarray(circ, dtype=np.uint8)).to(self._dev()).contiguous(), norm)
+                cache.clear()
+                cache[id(norm)] = keep
+            aff = _lib.nf_affine(keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr())
+        _lib.check(lib.nfisam_flow_set_bad_counter(h, counter.data_ptr() if counter is not None else None))
+        try:
+            _lib.check(lib.nfisam_flow_inverse(h, z_dev.data_ptr(), x_s_dev.data_ptr() if sep else None, n, sep, f,
+                                               out.data_ptr(), None, ctypes.byref(aff) if aff is not None else None,
+                                               self._stream()))
+        finally:
+            lib.nfisam_flow_set_bad_counter(h, None)
+        return out
+
     def inverse(self, z):
         """(x, log_det) like src/flows/flows.py:95-113."""
         return self._inverse(z, None, want_logdet=True)

@@ -135,6 +135,15 @@ class NormalizingFlowModelWithSeparator(NormalizingFlowModel, ConditionalSampler
             raise ValueError(f"separator dim {obs_dim} + latent dim {z.shape[1]} exceeds the model dim {self.dim}")
         return self.flows[0].inverse_given_separator(z, xs, norm=self._norm())
 
+    def draw_latent(self, n, obs_dim, conditional_dim):
+        """The latent block conditional_sample_given_observation would draw (same RNG consumption)."""
+        return torch.randn((n, self.prior.dim), dtype=torch.float32, generator=self.rng)[:, obs_dim:obs_dim + conditional_dim]
+
+    def conditional_sample_device(self, z_dev, x_s_dev, counter=None):
+        """Device-resident conditional sampling: latent draws and UN-normalised separator samples as CUDA tensors,
+        frontal samples returned as a CUDA tensor, nothing synchronises."""
+        return self.flows[0].inverse_device(z_dev, x_s_dev, norm=self._norm(), counter=counter)
+
     def separator_forward(self, x):
         """Push separator samples to the latent space: (z, separator_prior_logprob, separator_log_det) in the
         reference's output layout (NFiSAM.py:157-173)."""
@@ -290,6 +299,8 @@ class NFiSAM(FactorGraphSolver):
     def sample_posterior(self, timer=None, *args, **kwargs):
         if self._scheduler.distributed or self._args.deterministic_cliques:
             return self._scheduler.sample_posterior(timer=timer)
+        if torch.cuda.is_available():
+            return self._scheduler.sample_posterior_device(timer=timer)
         return super().sample_posterior(timer=timer)
 
 

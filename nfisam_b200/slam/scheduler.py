@@ -175,7 +175,66 @@ class CliqueScheduler:
                                                   torch.tensor(rest[:d]), torch.tensor(rest[d:2 * d]))
         return model, rest[2 * d:]
 
-    # -- down-pass ------------------------------------------------------------------------------------
+    # -- down-pass, single process: device-resident ----------------------------------------------------
+    def sample_posterior_device(self, timer: List[float] = None):
+        """Root -> leaves like FactorGraphSolver.sample_posterior (src/slam/FactorGraphSolver.py:497-550), same
+        clique order and the same CPU latent draws, but the separator samples never leave the GPU: one H2D copy of
+        all latent draws, one inverse kernel per clique reading / writing device tensors, one D2H copy of all
+        variables, one discriminant check for the whole pass."""
+        s = self.solver
+        n = s._args.posterior_sample_num
+        start = time.time()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        order = []
+        stack = [s._physical_bayes_tree.root]
+        while stack:
+            clique = stack.pop()
+            order.append(clique)
+            stack.extend(clique.children)
+        # latent draws on the host, in clique order (RNG parity with the serial loop), one upload
+        draws, width = [], 0
+        for clique in order:
+            model = s._clique_density_model[clique]
+            obs_dim = len(s._clique_true_obs[clique]) + clique.separator_dim
+            z = model.draw_latent(n, obs_dim, clique.frontal_dim)
+            draws.append((width, z.shape[1]))
+            width += z.shape[1]
+            order[len(draws) - 1] = (clique, z)
+        zall = torch.empty((n, width), dtype=torch.float32).pin_memory() if width else torch.empty((n, 0))
+        for (clique, z), (off, w) in zip(order, draws):
+            zall[:, off:off + w] = z
+        zdev = zall.to(dev, non_blocking=True)
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        dev_samples, col_of, total = {}, {}, 0
+        for (clique, _), (off, w) in zip(order, draws):
+            frontal = sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v])
+            separator = sorted(clique.separator, key=lambda v: s._reverse_ordering_map[v])
+            model = s._clique_density_model[clique]
+            obs = s._clique_true_obs[clique]
+            blocks = []
+            if len(obs):
+                blocks.append(torch.as_tensor(np.asarray(obs, dtype=np.float32)).to(dev).expand(n, len(obs)))
+            blocks += [dev_samples[v] for v in separator]
+            xs = torch.cat(blocks, dim=1).contiguous() if blocks else None
+            out = model.conditional_sample_device(zdev[:, off:off + w].contiguous(), xs, counter=counter)
+            col = 0
+            for v in frontal:
+                dev_samples[v] = out[:, col:col + v.dim]
+                col += v.dim
+        names = list(dev_samples.keys())
+        host = torch.cat([dev_samples[v] for v in names], dim=1).cpu().numpy() if names else np.zeros((n, 0), np.float32)
+        bad = int(counter.item())
+        if bad:
+            raise AssertionError(f"negative discriminant in the inverse spline for {bad} samples")   # src/flows/utils.py:133
+        samples, col = {}, 0
+        for v in names:
+            samples[v] = host[:, col:col + v.dim]
+            col += v.dim
+        if timer is not None:
+            timer.append(time.time() - start)
+        return samples
+
+    # -- down-pass, distributed / deterministic ---------------------------------------------------------
     def sample_posterior(self, timer: List[float] = None):
         """Root -> leaves with per-clique seeded latent draws; under torch.distributed the owner of a clique
         draws and broadcasts its frontal samples (the separator samples of its children)."""
