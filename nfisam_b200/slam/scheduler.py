@@ -175,14 +175,19 @@ class CliqueScheduler:
                                                   torch.tensor(rest[:d]), torch.tensor(rest[d:2 * d]))
         return model, rest[2 * d:]
 
-    # -- down-pass, single process: device-resident ----------------------------------------------------
-    def sample_posterior_device(self, timer: List[float] = None):
-        """Root -> leaves like FactorGraphSolver.sample_posterior (src/slam/FactorGraphSolver.py:497-550), same
-        clique order and the same CPU latent draws, but the separator samples never leave the GPU: one H2D copy of
-        all latent draws, one inverse kernel per clique reading / writing device tensors, one D2H copy of all
-        variables, one discriminant check for the whole pass."""
+    # -- down-pass: device-resident -------------------------------------------------------------------
+    def sample_posterior_device(self, timer: List[float] = None, seeded: bool = False):
+        """Root -> leaves like FactorGraphSolver.sample_posterior (src/slam/FactorGraphSolver.py:497-550): same
+        clique order and CPU latent draws (global torch RNG, or one generator per clique when `seeded`), but the
+        separator samples never leave the GPU: one H2D copy of all latent draws, one inverse kernel per clique
+        reading / writing device tensors, one D2H copy of all variables, one discriminant check for the pass.
+        Under torch.distributed (NCCL) a clique is sampled by its owner rank and its frontal samples are broadcast
+        device-to-device to the other ranks (the separator samples of its children)."""
+        import torch.distributed as dist
+
         s = self.solver
         n = s._args.posterior_sample_num
+        rank, world = self._world()
         start = time.time()
         dev = torch.device("cuda", torch.cuda.current_device())
         order = []
@@ -191,32 +196,50 @@ class CliqueScheduler:
             clique = stack.pop()
             order.append(clique)
             stack.extend(clique.children)
+        owners = [zlib.crc32(_clique_name(c).encode()) % world for c in order]
         # latent draws on the host, in clique order (RNG parity with the serial loop), one upload
-        draws, width = [], 0
-        for clique in order:
+        spans, zs, width = [], [], 0
+        for clique, owner in zip(order, owners):
             model = s._clique_density_model[clique]
-            obs_dim = len(s._clique_true_obs[clique]) + clique.separator_dim
-            z = model.draw_latent(n, obs_dim, clique.frontal_dim)
-            draws.append((width, z.shape[1]))
-            width += z.shape[1]
-            order[len(draws) - 1] = (clique, z)
-        zall = torch.empty((n, width), dtype=torch.float32).pin_memory() if width else torch.empty((n, 0))
-        for (clique, z), (off, w) in zip(order, draws):
-            zall[:, off:off + w] = z
+            w = clique.frontal_dim
+            if owner == rank:
+                obs_dim = len(s._clique_true_obs[clique]) + clique.separator_dim
+                if seeded:
+                    gen = torch.Generator()
+                    gen.manual_seed(self._seed_for(clique, 2))
+                    model.rng = gen
+                try:
+                    zs.append(model.draw_latent(n, obs_dim, w))
+                finally:
+                    model.rng = None
+                spans.append((width, w))
+                width += w
+            else:
+                zs.append(None)
+                spans.append((0, 0))
+        zall = torch.empty((n, max(width, 1)), dtype=torch.float32).pin_memory()
+        for z, (off, w) in zip(zs, spans):
+            if z is not None:
+                zall[:, off:off + w] = z
         zdev = zall.to(dev, non_blocking=True)
         counter = torch.zeros(1, dtype=torch.int64, device=dev)
-        dev_samples, col_of, total = {}, {}, 0
-        for (clique, _), (off, w) in zip(order, draws):
+        dev_samples = {}
+        for clique, owner, (off, w) in zip(order, owners, spans):
             frontal = sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v])
             separator = sorted(clique.separator, key=lambda v: s._reverse_ordering_map[v])
-            model = s._clique_density_model[clique]
-            obs = s._clique_true_obs[clique]
-            blocks = []
-            if len(obs):
-                blocks.append(torch.as_tensor(np.asarray(obs, dtype=np.float32)).to(dev).expand(n, len(obs)))
-            blocks += [dev_samples[v] for v in separator]
-            xs = torch.cat(blocks, dim=1).contiguous() if blocks else None
-            out = model.conditional_sample_device(zdev[:, off:off + w].contiguous(), xs, counter=counter)
+            if owner == rank:
+                model = s._clique_density_model[clique]
+                obs = s._clique_true_obs[clique]
+                blocks = []
+                if len(obs):
+                    blocks.append(torch.as_tensor(np.asarray(obs, dtype=np.float32)).to(dev).expand(n, len(obs)))
+                blocks += [dev_samples[v] for v in separator]
+                xs = torch.cat(blocks, dim=1).contiguous() if blocks else None
+                out = model.conditional_sample_device(zdev[:, off:off + w].contiguous(), xs, counter=counter)
+            else:
+                out = torch.empty((n, clique.frontal_dim), dtype=torch.float32, device=dev)
+            if world > 1:
+                dist.broadcast(out, src=owner)
             col = 0
             for v in frontal:
                 dev_samples[v] = out[:, col:col + v.dim]
@@ -234,10 +257,13 @@ class CliqueScheduler:
             timer.append(time.time() - start)
         return samples
 
-    # -- down-pass, distributed / deterministic ---------------------------------------------------------
+    # -- down-pass, host path (CPU communicator: gloo tests) -------------------------------------------
     def sample_posterior(self, timer: List[float] = None):
         """Root -> leaves with per-clique seeded latent draws; under torch.distributed the owner of a clique
-        draws and broadcasts its frontal samples (the separator samples of its children)."""
+        draws and broadcasts its frontal samples (the separator samples of its children).  Uses the
+        device-resident pass whenever the communicator lives on the GPU."""
+        if torch.cuda.is_available() and self._comm_device().type == "cuda" or (torch.cuda.is_available() and not self.distributed):
+            return self.sample_posterior_device(timer=timer, seeded=True)
         s = self.solver
         a = s._args
         n = a.posterior_sample_num
