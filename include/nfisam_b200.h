@@ -119,6 +119,18 @@ int nfisam_flow_pop_bad_count(nf_flow_t* f, void* stream, int64_t* count);
  * per-call synchronisation and check one shared counter at the end of a pass. */
 int nfisam_flow_set_bad_counter(nf_flow_t* f, unsigned long long* counter_dev);
 
+/* Building block of the posterior down-pass (FactorGraphSolver.sample_posterior, src/slam/FactorGraphSolver.py:497-550):
+ * nfisam_flow_inverse with fused normalisation, but the given columns are gathered from -- and the generated
+ * columns scattered into -- ONE device sample matrix S (n, ld_s) that holds every variable of the graph:
+ *   given column j (j < sep_dim)  = S[:, sep_cols[j]]  if sep_cols[j] >= 0, else the constant sep_const[j]
+ *                                   (the clique's observation vector, which the reference tiles, :518-526);
+ *   generated column c (c < out_dim) is written to S[:, out_cols[c]];
+ *   latent draws are z_dev[:, z_col0 .. z_col0 + out_dim) of a (n, ld_z) matrix.
+ * The index lists are host arrays (they travel as kernel parameters).  Asynchronous on `stream`. */
+int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z_col0, float* s_dev, int ld_s,
+                               const int32_t* sep_cols_host, const float* sep_const_host, int sep_dim,
+                               const int32_t* out_cols_host, int out_dim, int64_t n, const nf_affine* norm, void* stream);
+
 /* Host-buffer convenience used for the end-to-end numbers: pinned staging, chunked
  * H2D -> kernel -> D2H pipelining on two internal streams.  Synchronous. */
 int nfisam_flow_log_prob_host(nf_flow_t* f, const float* x_host, int64_t n, int d_in, float* logp_host);

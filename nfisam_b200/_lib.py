@@ -81,6 +81,8 @@ SYMBOLS = {
     "nfisam_flow_inverse": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _P, ctypes.POINTER(nf_affine), _P]),
     "nfisam_flow_pop_bad_count": (_INT, [_P, _P, ctypes.POINTER(_I64)]),
     "nfisam_flow_set_bad_counter": (_INT, [_P, _P]),
+    "nfisam_flow_inverse_gather": (_INT, [_P, _P, _INT, _INT, _P, _INT, _P, _P, _INT, _P, _INT, _I64,
+                                          ctypes.POINTER(nf_affine), _P]),
     "nfisam_flow_log_prob_host": (_INT, [_P, _P, _I64, _INT, _P]),
     "nfisam_flow_inverse_host": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _P, _P, _P]),
     "nfisam_flow_train": (_INT, [_P, _P, _I64, ctypes.POINTER(nf_train_cfg), _P, ctypes.POINTER(ctypes.c_int32), _P]),

@@ -277,6 +277,30 @@ int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev
                              f->d_bad_ext ? f->d_bad_ext : f->d_bad, f->device, (cudaStream_t)stream);
 }
 
+int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z_col0, float* s_dev, int ld_s,
+                               const int32_t* sep_cols_host, const float* sep_const_host, int sep_dim,
+                               const int32_t* out_cols_host, int out_dim, int64_t n, const nf_affine* norm, void* stream) {
+    if (!f || !z_dev || !s_dev || !out_cols_host) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n < 0 || sep_dim < 0 || out_dim < 1 || sep_dim + out_dim > f->fd.d)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad n / sep_dim / out_dim (sep_dim + out_dim must be <= dim)");
+    if (sep_dim > 0 && !sep_cols_host) return nf_set_error(NF_ERR_BAD_ARG, "sep_cols_host is NULL");
+    for (int j = 0; j < sep_dim; ++j)
+        if (sep_cols_host[j] >= ld_s || (sep_cols_host[j] < 0 && !sep_const_host))
+            return nf_set_error(NF_ERR_BAD_ARG, "given column %d out of range / constant missing", j);
+    for (int c = 0; c < out_dim; ++c)
+        if (out_cols_host[c] < 0 || out_cols_host[c] >= ld_s) return nf_set_error(NF_ERR_BAD_ARG, "output column %d out of range", c);
+    if (z_col0 < 0 || z_col0 + out_dim > ld_z) return nf_set_error(NF_ERR_BAD_ARG, "latent columns out of range");
+    const float* mean = nullptr; const float* stdv = nullptr; const uint8_t* circ = nullptr;
+    if (norm) {
+        if (!norm->mean_dev || !norm->std_dev || !norm->circular_dev) return nf_set_error(NF_ERR_BAD_ARG, "incomplete nf_affine");
+        mean = norm->mean_dev; stdv = norm->std_dev; circ = norm->circular_dev;
+    }
+    DeviceGuard g(f->device);
+    return nf_launch_inverse_gather(f->fd, f->d_pk, z_dev, ld_z, z_col0, s_dev, ld_s, sep_cols_host, sep_const_host, sep_dim,
+                                    out_cols_host, out_dim, n, mean, stdv, circ, f->d_bad_ext ? f->d_bad_ext : f->d_bad,
+                                    f->device, (cudaStream_t)stream);
+}
+
 int nfisam_flow_set_bad_counter(nf_flow_t* f, unsigned long long* counter_dev) {
     if (!f) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
     f->d_bad_ext = counter_dev;

@@ -88,12 +88,21 @@ __global__ void nf_rowsum_kernel(const float* __restrict__ ws, int64_t n, int d_
     logdet[r] = acc;
 }
 
-template <int K, int H>
+// Column indirection for the posterior down-pass (nfisam_flow_inverse_gather): given column j comes from
+// S[:, sep_cols[j]] (or is the constant sep_const[j] when sep_cols[j] < 0), generated column c goes to S[:, out_cols[c]].
+struct NfGather {
+    int sep_cols[NF_MAX_DIM];
+    float sep_const[NF_MAX_DIM];
+    int out_cols[NF_MAX_DIM];
+    int ld_s, ld_z, z_col0;
+};
+
+template <int K, int H, bool GATHER>
 __global__ void __launch_bounds__(TPB)
 nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, float B, const float* __restrict__ zin,  // d = sep + generated dims
                   const float* __restrict__ xsep, int64_t n, float* __restrict__ xout, float* __restrict__ logdet,
                   const float* __restrict__ mean, const float* __restrict__ stdv, const uint8_t* __restrict__ circ,
-                  unsigned long long* __restrict__ bad_count) {
+                  unsigned long long* __restrict__ bad_count, const __grid_constant__ NfGather ga) {
     constexpr int PP = ((3 * K - 1) + 3) & ~3;
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;
@@ -110,7 +119,9 @@ nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, floa
         __syncthreads();
         for (int t = threadIdx.x; t < cnt * sep; t += TPB) {
             const int r = t / sep, c = t - r * sep;
-            float v = xsep[s0 * sep + t];
+            float v;
+            if (GATHER) v = ga.sep_cols[c] >= 0 ? xout[(s0 + r) * ga.ld_s + ga.sep_cols[c]] : ga.sep_const[c];
+            else v = xsep[s0 * sep + t];
             if (has_norm) {
                 v = v - mean[c];
                 if (circ[c]) v = nf_wrap_pipi(v);
@@ -120,7 +131,7 @@ nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, floa
         }
         for (int t = threadIdx.x; t < cnt * f; t += TPB) {
             const int r = t / f, c = t - r * f;
-            zs[r * dp + c] = zin[s0 * f + t];
+            zs[r * dp + c] = GATHER ? zin[(s0 + r) * ga.ld_z + ga.z_col0 + c] : zin[s0 * f + t];
         }
         __syncthreads();
         if (threadIdx.x < cnt) {
@@ -147,7 +158,8 @@ nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, floa
                 v = fmaf(v, stdv[sep + c], mean[sep + c]);
                 if (circ[sep + c]) v = nf_wrap_pipi(v);
             }
-            xout[s0 * f + t] = v;
+            if (GATHER) xout[(s0 + r) * ga.ld_s + ga.out_cols[c]] = v;
+            else xout[s0 * f + t] = v;
         }
     }
 }
@@ -183,22 +195,22 @@ int launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_
     return nf_check_launch("nf_forward_kernel");
 }
 
-template <int K, int H>
+template <int K, int H, bool GATHER>
 int launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep,
                    int out_dim, float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
-                   unsigned long long* bad, int device, cudaStream_t st) {
+                   unsigned long long* bad, const NfGather& ga, int device, cudaStream_t st) {
     const int d_end = sep + out_dim;
     const int wcount = nf_block_off(d_end, H, fd.Pp);
     const int dp = d_end | 1;
     const size_t smem = sizeof(float) * ((size_t)wcount + 2 * (size_t)TPB * dp);
-    auto kern = nf_inverse_kernel<K, H>;
+    auto kern = nf_inverse_kernel<K, H, GATHER>;
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return nf_set_error(NF_ERR_UNSUPPORTED, "flow does not fit in shared memory");
     }
     const int64_t tiles = (n + TPB - 1) / TPB;
     const int grid = grid_for(kern, smem, tiles, device);
-    kern<<<grid, TPB, smem, st>>>(pk, wcount, d_end, sep, fd.B, zin, xsep, n, xout, logdet, mean, stdv, circ, bad);
+    kern<<<grid, TPB, smem, st>>>(pk, wcount, d_end, sep, fd.B, zin, xsep, n, xout, logdet, mean, stdv, circ, bad, ga);
     nf_count_launch();
     return nf_check_launch("nf_inverse_kernel");
 }
@@ -220,9 +232,29 @@ int nf_launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, c
                       int out_dim, float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
                       unsigned long long* bad, int device, cudaStream_t st) {
     if (n == 0) return NF_OK;
+    static const NfGather none = {};
 #define NF_CASE(KK, HH) \
     if (fd.K == KK && fd.H == HH) \
-        return launch_inverse<KK, HH>(fd, pk, zin, xsep, n, sep, out_dim, xout, logdet, mean, stdv, circ, bad, device, st);
+        return launch_inverse<KK, HH, false>(fd, pk, zin, xsep, n, sep, out_dim, xout, logdet, mean, stdv, circ, bad, none, \
+                                             device, st);
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
+}
+
+int nf_launch_inverse_gather(const NfFlowDims& fd, const float* pk, const float* z, int ld_z, int z_col0, float* s_mat,
+                             int ld_s, const int32_t* sep_cols, const float* sep_const, int sep, const int32_t* out_cols,
+                             int out_dim, int64_t n, const float* mean, const float* stdv, const uint8_t* circ,
+                             unsigned long long* bad, int device, cudaStream_t st) {
+    if (n == 0) return NF_OK;
+    NfGather ga = {};
+    for (int j = 0; j < sep; ++j) { ga.sep_cols[j] = sep_cols[j]; ga.sep_const[j] = sep_const ? sep_const[j] : 0.0f; }
+    for (int c = 0; c < out_dim; ++c) ga.out_cols[c] = out_cols[c];
+    ga.ld_s = ld_s; ga.ld_z = ld_z; ga.z_col0 = z_col0;
+#define NF_CASE(KK, HH) \
+    if (fd.K == KK && fd.H == HH) \
+        return launch_inverse<KK, HH, true>(fd, pk, z, nullptr, n, sep, out_dim, s_mat, nullptr, mean, stdv, circ, bad, ga, \
+                                            device, st);
     NF_FOREACH_KH(NF_CASE)
 #undef NF_CASE
     return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");

@@ -36,6 +36,11 @@ int nf_launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, c
                       int out_dim, float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
                       unsigned long long* bad, int device, cudaStream_t st);
 
+int nf_launch_inverse_gather(const NfFlowDims& fd, const float* pk, const float* z, int ld_z, int z_col0, float* s_mat,
+                             int ld_s, const int32_t* sep_cols, const float* sep_const, int sep, const int32_t* out_cols,
+                             int out_dim, int64_t n, const float* mean, const float* stdv, const uint8_t* circ,
+                             unsigned long long* bad, int device, cudaStream_t st);
+
 // nf_train_kernel.cu
 struct NfTrainCtrl {
     int stop;               // 1: the stopping rule fired (or the loss went NaN)

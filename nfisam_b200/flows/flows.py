@@ -323,6 +323,37 @@ class NSF_AR(nn.Module):
             lib.nfisam_flow_set_bad_counter(h, None)
         return out
 
+    def _affine(self, norm):
+        cache = self.__dict__.setdefault("_norm_dev", {})
+        keep = cache.get(id(norm))
+        if keep is None or keep[3] is not norm:
+            mean, std, circ = norm
+            keep = (self._in(mean), self._in(std),
+                    torch.as_tensor(np.asarray(circ, dtype=np.uint8)).to(self._dev()).contiguous(), norm)
+            cache.clear()
+            cache[id(norm)] = keep
+        return _lib.nf_affine(keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr())
+
+    def inverse_gather(self, z_dev, z_col0, s_dev, sep_cols, sep_const, out_cols, norm=None, counter=None):
+        """One clique of the posterior down-pass on a device sample matrix (nfisam_flow_inverse_gather): given columns
+        are read from s_dev (or are constants), generated columns are written into s_dev.  No synchronisation."""
+        lib = _lib.load()
+        h = self.handle()
+        sep, out = len(sep_cols), len(out_cols)
+        sc = (ctypes.c_int32 * max(sep, 1))(*[int(c) for c in sep_cols])
+        sk = (ctypes.c_float * max(sep, 1))(*[float(c) for c in sep_const])
+        oc = (ctypes.c_int32 * out)(*[int(c) for c in out_cols])
+        aff = self._affine(norm) if norm is not None else None
+        if counter is not None:
+            _lib.check(lib.nfisam_flow_set_bad_counter(h, counter.data_ptr()))
+        try:
+            _lib.check(lib.nfisam_flow_inverse_gather(h, z_dev.data_ptr(), int(z_dev.shape[1]), int(z_col0), s_dev.data_ptr(),
+                                                      int(s_dev.shape[1]), sc, sk, sep, oc, out, int(s_dev.shape[0]),
+                                                      ctypes.byref(aff) if aff is not None else None, self._stream()))
+        finally:
+            if counter is not None:
+                lib.nfisam_flow_set_bad_counter(h, None)
+
     def inverse(self, z):
         """(x, log_det) like src/flows/flows.py:95-113."""
         return self._inverse(z, None, want_logdet=True)

@@ -223,36 +223,33 @@ class CliqueScheduler:
                 zall[:, off:off + w] = z
         zdev = zall.to(dev, non_blocking=True)
         counter = torch.zeros(1, dtype=torch.int64, device=dev)
-        dev_samples = {}
+        # one device matrix holds every variable; each clique's frontal block is a contiguous column range
+        col_of, total = {}, 0
+        for clique in order:
+            for v in sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v]):
+                col_of[v] = total
+                total += v.dim
+        S = torch.empty((n, total), dtype=torch.float32, device=dev)
         for clique, owner, (off, w) in zip(order, owners, spans):
             frontal = sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v])
             separator = sorted(clique.separator, key=lambda v: s._reverse_ordering_map[v])
+            out_cols = [col_of[v] + k for v in frontal for k in range(v.dim)]
             if owner == rank:
                 model = s._clique_density_model[clique]
-                obs = s._clique_true_obs[clique]
-                blocks = []
-                if len(obs):
-                    blocks.append(torch.as_tensor(np.asarray(obs, dtype=np.float32)).to(dev).expand(n, len(obs)))
-                blocks += [dev_samples[v] for v in separator]
-                xs = torch.cat(blocks, dim=1).contiguous() if blocks else None
-                out = model.conditional_sample_device(zdev[:, off:off + w].contiguous(), xs, counter=counter)
-            else:
-                out = torch.empty((n, clique.frontal_dim), dtype=torch.float32, device=dev)
+                obs = [float(o) for o in s._clique_true_obs[clique]]
+                sep_cols = [-1] * len(obs) + [col_of[v] + k for v in separator for k in range(v.dim)]
+                sep_const = obs + [0.0] * (len(sep_cols) - len(obs))
+                model.flows[0].inverse_gather(zdev, off, S, sep_cols, sep_const, out_cols, norm=model._norm(), counter=counter)
             if world > 1:
-                dist.broadcast(out, src=owner)
-            col = 0
-            for v in frontal:
-                dev_samples[v] = out[:, col:col + v.dim]
-                col += v.dim
-        names = list(dev_samples.keys())
-        host = torch.cat([dev_samples[v] for v in names], dim=1).cpu().numpy() if names else np.zeros((n, 0), np.float32)
+                block = S[:, out_cols[0]:out_cols[-1] + 1].contiguous()
+                dist.broadcast(block, src=owner)
+                if owner != rank:
+                    S[:, out_cols[0]:out_cols[-1] + 1] = block
+        host = S.cpu().numpy()
         bad = int(counter.item())
         if bad:
             raise AssertionError(f"negative discriminant in the inverse spline for {bad} samples")   # src/flows/utils.py:133
-        samples, col = {}, 0
-        for v in names:
-            samples[v] = host[:, col:col + v.dim]
-            col += v.dim
+        samples = {v: host[:, c:c + v.dim] for v, c in col_of.items()}
         if timer is not None:
             timer.append(time.time() - start)
         return samples
