@@ -10,26 +10,40 @@ class FactorGraph:
     def __init__(self):
         self._vars: List[Variable] = []
         self._factors: List[Factor] = []
-        self._neighbors: Dict[Variable, Set[Variable]] = {}
+        self._var_set: Set[Variable] = set()
+        self._adjacency = None            # built lazily: sub-graphs are created far more often than eliminated
 
     vars = property(lambda self: self._vars)
     factors = property(lambda self: self._factors)
 
     def add_node(self, var: Variable) -> "FactorGraph":
-        if var in self._neighbors:
+        if var in self._var_set:
             raise KeyError("The node has already existed in the graph")
         self._vars.append(var)
-        self._neighbors[var] = set()
+        self._var_set.add(var)
+        self._adjacency = None
         return self
 
     def add_factor(self, factor: Factor) -> "FactorGraph":
+        for v in factor.vars:
+            if v not in self._var_set:
+                raise KeyError(f"factor touches a variable that is not in the graph: {v.name}")
         self._factors.append(factor)
-        vs = list(factor.vars)
-        for a in vs:
-            for b in vs:
-                if a != b:
-                    self._neighbors[a].add(b)
+        self._adjacency = None
         return self
+
+    @property
+    def _neighbors(self) -> Dict[Variable, Set[Variable]]:
+        if self._adjacency is None:
+            adj = {v: set() for v in self._vars}
+            for f in self._factors:
+                vs = list(f.vars)
+                for a in vs:
+                    for b in vs:
+                        if a != b:
+                            adj[a].add(b)
+            self._adjacency = adj
+        return self._adjacency
 
     def get_neighbors_in_factor_graph(self, key: Variable) -> Set[Variable]:
         return self._neighbors[key]

@@ -199,27 +199,25 @@ class CliqueScheduler:
         owners = [zlib.crc32(_clique_name(c).encode()) % world for c in order]
         # latent draws on the host, in clique order (RNG parity with the serial loop), one upload
         spans, zs, width = [], [], 0
-        for clique, owner in zip(order, owners):
-            model = s._clique_density_model[clique]
-            w = clique.frontal_dim
-            if owner == rank:
+        if seeded:
+            # one generator per step: every rank draws the same (n, total) latent matrix and a clique uses its own
+            # columns, so the draws do not depend on which rank owns the clique (nor on the number of ranks)
+            for clique in order:
+                spans.append((width, clique.frontal_dim))
+                width += clique.frontal_dim
+            gen = torch.Generator()
+            gen.manual_seed((7919 * s._step_counter + 104729 * 2 + int(s._args.seed)) % (2 ** 31 - 1))
+            zall = torch.randn((n, max(width, 1)), dtype=torch.float32, generator=gen).pin_memory()
+        else:
+            for clique, owner in zip(order, owners):
+                model = s._clique_density_model[clique]
+                w = clique.frontal_dim
                 obs_dim = len(s._clique_true_obs[clique]) + clique.separator_dim
-                if seeded:
-                    gen = torch.Generator()
-                    gen.manual_seed(self._seed_for(clique, 2))
-                    model.rng = gen
-                try:
-                    zs.append(model.draw_latent(n, obs_dim, w))
-                finally:
-                    model.rng = None
+                zs.append(model.draw_latent(n, obs_dim, w))      # the reference's RNG consumption, clique by clique
                 spans.append((width, w))
                 width += w
-            else:
-                zs.append(None)
-                spans.append((0, 0))
-        zall = torch.empty((n, max(width, 1)), dtype=torch.float32).pin_memory()
-        for z, (off, w) in zip(zs, spans):
-            if z is not None:
+            zall = torch.empty((n, max(width, 1)), dtype=torch.float32).pin_memory()
+            for z, (off, w) in zip(zs, spans):
                 zall[:, off:off + w] = z
         zdev = zall.to(dev, non_blocking=True)
         counter = torch.zeros(1, dtype=torch.int64, device=dev)

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Small run of every kernel of libnfisam_b200.so, meant to be executed under compute-sanitizer
+(memcheck / racecheck / synccheck) on a B200:
+
+    compute-sanitizer --tool memcheck  python scripts/sanitize_smoke.py
+    compute-sanitizer --tool racecheck python scripts/sanitize_smoke.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from nfisam_b200.factors import JointFactor  # noqa: E402
+from nfisam_b200.flows import NSF_AR  # noqa: E402
+from nfisam_b200.slam.graph_io import read_factor_graph_from_file  # noqa: E402
+
+
+def main():
+    torch.manual_seed(0)
+    rng = np.random.default_rng(0)
+    for (d, K, H) in ((5, 9, 8), (7, 15, 8), (4, 5, 16)):
+        f = NSF_AR(dim=d, K=K, hidden_dim=H)
+        x = torch.tensor(rng.standard_normal((333, d)).astype(np.float32) * 2.0)
+        f.forward(x)
+        f.forward(x, reference_layout=False)
+        f.log_prob(x[:, :max(1, d - 2)].contiguous())
+        f.inverse(x)
+        f.inverse_given_separator(x[:, :2].contiguous(), x[:, :2].contiguous())
+        f.loss_and_grad(x)
+        f.fit(x, 12, 0.01, average_window=5)
+        big = torch.tensor(rng.standard_normal((16400, d)).astype(np.float32))
+        f.fit(big, 3, 0.01, average_window=0)           # plain (large-batch) mode
+        S = torch.zeros((333, 9), device="cuda")
+        z = torch.randn(333, 6, device="cuda")
+        f.inverse_gather(z, 1, S, [-1, 0], [0.3, 0.0], [4, 5], norm=(np.zeros(d, np.float32), np.ones(d, np.float32),
+                                                                    np.zeros(d, np.uint8)))
+    nodes, truth, factors = read_factor_graph_from_file(os.path.join(ROOT, "tests", "data", "small_case1_da.fg"))
+    jf = JointFactor(factors, nodes)
+    xx = np.concatenate([truth[v] for v in nodes]) + rng.standard_normal((500, 22)) * 0.3
+    jf.log_pdf(xx, per_factor=True)
+    mix = [f for f in factors if hasattr(f, "posterior_weights")][0]
+    col = jf._col_of
+    mix.posterior_weights({v: xx[:, col[v]:col[v] + v.dim] for v in mix.vars})
+    torch.cuda.synchronize()
+    print("sanitize_smoke: done")
+
+
+if __name__ == "__main__":
+    main()
