@@ -196,7 +196,19 @@ class CliqueScheduler:
             clique = stack.pop()
             order.append(clique)
             stack.extend(clique.children)
-        owners = [zlib.crc32(_clique_name(c).encode()) % world for c in order]
+        # Ownership by top-level subtree: the root clique is sampled redundantly by every rank (replicated model,
+        # deterministic kernel => identical separator samples everywhere, no broadcast needed), each child subtree
+        # of the root is sampled entirely by one rank, and ONE all-reduce assembles the sample matrix at the end.
+        # (Broadcasting every clique's frontal block was measured at 25 ms/step on 8 GPUs for a 512-pose graph
+        # against 12 ms for the whole pass on one GPU: per-clique collectives are latency-bound.)
+        owner_of = {id(s._physical_bayes_tree.root): -1}
+        for k, child in enumerate(s._physical_bayes_tree.root.children):
+            stack2 = [child]
+            while stack2:
+                c = stack2.pop()
+                owner_of[id(c)] = k % world
+                stack2.extend(c.children)
+        owners = [owner_of[id(c)] for c in order]
         # latent draws on the host, in clique order (RNG parity with the serial loop), one upload
         spans, zs, width = [], [], 0
         if seeded:
@@ -227,22 +239,23 @@ class CliqueScheduler:
             for v in sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v]):
                 col_of[v] = total
                 total += v.dim
-        S = torch.empty((n, total), dtype=torch.float32, device=dev)
+        S = torch.zeros((n, total), dtype=torch.float32, device=dev)
         for clique, owner, (off, w) in zip(order, owners, spans):
             frontal = sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v])
             separator = sorted(clique.separator, key=lambda v: s._reverse_ordering_map[v])
             out_cols = [col_of[v] + k for v in frontal for k in range(v.dim)]
-            if owner == rank:
+            if owner == rank or owner < 0:
                 model = s._clique_density_model[clique]
                 obs = [float(o) for o in s._clique_true_obs[clique]]
                 sep_cols = [-1] * len(obs) + [col_of[v] + k for v in separator for k in range(v.dim)]
                 sep_const = obs + [0.0] * (len(sep_cols) - len(obs))
                 model.flows[0].inverse_gather(zdev, off, S, sep_cols, sep_const, out_cols, norm=model._norm(), counter=counter)
-            if world > 1:
-                block = S[:, out_cols[0]:out_cols[-1] + 1].contiguous()
-                dist.broadcast(block, src=owner)
-                if owner != rank:
-                    S[:, out_cols[0]:out_cols[-1] + 1] = block
+        if world > 1:
+            if rank != 0:     # the redundantly sampled root block is contributed by rank 0 only
+                root_cols = [col_of[v] + k for v in s._physical_bayes_tree.root.frontal for k in range(v.dim)]
+                S[:, min(root_cols):max(root_cols) + 1] = 0.0
+            dist.all_reduce(S, op=dist.ReduceOp.SUM)       # x + 0 + ... + 0 is exact: identical on every rank
+            dist.all_reduce(counter, op=dist.ReduceOp.SUM)
         host = S.cpu().numpy()
         bad = int(counter.item())
         if bad:
