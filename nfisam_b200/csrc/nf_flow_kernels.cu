@@ -9,9 +9,6 @@
 namespace {
 
 constexpr int TPB = 128;
-#ifndef NF_FWD_MIN_BLOCKS
-#define NF_FWD_MIN_BLOCKS 1
-#endif
 
 __device__ __forceinline__ void load_weights(float* sw, const float* __restrict__ pk, int count) {
     const float4* src = reinterpret_cast<const float4*>(pk);
@@ -23,7 +20,7 @@ __device__ __forceinline__ void load_weights(float* sw, const float* __restrict_
 constexpr int WANT_Z = 1, WANT_LD = 2, WANT_LP = 4, REF_LAYOUT = 8;
 
 template <int K, int H>
-__global__ void __launch_bounds__(TPB, NF_FWD_MIN_BLOCKS)
+__global__ void __launch_bounds__(TPB)
 nf_forward_kernel(const float* __restrict__ pk, int wcount, int d_in, float B, const float* __restrict__ x, int64_t n,
                   float* __restrict__ z, float* __restrict__ logdet, float* __restrict__ logp, float* __restrict__ ws,
                   int mode) {
