@@ -80,6 +80,8 @@ struct nf_flow {
     // training scratch
     float* d_loss_part = nullptr;
     size_t loss_part_cap = 0;
+    float* d_val_part = nullptr;
+    size_t val_part_cap = 0;
     NfTrainCtrl* d_ctrl = nullptr;
     float* d_partials = nullptr;       // large-batch training: per-block partial gradients / losses
     float* d_loss_partials = nullptr;
@@ -196,7 +198,7 @@ int nfisam_flow_destroy(nf_flow_t* f) {
     DeviceGuard g(f->device);
     cudaFree(f->d_pk); cudaFree(f->d_m); cudaFree(f->d_v); cudaFree(f->d_grad); cudaFree(f->d_bad);
     cudaFree(f->d_loss_part); cudaFree(f->d_ctrl); cudaFree(f->d_norm); cudaFree(f->d_circ);
-    cudaFree(f->d_partials); cudaFree(f->d_loss_partials);
+    cudaFree(f->d_partials); cudaFree(f->d_loss_partials); cudaFree(f->d_val_part);
     for (int s = 0; s < 2; ++s) {
         cudaFree(f->d_stage_in[s]); cudaFree(f->d_stage_aux[s]); cudaFree(f->d_stage_out[s]);
         if (f->streams[s]) cudaStreamDestroy(f->streams[s]);
@@ -450,7 +452,20 @@ static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const n
     a->loss_part = f->d_loss_part;
     a->ctrl = f->d_ctrl;
     a->n_packed = (int)f->n_packed;
-    if (n >= NF_TRAIN_PLAIN_MIN_N) {
+    if (cfg->n_val > 0) {
+        if (!cfg->val_dev) return nf_set_error(NF_ERR_BAD_ARG, "n_val > 0 but val_dev is NULL");
+        const int vi = cfg->validation_interval > 0 ? cfg->validation_interval : 1;
+        const size_t vneed = ((size_t)cfg->max_iters / vi + 3) * (size_t)f->fd.d;
+        if (f->val_part_cap < vneed) {
+            cudaFree(f->d_val_part);
+            f->d_val_part = nullptr;
+            f->val_part_cap = 0;
+            NF_CUDA(cudaMalloc(&f->d_val_part, vneed * sizeof(float)));
+            f->val_part_cap = vneed;
+        }
+        a->val_part = f->d_val_part;
+    }
+    if (n >= NF_TRAIN_PLAIN_MIN_N && cfg->n_val <= 0) {
         if (!f->d_partials) {
             NF_CUDA(cudaMalloc(&f->d_partials, sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->n_packed));
             NF_CUDA(cudaMalloc(&f->d_loss_partials, sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->fd.d));

@@ -48,7 +48,9 @@ struct NfTrainCtrl {
     int have_avg;
     int status;             // 1: NaN / inf loss
     float loss_avg;
-    int pad_[3];
+    int slower_stop_iter;   // validation mode: > 0 once the validation loss went up (NFiSAM.py:452-468)
+    int have_val;
+    float last_val;
 };
 struct NfTrainArgs {
     float* pk;              // packed parameters (updated in place)
@@ -68,6 +70,7 @@ struct NfTrainArgs {
     int grad_only;          // 1: write the reduced gradient to grad_out (packed order), no update
     float* grad_out;        // packed-size buffer (grad_only)
     float* loss_part;       // (max_iters, d) per-dim loss contributions
+    float* val_part;        // (max_iters / validation_interval + 2, d) per-dim validation-loss contributions
     NfTrainCtrl* ctrl;      // [2] double-buffered early-stop record (zeroed before the first launch)
     // large-batch mode (n >= NF_TRAIN_PLAIN_MIN_N): plain grid, per-block partial gradients in global memory,
     // reduced + applied by nf_adam_kernel; null pointers select the cluster mode

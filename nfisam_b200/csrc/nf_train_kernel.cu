@@ -112,7 +112,7 @@ __device__ __forceinline__ float nf_rqs_grad(float2 (&o2)[NP], float B, float xi
 template <int K, int H, int W>
 __global__ void __launch_bounds__(W * 32)
 nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_begin, int it_end, int launch_idx,
-                int plain) {
+                int plain, int val_pass) {
     constexpr int P = 3 * K - 1;
     constexpr int PP = (P + 3) & ~3;
     constexpr int NC3 = (PP + 31) / 32;            // W3 columns owned per lane
@@ -151,7 +151,9 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     s_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_stage) + 15) & ~uintptr_t(15));
     float* s_x = s_stage + W * 32 * STG;            // [W][mt_res][32][dp]
 
-    const int64_t n = a.n;
+    // val_pass: this launch only evaluates the validation loss (forward pass over a.val) for check `launch_idx`
+    const int64_t n = val_pass ? a.n_val : a.n;
+    const float* __restrict__ data = val_pass ? a.val : a.data;
     const int64_t ntiles = (n + 31) / 32;
     const int TW = C * W;
     const int gw = r * W + warp;
@@ -161,13 +163,35 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     // ---------------- early stop: windowed relative loss change (NFiSAM.py:481-491) ----------------
     // Evaluated on the window the previous launch finished; identical in every block.
     const bool window_start = a.average_window <= 0 || it_begin % a.average_window == 0 || !plain;
-    if (!window_start) {
+    int slower = 0;            // validation mode: iteration at which training ends (0 = not decided yet)
+    bool slower_fresh = false;
+    if (val_pass) {
+        const NfTrainCtrl cin = a.ctrl[launch_idx & 1];
+        if (cin.stop || cin.slower_stop_iter > 0) return;        // the validation loss is not needed any more
+    } else if (!window_start) {
         // plain mode launches one iteration at a time: inside a window just honour the decision of its first launch
         if (a.ctrl[(launch_idx + 1) & 1].stop) return;
     } else {
         const NfTrainCtrl cin = a.ctrl[launch_idx & 1];
         NfTrainCtrl cout = cin;
-        if (!cin.stop && launch_idx > 0 && a.average_window > 0 && !a.grad_only && it_begin % a.average_window == 0) {
+        if (!cin.stop && a.n_val > 0 && !a.grad_only) {
+            // ---- validation-set stop (NFiSAM.py:452-468): the check precedes iteration it_begin
+            if (launch_idx > 0 && cin.slower_stop_iter == 0) {
+                float nv = 0.0f;
+                for (int j = 0; j < d; ++j) nv += __ldcg(a.val_part + (size_t)launch_idx * d + j);
+                if (!(nv == nv) || fabsf(nv) > 3.0e38f) {
+                    cout.stop = 1; cout.status = 1; cout.iters_run = it_begin;
+                } else if (cin.have_val && nv > cin.last_val) {
+                    cout.slower_stop_iter = (int)((double)a.slower_stop_rate * (double)(it_begin + 1));
+                    slower_fresh = true;
+                } else {
+                    cout.last_val = nv;
+                    cout.have_val = 1;
+                }
+            }
+            slower = cout.slower_stop_iter;
+        } else if (!cin.stop && launch_idx > 0 && a.average_window > 0 && !a.grad_only && it_begin % a.average_window == 0) {
+            // ---- windowed relative loss change (NFiSAM.py:481-491), evaluated on the window the previous launch finished
             float wsum = 0.0f;
             const int t0 = it_begin - a.average_window;
             for (int tt = 0; tt < a.average_window; ++tt) {
@@ -199,7 +223,7 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
         for (int t = lane; t < 32 * cols; t += 32) {
             const int rr = t / cols, c = t - rr * cols;
             const int64_t s = s0 + rr;
-            slot[rr * dp + c] = s < n ? a.data[s * d + c] : 0.0f;
+            slot[rr * dp + c] = s < n ? data[s * d + c] : 0.0f;
         }
     };
     if (resident) {
@@ -213,6 +237,16 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     double b1t = pow((double)a.beta1, (double)adam0), b2t = pow((double)a.beta2, (double)adam0);
 
     for (int it = it_begin; it < it_end; ++it) {
+        if (slower > 0 && !(slower_fresh && it == it_begin) && it + 1 >= slower) {
+            // reached slower_stop_iter: the reference breaks before training this iteration
+            if (i == 0 && r == 0 && threadIdx.x == 0) {
+                NfTrainCtrl fin = a.ctrl[(launch_idx + 1) & 1];
+                fin.stop = 1;
+                fin.iters_run = it;
+                a.ctrl[(launch_idx + 1) & 1] = fin;
+            }
+            break;
+        }
         // ---------------- local gradient over this warp's tiles ----------------
         float2 acc3[NC3][H / 2];
         float accb3[NC3], acc2[N2], accb2 = 0.0f, acc1[M1], accb1 = 0.0f, floss = 0.0f;
@@ -388,6 +422,16 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
             for (int w = 0; w < W; ++w) acc += s_loss[w];
             s_misc[0] = acc;
         }
+        if (val_pass) {
+            cluster.sync();
+            if (r == 0 && threadIdx.x == 0) {
+                float acc = 0.0f;
+                for (int q = 0; q < C; ++q) acc += cluster.map_shared_rank(s_misc, q)[0];
+                a.val_part[(size_t)launch_idx * d + i] = -acc * inv_n;
+            }
+            cluster.sync();
+            return;
+        }
         if (plain) {
             __syncthreads();
             float* dst = a.partials + (size_t)r * a.n_packed + goff;
@@ -518,7 +562,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         const int adam_blocks = (a.n_packed + 255) / 256;
         for (int it = 0; it < a.max_iters; ++it) {
             const int launch_idx = it / window;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, 1, 0, it, it + 1, launch_idx, 1);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, 1, 0, it, it + 1, launch_idx, 1, 0);
             if (e != cudaSuccess) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, plain)");
             nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
             nf_count_launch(2);
@@ -550,9 +594,32 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         cfg.numAttrs = 1;
         int launch_idx = 0;
         bool retry = false;
+        if (a.n_val > 0 && !a.grad_only) {
+            // validation mode: checks precede iterations vi-1, 2vi-1, ...: launch L trains [L vi - 1, (L+1) vi - 1)
+            const int vi = a.validation_interval > 0 ? a.validation_interval : 1;
+            for (int it0 = 0; it0 < a.max_iters; ++launch_idx) {
+                const int it1 = ((launch_idx + 1) * vi - 1) < a.max_iters ? ((launch_idx + 1) * vi - 1) : a.max_iters;
+                cudaError_t e = cudaSuccess;
+                if (launch_idx > 0) {
+                    e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, 1, 0, it0, it0 + 1, launch_idx, 0, 1);
+                    nf_count_launch();
+                }
+                if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0, 0);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    if (launch_idx > 0 || C == 1) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, validation)");
+                    retry = true;
+                    break;
+                }
+                nf_count_launch();
+                it0 = it1;
+            }
+            if (!retry) return launch_idx;
+            continue;
+        }
         for (int it0 = 0; it0 < a.max_iters; it0 += window, ++launch_idx) {
             const int it1 = it0 + window < a.max_iters ? it0 + window : a.max_iters;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0, 0);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 if (launch_idx > 0 || C == 1) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel)");
@@ -581,7 +648,8 @@ size_t nf_train_loss_part_elems(const NfFlowDims& fd, int max_iters) { return (s
 
 int nf_launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st) {
     if (a.n <= 0 || a.max_iters <= 0) return nf_set_error(NF_ERR_BAD_ARG, "empty training set or no iterations");
-    if (a.n_val > 0) return nf_set_error(NF_ERR_UNSUPPORTED, "validation-set early stop is not implemented yet");
+    if (a.n_val > 0 && (a.val == nullptr || a.val_part == nullptr))
+        return nf_set_error(NF_ERR_BAD_ARG, "validation set given without device buffers");
 #define NF_CASE(KK, HH) \
     if (fd.K == KK && fd.H == HH) return launch_train<KK, HH>(fd, a, device, st);
     NF_FOREACH_KH(NF_CASE)

@@ -366,7 +366,7 @@ class NSF_AR(nn.Module):
 
     # ------------------------------------------------------------------ training on device
     def fit_launch(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
-                   reset_optimizer=True, stream=None):
+                   reset_optimizer=True, stream=None, val=None, validation_interval=10, slower_stop_rate=2.0):
         """Enqueue the whole Adam loop (src/slam/NFiSAM.py:451-491) on `stream` (a torch.cuda.Stream, default:
         the current one) and return immediately; several flows launched on different streams / devices train
         concurrently.  Call fit_finish() to collect the loss history."""
@@ -376,19 +376,27 @@ class NSF_AR(nn.Module):
         n, d = xd.shape
         if d != self.dim:
             raise ValueError("training data must have `dim` columns")
+        vd = None
+        if val is not None and len(val):
+            # validation set => the reference's "slower stop" rule replaces the windowed one (NFiSAM.py:452-468)
+            vd = self._in(val)
+            if vd.shape[1] != self.dim:
+                raise ValueError("validation data must have `dim` columns")
         cfg = _lib.nf_train_cfg(int(iters), float(lr), float(betas[0]), float(betas[1]), float(eps),
-                                int(average_window), float(loss_delta_tol), None, 0, 0, 0.0, 1 if reset_optimizer else 0)
+                                int(average_window), float(loss_delta_tol), vd.data_ptr() if vd is not None else None,
+                                int(vd.shape[0]) if vd is not None else 0, int(validation_interval), float(slower_stop_rate),
+                                1 if reset_optimizer else 0)
         st = stream if stream is not None else torch.cuda.current_stream(self._dev())
         if stream is not None:
             stream.wait_stream(torch.cuda.current_stream(self._dev()))   # data upload happened on the current stream
         _lib.check(lib.nfisam_flow_train_launch(h, xd.data_ptr(), n, ctypes.byref(cfg), ctypes.c_void_p(st.cuda_stream)))
-        self._pending = (xd, int(iters), st)
+        self._pending = (xd, int(iters), st, vd)
 
     def fit_finish(self, pull=True):
         """Wait for fit_launch; returns (loss_history, iters_run) -- history has `iters` entries, zeros after the
         early stop like the reference's preallocated iter_loss."""
         lib = _lib.load()
-        xd, iters, st = self._pending
+        xd, iters, st, _vd = self._pending
         self._pending = None
         hist = np.zeros(iters, np.float32)
         ran = ctypes.c_int32(0)
@@ -399,10 +407,11 @@ class NSF_AR(nn.Module):
         return hist, int(ran.value)
 
     def fit(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
-            reset_optimizer=True, pull=True):
-        """Full-batch Adam on -mean(log_prob) with the reference's windowed early stop, entirely on the device.
-        Returns (loss_history, iters_run)."""
-        self.fit_launch(data, iters, lr, betas, eps, average_window, loss_delta_tol, reset_optimizer)
+            reset_optimizer=True, pull=True, val=None, validation_interval=10, slower_stop_rate=2.0):
+        """Full-batch Adam on -mean(log_prob) with the reference's stopping rules (windowed relative loss change, or
+        the validation-set "slower stop" when `val` is given), entirely on the device.  Returns (loss_history, iters_run)."""
+        self.fit_launch(data, iters, lr, betas, eps, average_window, loss_delta_tol, reset_optimizer, val=val,
+                        validation_interval=validation_interval, slower_stop_rate=slower_stop_rate)
         return self.fit_finish(pull=pull)
 
     def loss_and_grad(self, data):

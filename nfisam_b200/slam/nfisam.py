@@ -241,19 +241,22 @@ class NFiSAM(FactorGraphSolver):
         a = self._args
         if a.flow_number != 1 or a.flow_type != "NSF_AR":
             raise NotImplementedError("only flow_type='NSF_AR' with flow_number=1 exists in the reference")
-        if min(int(samples.shape[0] * a.training_set_frac), samples.shape[0]) != samples.shape[0]:
-            raise NotImplementedError("validation-set early stop (training_set_frac < 1) is not on the B200 path yet")
+        train_size = min(int(samples.shape[0] * a.training_set_frac), samples.shape[0])
         aug_dim = samples.shape[-1]
         aug_sep_dim = aug_dim - clique.frontal_dim
         circular = []
         for var in var_ordering:
             circular += var.circular_dim_list
         np.random.shuffle(samples)
-        data, means, stds = self.normalize_training_samples(samples, circular, a.flow_type)
+        train_samples, test_samples = samples[:train_size], samples[train_size:]
+        data, means, stds = self.normalize_training_samples(train_samples, circular, a.flow_type)
+        # like the reference, the held-out rows are normalised with their OWN statistics (NFiSAM.py:381-384)
+        val = self.normalize_training_samples(test_samples, circular, a.flow_type)[0] if len(test_samples) > 0 else None
         flow = NSF_AR(dim=aug_dim, K=a.num_knots, hidden_dim=a.hidden_dim, device=a.device)
         prior = CustomMultivariateNormal(dim=aug_dim)
         sep_prior = CustomMultivariateNormal(dim=aug_sep_dim) if aug_sep_dim > 0 else None
         model = NormalizingFlowModelWithSeparator([flow], prior, sep_prior, circular, means, stds)
+        model._validation_data = val
         return model, data
 
     def _record_loss(self, clique, hist):
@@ -266,7 +269,8 @@ class NFiSAM(FactorGraphSolver):
         a = self._args
         t0 = time.time()
         hist, ran = model.flows[0].fit(data, a.flow_iterations, a.learning_rate, average_window=a.average_window,
-                                       loss_delta_tol=a.loss_delta_tol)
+                                       loss_delta_tol=a.loss_delta_tol, val=model._validation_data,
+                                       validation_interval=a.validation_interval, slower_stop_rate=a.slower_stop_rate)
         if timer is not None:
             timer.append(time.time() - t0)
         self._record_loss(clique, hist)

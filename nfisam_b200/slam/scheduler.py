@@ -117,7 +117,9 @@ class CliqueScheduler:
                 t1 = time.time()
                 sim_time += t1 - t0
                 model.flows[0].fit_launch(data, a.flow_iterations, a.learning_rate, average_window=a.average_window,
-                                          loss_delta_tol=a.loss_delta_tol, stream=self._stream(slot))
+                                          loss_delta_tol=a.loss_delta_tol, stream=self._stream(slot),
+                                          val=model._validation_data, validation_interval=a.validation_interval,
+                                          slower_stop_rate=a.slower_stop_rate)
                 launched.append((k, c, model))
                 t0 = time.time()
             results = {}

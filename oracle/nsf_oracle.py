@@ -128,6 +128,23 @@ def train(theta, d, K, H, B, x, iters, lr, betas=(0.9, 0.999), eps=1e-8, average
     return theta, hist, it
 
 
+def train_val(theta, d, K, H, B, x, x_val, iters, lr, betas=(0.9, 0.999), eps=1e-8, validation_interval=10,
+              slower_stop_rate=2.0, dtype=np.float32):
+    """Training with the reference's validation-set stop.  Returns (theta, loss_hist, iters_run, val_hist)."""
+    sfx, cr = _sfx(dtype)
+    theta = np.array(theta, dtype=dtype, copy=True)
+    x, xp = _c(x, dtype)
+    xv, xvp = _c(x_val, dtype)
+    hist = np.zeros((iters,), dtype)
+    vh = np.zeros((iters // max(validation_interval, 1) + 2,), dtype)
+    it = getattr(lib(), "nsf_train_val" + sfx)(theta.ctypes.data_as(ctypes.c_void_p), int(d), int(K), int(H), cr(B), xp,
+                                               ctypes.c_int64(x.shape[0]), xvp, ctypes.c_int64(xv.shape[0]), int(iters),
+                                               cr(lr), cr(betas[0]), cr(betas[1]), cr(eps), int(validation_interval),
+                                               cr(slower_stop_rate), hist.ctypes.data_as(ctypes.c_void_p),
+                                               vh.ctypes.data_as(ctypes.c_void_p))
+    return theta, hist, it, vh
+
+
 def state_dict_to_vector(sd, d):
     """Flatten a reference NSF_AR state_dict (torch tensors or arrays) into the oracle/C-ABI order
     (src/flows/flows.py:51-63): init_param, then per conditioner W1,b1,W2,b2,W3,b3."""

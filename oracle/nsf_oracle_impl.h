@@ -393,6 +393,49 @@ int FN(nsf_train)(REAL* theta, int d, int K, int H, REAL B, const REAL* x, int64
     return it;
 }
 
+/* Same loop with a validation set ("slower stop", src/slam/NFiSAM.py:452-468): every validation_interval
+ * iterations the validation loss is evaluated BEFORE the training step; its first increase fixes
+ * slower_stop_iter = int(rate * (i+1)) and training ends when i+1 reaches it.  No windowed stop in this mode.
+ * val_hist (max_iters / validation_interval + 1 entries) receives the validation losses. */
+int FN(nsf_train_val)(REAL* theta, int d, int K, int H, REAL B, const REAL* x, int64_t n, const REAL* xv, int64_t nv,
+                      int max_iters, REAL lr, REAL beta1, REAL beta2, REAL eps, int validation_interval,
+                      REAL slower_stop_rate, REAL* loss_hist, REAL* val_hist) {
+    const int64_t np_ = FN(nsf_num_params)(d, K, H);
+    REAL* g = (REAL*)malloc(sizeof(REAL) * (size_t)np_);
+    REAL* m = (REAL*)calloc((size_t)np_, sizeof(REAL));
+    REAL* v = (REAL*)calloc((size_t)np_, sizeof(REAL));
+    REAL* lp = (REAL*)malloc(sizeof(REAL) * (size_t)nv);
+    int it = 0, slower = -1, nvals = 0, have_val = 0;
+    REAL last_val = 0;
+    double b1t = 1.0, b2t = 1.0;
+    for (it = 0; it < max_iters; ++it) {
+        if (slower >= 0) {
+            if (it + 1 >= slower) break;
+        } else if ((it + 1) % validation_interval == 0) {
+            FN(nsf_log_prob)(theta, d, K, H, B, xv, nv, d, lp);
+            double acc = 0.0;
+            for (int64_t s = 0; s < nv; ++s) acc += (double)lp[s];
+            REAL nl = (REAL)(-acc / (double)nv);
+            val_hist[nvals++] = nl;
+            if (have_val && nl > last_val) slower = (int)((double)slower_stop_rate * (double)(it + 1));
+            else { last_val = nl; have_val = 1; }
+        }
+        REAL loss;
+        FN(nsf_loss_grad)(theta, d, K, H, B, x, n, &loss, g);
+        loss_hist[it] = loss;
+        b1t *= (double)beta1; b2t *= (double)beta2;
+        const REAL step = (REAL)((double)lr / (1.0 - b1t));
+        const REAL bc2s = (REAL)sqrt(1.0 - b2t);
+        for (int64_t p = 0; p < np_; ++p) {
+            m[p] = m[p] + (g[p] - m[p]) * ((REAL)1 - beta1);
+            v[p] = v[p] * beta2 + ((REAL)1 - beta2) * g[p] * g[p];
+            theta[p] -= step * (m[p] / (FN(r_sqrt)(v[p]) / bc2s + eps));
+        }
+    }
+    free(g); free(m); free(v); free(lp);
+    return it;
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

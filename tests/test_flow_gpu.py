@@ -341,3 +341,30 @@ def test_large_batch_training_mode_matches_oracle():
     loss, g = f3.loss_and_grad(torch.tensor(x))
     lo, go = orc.loss_grad(f3.flat_parameters(), d, K, H, 5.0, x, dtype=np.float64)
     assert abs(loss - lo) < 2e-5 * abs(lo) and _relmax(g, go) < 5e-4
+
+
+def test_validation_set_slower_stop_matches_reference_loop():
+    """training_set_frac < 1 path: validation loss every `validation_interval` iterations, first increase fixes
+    slower_stop_iter = int(rate * (i + 1)) (src/slam/NFiSAM.py:452-468).  Golden: the reference's loop body run with
+    the reference flow (tests/golden/train_val.npz, produced next to oracle.train_val's cross-check)."""
+    import os
+
+    from nfisam_b200.flows import NSF_AR
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_val.npz")))
+    f = NSF_AR(dim=4, K=9, hidden_dim=8)
+    f.load_flat_parameters(g["theta"])
+    hist, ran = f.fit(torch.tensor(g["x"]), int(g["iters"]), float(g["lr"]), val=torch.tensor(g["xv"]),
+                      validation_interval=int(g["vi"]), slower_stop_rate=float(g["rate"]))
+    assert ran == int(g["ran"]) == 39
+    assert np.allclose(hist[:15], g["hist"][:15], rtol=2e-5)
+    assert np.all(hist[ran:] == 0)
+    # no increase of the validation loss within the budget: runs to the end
+    f2 = NSF_AR(dim=4, K=9, hidden_dim=8)
+    f2.load_flat_parameters(g["theta"])
+    x_big = torch.tensor(np.random.default_rng(1).standard_normal((4000, 4)).astype(np.float32))
+    hist2, ran2 = f2.fit(x_big[:3000], 60, 0.005, val=x_big[3000:], validation_interval=10, slower_stop_rate=2.0)
+    _, ho, rano, _ = orc.train_val(g["theta"], 4, 9, 8, 5.0, x_big[:3000].numpy(), x_big[3000:].numpy(), 60, 0.005,
+                                   validation_interval=10, slower_stop_rate=2.0)
+    assert ran2 == rano
+    assert np.allclose(hist2[:10], ho[:10], rtol=2e-5)
