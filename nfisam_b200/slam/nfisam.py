@@ -12,13 +12,14 @@ New relative to the reference: `fit_tree_density_models` / `sample_posterior` ru
 schedule of scheduler.py (cliques of one Bayes-tree level train concurrently on CUDA streams and, under
 torch.distributed, on different GPUs; NCCL only moves trained parameters up and separator samples down).
 """
+import math
 import os
 import time
 from typing import List
 
 import numpy as np
 import torch
-from scipy.stats import circmean, norm
+from scipy.stats import norm
 
 from ..flows import NSF_AR, CustomMultivariateNormal, NormalizingFlowModel
 from ..factors.factors import Factor
@@ -31,6 +32,15 @@ from .variables import Variable
 
 def theta_to_pipi(theta):
     return (theta + np.pi) % (2.0 * np.pi) - np.pi
+
+
+def circmean(samples, high=np.pi, low=-np.pi, axis=0):
+    """scipy.stats.circmean(samples, high, low, axis) restated without its array-API / nan-policy wrappers (0.8 ms per
+    call, a fifth of a clique's host time); bit-identical results (checked in tests/test_model_cpu.py)."""
+    period = high - low
+    scaled = samples * ((2.0 * math.pi) / period)
+    res = np.arctan2(np.sum(np.sin(scaled), axis=axis), np.sum(np.cos(scaled), axis=axis))
+    return (res * (period / (2.0 * math.pi)) - low) % period + low
 
 
 class NFiSAMArgs(SolverArgs):
@@ -247,7 +257,9 @@ class NFiSAM(FactorGraphSolver):
         circular = []
         for var in var_ordering:
             circular += var.circular_dim_list
-        np.random.shuffle(samples)
+        # same permutation and RNG consumption as the reference's in-place np.random.shuffle(samples) (NFiSAM.py:375),
+        # 25x faster than numpy's row-by-row shuffle of a 2-D array
+        samples = samples[np.random.permutation(samples.shape[0])]
         train_samples, test_samples = samples[:train_size], samples[train_size:]
         data, means, stds = self.normalize_training_samples(train_samples, circular, a.flow_type)
         # like the reference, the held-out rows are normalised with their OWN statistics (NFiSAM.py:381-384)

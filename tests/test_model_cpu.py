@@ -66,3 +66,26 @@ def check_wrapper(g, rtol):
 def test_wrapper_host_logic_with_oracle_backend(g):
     with oracle_backend():
         check_wrapper(g, rtol=1e-4)
+
+
+def test_host_shortcuts_are_bit_identical_to_the_reference_calls():
+    """np.random.permutation indexing == in-place np.random.shuffle (same rows, same RNG state afterwards); the
+    restated circular mean == scipy.stats.circmean."""
+    from scipy.stats import circmean as scipy_circmean
+
+    from nfisam_b200.slam.nfisam import circmean
+
+    np.random.seed(7)
+    a = np.random.standard_normal((500, 7))
+    b = a.copy()
+    np.random.seed(11)
+    np.random.shuffle(a)
+    after_a = np.random.random()
+    np.random.seed(11)
+    b = b[np.random.permutation(b.shape[0])]
+    after_b = np.random.random()
+    assert np.array_equal(a, b) and after_a == after_b
+    rng = np.random.default_rng(0)
+    for _ in range(30):
+        x = rng.standard_normal((int(rng.integers(5, 2000)), int(rng.integers(1, 5)))) * rng.uniform(0.1, 3) + rng.uniform(-4, 4)
+        assert np.array_equal(circmean(x, high=np.pi, low=-np.pi, axis=0), scipy_circmean(x, high=np.pi, low=-np.pi, axis=0))
