@@ -109,8 +109,56 @@ __device__ __forceinline__ float nf_rqs_grad(float2 (&o2)[NP], float B, float xi
     return f;
 }
 
-template <int K, int H, int W>
-__global__ void __launch_bounds__(W * 32)
+// Outer products of one 32-sample tile, accumulated into lane-owned registers.  The tile's per-sample vectors
+// (gout | h2 | g2 | h1 | g1) sit in the warp's staging rows; lane ownership:
+//   W3t[k][p] / b3[p]   lane = p (+32 c);      W2t[k][j] / b2[j]   j = lane % H, k = lane / H + LG m;
+//   W1t[k][j] / b1[j]   j = lane % H, k = lane / H + LG m for m < MC = ceil(i / LG)   (MC is a template parameter:
+//   the conditioner of dim i has only i input rows, so early dims skip most of the M1 chunks).
+template <int H, int PP, int NC3, int N2, int LG, int M1, int MC>
+__device__ __forceinline__ void nf_reduce_tile(const float* __restrict__ stage, const float* __restrict__ slot, int stg,
+                                               int dp, int i, int lane, float2 (&acc3)[NC3][H / 2], float (&accb3)[NC3],
+                                               float (&acc2)[N2], float& accb2, float (&acc1)[M1], float& accb1) {
+    const int jl = lane % H, kg = lane / H;
+#pragma unroll 4
+    for (int ss = 0; ss < 32; ++ss) {
+        const float* rw_ = stage + ss * stg;
+        float2 hv[H / 2];
+#pragma unroll
+        for (int k = 0; k < H; k += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(rw_ + PP + k);
+            hv[k / 2] = make_float2(v.x, v.y);
+            hv[k / 2 + 1] = make_float2(v.z, v.w);
+        }
+#pragma unroll
+        for (int c = 0; c < NC3; ++c) {
+            const int p = lane + 32 * c;
+            if (p < PP) {
+                const float g = rw_[p];
+                accb3[c] += g;
+                const float2 gg = make_float2(g, g);
+#pragma unroll
+                for (int k = 0; k < H / 2; ++k) acc3[c][k] = nf_fma2(gg, hv[k], acc3[c][k]);
+            }
+        }
+        const float g2j = rw_[PP + H + jl];
+        accb2 += g2j;
+#pragma unroll
+        for (int m = 0; m < N2; ++m) acc2[m] = fmaf(g2j, rw_[PP + 2 * H + kg + LG * m], acc2[m]);
+        const float g1j = rw_[PP + 3 * H + jl];
+        accb1 += g1j;
+        const float* xr = slot + ss * dp;
+#pragma unroll
+        for (int m = 0; m < MC; ++m) {
+            const int k = kg + LG * m;
+            if (m < MC - 1 || k < i) acc1[m] = fmaf(g1j, xr[k], acc1[m]);
+        }
+    }
+}
+
+// MINB = 1: latency-optimised build (full register budget, one block per SM, cluster mode);
+// MINB = 2: throughput build for the large-batch mode (<= 128 registers, two blocks per SM).
+template <int K, int H, int W, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB)
 nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_begin, int it_end, int launch_idx,
                 int plain, int val_pass) {
     constexpr int P = 3 * K - 1;
@@ -330,7 +378,6 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
             }
             __syncwarp();
             // ------------- outer products over the tile, lane-owned accumulators -------------
-            const int jl = lane % H, kg = lane / H;
             if (i == 0) {
                 for (int ss = 0; ss < 32; ++ss) {
                     const float* rw_ = stage + ss * STG;
@@ -341,39 +388,18 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                     }
                 }
             } else {
-                for (int ss = 0; ss < 32; ++ss) {
-                    const float* rw_ = stage + ss * STG;
-                    float2 hv[H / 2];
-#pragma unroll
-                    for (int k = 0; k < H; k += 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(rw_ + PP + k);
-                        hv[k / 2] = make_float2(v.x, v.y);
-                        hv[k / 2 + 1] = make_float2(v.z, v.w);
-                    }
-#pragma unroll
-                    for (int c = 0; c < NC3; ++c) {
-                        const int p = lane + 32 * c;
-                        if (p < PP) {
-                            const float g = rw_[p];
-                            accb3[c] += g;
-                            const float2 gg = make_float2(g, g);
-#pragma unroll
-                            for (int k = 0; k < H / 2; ++k) acc3[c][k] = nf_fma2(gg, hv[k], acc3[c][k]);
-                        }
-                    }
-                    const float g2j = rw_[PP + H + jl];
-                    accb2 += g2j;
-#pragma unroll
-                    for (int m = 0; m < N2; ++m) acc2[m] = fmaf(g2j, rw_[PP + 2 * H + kg + LG * m], acc2[m]);
-                    const float g1j = rw_[PP + 3 * H + jl];
-                    accb1 += g1j;
-                    const float* xr = slot + ss * dp;
-#pragma unroll
-                    for (int m = 0; m < M1; ++m) {
-                        const int k = kg + LG * m;
-                        if (k < i) acc1[m] = fmaf(g1j, xr[k], acc1[m]);
-                    }
+                const int mcnt = (i + LG - 1) / LG;       // W1 chunks this dim needs (uniform over the block)
+#define NF_RED(MCV) nf_reduce_tile<H, PP, NC3, N2, LG, M1, MCV>(stage, slot, STG, dp, i, lane, acc3, accb3, acc2, accb2, acc1, accb1)
+                switch (mcnt) {
+                    case 1: NF_RED(1); break;
+                    case 2: NF_RED(2); break;
+                    case 3: NF_RED(3); break;
+                    case 4: NF_RED(4); break;
+                    case 5: NF_RED(5); break;
+                    case 6: NF_RED(6); break;
+                    default: NF_RED(M1); break;
                 }
+#undef NF_RED
             }
             __syncwarp();
         }
@@ -530,7 +556,8 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
     // cluster size: enough blocks per dim that a warp owns about one tile, max 8 (portable limit)
     int C = 1;
     while (C < 8 && (int64_t)C * W < ntiles) C *= 2;
-    auto kern = nf_train_kernel<K, H, W>;
+    auto kern = nf_train_kernel<K, H, W, 1>;
+    auto kern_big = nf_train_kernel<K, H, W, 2>;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const int window = a.grad_only ? 1 : (a.average_window > 0 ? a.average_window : 64);
@@ -538,9 +565,9 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         // ---- large-batch mode: two launches per iteration, about two blocks per SM over all dims
         const size_t smem = train_smem_bytes<K, H, W>(d - 1, 1, 1);
         if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
-        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NF_CUDA(cudaFuncSetAttribute(kern_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_big, W * 32, smem);
         if (per_sm < 1) per_sm = 1;
         int blocks = (nf_sm_count(device) * per_sm + d - 1) / d;
         const int64_t want = (ntiles + W - 1) / W;
@@ -562,7 +589,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         const int adam_blocks = (a.n_packed + 255) / 256;
         for (int it = 0; it < a.max_iters; ++it) {
             const int launch_idx = it / window;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, 1, 0, it, it + 1, launch_idx, 1, 0);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern_big, a, d, fd.B, 1, 0, it, it + 1, launch_idx, 1, 0);
             if (e != cudaSuccess) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, plain)");
             nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
             nf_count_launch(2);
@@ -644,6 +671,14 @@ int launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStr
 
 }  // namespace
 
+// The instantiations are split over two translation units (-DNF_TRAIN_PART=0 / 1: hidden 8 / hidden 16) so that
+// the build parallelises; part 0 owns the public entry point and forwards what it does not hold.
+#ifndef NF_TRAIN_PART
+#define NF_TRAIN_PART 0
+#endif
+int nf_launch_train_part1(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st);
+
+#if NF_TRAIN_PART == 0
 size_t nf_train_loss_part_elems(const NfFlowDims& fd, int max_iters) { return (size_t)max_iters * fd.d; }
 
 int nf_launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st) {
@@ -651,8 +686,17 @@ int nf_launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cuda
     if (a.n_val > 0 && (a.val == nullptr || a.val_part == nullptr))
         return nf_set_error(NF_ERR_BAD_ARG, "validation set given without device buffers");
 #define NF_CASE(KK, HH) \
-    if (fd.K == KK && fd.H == HH) return launch_train<KK, HH>(fd, a, device, st);
+    if (HH == 8 && fd.K == KK && fd.H == HH) return launch_train<KK, (HH == 8 ? HH : 8)>(fd, a, device, st);
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    return nf_launch_train_part1(fd, a, device, st);
+}
+#else
+int nf_launch_train_part1(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st) {
+#define NF_CASE(KK, HH) \
+    if (HH != 8 && fd.K == KK && fd.H == HH) return launch_train<KK, (HH != 8 ? HH : 16)>(fd, a, device, st);
     NF_FOREACH_KH(NF_CASE)
 #undef NF_CASE
     return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
 }
+#endif
