@@ -38,6 +38,14 @@ def flops_fwd(d, H, K):
     return 2 * macs + (d - 1) * (2 * H + 3 * K - 1) + d * (15 * K + 45)
 
 
+def flops_fwd_executed(d, H, K):
+    """FLOPs the kernel actually issues: only the two derivative columns of the bin that holds the input are
+    evaluated (nf_common.cuh, lazy derivative rows), the 2K width / height columns are padded to a multiple of 4."""
+    ppw = (2 * K + 3) // 4 * 4
+    macs = H * d * (d - 1) // 2 + (d - 1) * (H * H + H * (ppw + 2))
+    return 2 * macs + (d - 1) * (2 * H + ppw + 2) + d * (13 * K + 55)
+
+
 def sfu_fwd(d, H, K):
     return 2 * H * (d - 1) + d * (4 * K + 4)
 
@@ -329,7 +337,8 @@ def run_gpu(args):
                            "MEASURED_PEAKS.json holds no FP32 figure. The kernel is FMA/MUFU-bound (95 flop/B), not HBM- or "
                            "tensor-bound (SURVEY.md 8d)",
             "fp32_probe_tflops": {"ffma_reg": peaks[0], "ffma2": peaks[1], "ffma_const": peaks[2]},
-            "flops_per_sample": fl, "sfu_ops_per_sample": sfu_fwd(D, HID, K_BINS),
+            "flops_per_sample": fl, "executed_flops_per_sample": flops_fwd_executed(D, HID, K_BINS),
+            "sfu_ops_per_sample": sfu_fwd(D, HID, K_BINS),
             "mufu": {"achieved_gops": sfu_fwd(D, HID, K_BINS) * n / (per_launch_ms * 1e-3) * 1e-9, "peak_gops": mufu_peak.value},
             "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                     "algorithmic_bytes_per_sample": 4 * D + 4, "peak_source": hbm_src},

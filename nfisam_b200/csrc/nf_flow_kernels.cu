@@ -49,10 +49,8 @@ nf_forward_kernel(const float* __restrict__ pk, int wcount, int d_in, float B, c
             const int64_t s = s0 + threadIdx.x;
             float ld_acc = 0.0f, sq_acc = 0.0f;
             for (int i = 0; i < d_in; ++i) {
-                float2 out2[PP / 2];
-                nf_conditioner<K, H>(sw, i, xrow, out2);
                 float ld;
-                const float zz = nf_rqs_forward<K>(out2, B, xrow[i], ld);
+                const float zz = nf_forward_dim<K, H>(sw, i, xrow, B, xrow[i], ld);
                 ld_acc += ld;
                 sq_acc = fmaf(zz, zz, sq_acc);
                 if (ref_layout) {
@@ -137,10 +135,8 @@ nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, floa
             float ld_acc = 0.0f;
             bool bad = false;
             for (int i = sep; i < d; ++i) {
-                float2 out2[PP / 2];
-                nf_conditioner<K, H>(sw, i, xrow, out2);
                 float ld;
-                const float xi = nf_rqs_inverse<K>(out2, B, zrow[i - sep], ld, bad);
+                const float xi = nf_inverse_dim<K, H>(sw, i, xrow, B, zrow[i - sep], ld, bad);
                 ld_acc += ld;
                 xrow[i] = xi;
             }
