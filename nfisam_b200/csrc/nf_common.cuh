@@ -21,15 +21,14 @@
 // contiguous, so a warp whose lanes all evaluate the same conditioner reads them as float4
 // shared-memory broadcasts.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ int nf_pp(int K) { return ((3 * K - 1) + 3) & ~3; }
+__host__ __device__ constexpr __forceinline__ int nf_pp(int K) { return ((3 * K - 1) + 3) & ~3; }
 __host__ __device__ __forceinline__ int nf_block_size(int i, int H, int Pp) {
     return i == 0 ? Pp : i * H + H + H * H + H + H * Pp + Pp;
 }
-__host__ __device__ __forceinline__ int nf_block_off(int i, int H, int Pp) {
-    if (i == 0) return 0;
-    return Pp + H * ((i - 1) * i / 2) + (i - 1) * (2 * H + H * H + H * Pp + Pp);
+__host__ __device__ constexpr __forceinline__ int nf_block_off(int i, int H, int Pp) {
+    return i == 0 ? 0 : Pp + H * ((i - 1) * i / 2) + (i - 1) * (2 * H + H * H + H * Pp + Pp);
 }
-__host__ __device__ __forceinline__ int nf_packed_size(int d, int H, int Pp) { return nf_block_off(d, H, Pp); }
+__host__ __device__ constexpr __forceinline__ int nf_packed_size(int d, int H, int Pp) { return nf_block_off(d, H, Pp); }
 
 // ---------------------------------------------------------------------------------------------
 // Scalar math.  The flow kernels are bound by instruction issue (ncu: 83 % issue-active with libm
@@ -467,15 +466,10 @@ __device__ __forceinline__ void nf_bin_derivs(const float* __restrict__ b3, cons
     dk1 = bin == K - 1 ? NF_EDGE_DERIV : NF_MIN_DERIV + nf_softplus(u1);
 }
 
-// z_i and log|dz_i/dx_i| of dim i for one sample (src/flows/flows.py:77-89 + src/flows/utils.py:148-164)
-template <int K, int H>
-__device__ __forceinline__ float nf_forward_dim(const float* __restrict__ wbase, int i, const float* __restrict__ xrow, float B,
-                                                float xin, float& ld) {
-    float2 out2w[NfLazy<K>::PPW / 2];
-    float h2[H];
-    const float* b3;
-    const float* W3t;
-    nf_outputs_wh<K, H>(wbase, i, xrow, out2w, h2, b3, W3t);
+// Forward spline of one value given the width / height outputs; derivs(bin, dk, dk1) supplies the two knot derivatives.
+// src/flows/utils.py:148-164.  Branch-free: values outside [-B, B] (identity, log-det 0) run on a dummy in-range value.
+template <int K, int NP, typename DerivFn>
+__device__ __forceinline__ float nf_forward_tail(const float2 (&out2w)[NP], float B, float xin, float& ld, DerivFn derivs) {
     const bool inside = (xin >= -B && xin <= B);
     const float x = inside ? xin : 0.0f;
     float2 c[K + 1], dummy[K];
@@ -483,7 +477,7 @@ __device__ __forceinline__ float nf_forward_dim(const float* __restrict__ wbase,
     float2 lo, hi;
     const int bin = nf_locate_bin<K, false>(c, x, lo, hi);
     float dk, dk1;
-    nf_bin_derivs<K, H>(b3, W3t, h2, bin, dk, dk1);
+    derivs(bin, dk, dk1);
     const float xk = lo.x, yk = lo.y;
     const float wk = hi.x - xk, hk = hi.y - yk;
     const float rw = nf_rcp(wk);
@@ -501,6 +495,19 @@ __device__ __forceinline__ float nf_forward_dim(const float* __restrict__ wbase,
 #endif
     ld = inside ? l : 0.0f;
     return inside ? yk + nf_div(num, den) : xin;
+}
+
+// z_i and log|dz_i/dx_i| of dim i for one sample (src/flows/flows.py:77-89)
+template <int K, int H>
+__device__ __forceinline__ float nf_forward_dim(const float* __restrict__ wbase, int i, const float* __restrict__ xrow, float B,
+                                                float xin, float& ld) {
+    float2 out2w[NfLazy<K>::PPW / 2];
+    float h2[H];
+    const float* b3;
+    const float* W3t;
+    nf_outputs_wh<K, H>(wbase, i, xrow, out2w, h2, b3, W3t);
+    return nf_forward_tail<K>(out2w, B, xin, ld,
+                              [&](int bin, float& dk, float& dk1) { nf_bin_derivs<K, H>(b3, W3t, h2, bin, dk, dk1); });
 }
 
 // x_i and the inverse's log-det of dim i for one sample (src/flows/flows.py:104-112 + src/flows/utils.py:123-147)
