@@ -198,7 +198,7 @@ def cpu_baseline_block(theta, target_s=12.0):
     from oracle import nsf_oracle as orc  # noqa: F401  (build if needed)
 
     rate, _ = cpu_log_prob_rate(theta, 100_000)
-    n = int(min(max(rate * target_s, 100_000), 20_000_000))
+    n = int(min(max(rate * target_s, 100_000), N_PER_GPU))
     rate, dt = cpu_log_prob_rate(theta, n)
     return {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"oracle/nsf_oracle.c log_prob (OpenMP, {os.cpu_count()} threads) on {n} of the "

@@ -58,7 +58,7 @@ int64_t nfisam_launch_count(void);
  * operands, [1] packed FFMA2 (fma.rn.f32x2), [2] FFMA with constant-bank operands, all in TFLOP/s
  * (2 flops per FMA); [3] MUFU ex2 in Gop/s.  Synchronous, ~30 ms. */
 int nfisam_probe_pipe_peaks(int device, double* peaks4);
-/* sizeof of an ABI struct, for binding validation: 0 nf_train_cfg, 1 nf_factor_desc, 2 nf_affine. */
+/* sizeof of an ABI struct, for binding validation: 0 nf_train_cfg, 1 nf_factor_desc, 2 nf_affine, 3 nf_sim_op. */
 int nfisam_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -218,6 +218,66 @@ int nfisam_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const dou
  * normalised.  weights_out_host: n_desc doubles.  Synchronous. */
 int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_desc, const double* x_dev, int64_t n,
                                      int D, double* weights_out_host, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Clique training-set simulator ("next" row N1)  -- replaces SimulationBasedSampler.sample
+ * (src/sampler/SimulationBasedSampler.py:14-134) and the factor .sample methods it calls
+ * (src/factors/Factors.py:725-743 SE2 prior, 1196-1317 SE2 relative pose, 2575-2621 range,
+ * 3146-3157 / 3260-3276 / 3339-3374 mixtures) with one kernel: a thread owns a row (one joint sample of the
+ * clique variables and simulated observations) and runs the op list in order, each op reading
+ * columns written by earlier ops.
+ *
+ * Random numbers are counter-based: Philox4x32-10 keyed by `seed`, counter (row, slot, 0, 0); one call yields
+ * either two standard normals (Box-Muller in float64) or two uniforms on [0, 1).  The result is a pure
+ * function of (seed, op list): independent of grid shape, stream and GPU count, and reproducible by the CPU
+ * oracle (oracle/sim_oracle.py) to float64 rounding.
+ * ---------------------------------------------------------------------------------------- */
+typedef enum nf_sim_type {
+    NF_SIM_SE2_PRIOR = 0,   /* out(3) = obs * Exp(L eps)                                 Factors.py:725-731   */
+    NF_SIM_GAUSS_PRIOR = 1, /* out(n_out) = obs + L eps, n_out <= 3                      Factors.py:(R2 prior) */
+    NF_SIM_SE2_GEN_FWD = 2, /* out(3) = a * (obs * Exp(L eps))       (var1 given)        Factors.py:1252-1263 */
+    NF_SIM_SE2_GEN_BWD = 3, /* out(3) = a / (obs * Exp(L eps))       (var2 given)        Factors.py:1216-1229 */
+    NF_SIM_SE2_OBS = 4,     /* out(3) = (a^-1 * b) * Exp(L eps)      (both given)        Factors.py:1286-1300 */
+    NF_SIM_RANGE_GEN = 5,   /* out(2) = a[:2] + (obs0 + sigma eps) (cos u, sin u), u ~ U(-pi, pi)   Factors.py:2575-2603 */
+    NF_SIM_RANGE_OBS = 6,   /* out(1) = |b[:2] - a[:2]| + sigma eps                      Factors.py:2605-2621 */
+    NF_SIM_COPY_F32 = 7     /* out(n_out) = src[row, 0..n_out) (float32 samples of a flow-backed separator factor,
+                               src/slam/NFiSAM.py:283-291, produced by nfisam_flow_inverse_gather) */
+} nf_sim_type;
+
+typedef struct nf_sim_op {
+    int32_t type;            /* nf_sim_type */
+    int32_t row_lo, row_hi;  /* the op applies to rows [row_lo, row_hi): mixture components own contiguous row
+                                ranges whose sizes are the host's multinomial draw (Factors.py:3148, 3262) */
+    int32_t in_a, in_b;      /* first column of the given variable(s); -1 = unused */
+    int32_t out;             /* first output column */
+    int32_t n_out;           /* GAUSS_PRIOR / COPY_F32: number of output columns */
+    int32_t slot;            /* first noise slot of this op (SE2 ops use 2 slots, range ops 1 or 2, priors 2) */
+    double obs[3];           /* prior pose / relative pose / mean; RANGE: obs[0] = range */
+    double chol[6];          /* lower Cholesky factor of the noise covariance, packed (l00, l10, l11, l20, l21, l22);
+                                RANGE: chol[0] = sigma */
+    const float* src_dev;    /* COPY_F32: source matrix */
+    int64_t src_ld;          /* COPY_F32: its row stride in floats */
+} nf_sim_op;
+
+/* Runs the ops in order on every row.  s_dev: (n, ld) float64 row-major.  Up to 256 ops per launch travel in the
+ * kernel-parameter constant bank; longer lists are split into consecutive launches.  Asynchronous on `stream`. */
+int nfisam_simulate(const nf_sim_op* ops_host, int n_ops, uint64_t seed, double* s_dev, int64_t n, int ld,
+                    int device, void* stream);
+
+/* The two standard normals (normal != 0) or uniforms of (seed, row, slot) for rows [0, n): out_dev (n, 2) float64.
+ * Exposes the generator for parity tests. */
+int nfisam_sim_noise(uint64_t seed, int slot, int normal, double* out_dev, int64_t n, int device, void* stream);
+
+/* NFiSAM.normalize_training_samples (src/slam/NFiSAM.py:515-548) on the device.  Column j of the (n_rows, d)
+ * float32 training matrix is column cols_host[j] of s_dev, rows taken through perm_dev (int32 row indices; NULL =
+ * rows row0 .. row0 + n_rows - 1):
+ *   circular columns: mean = circular mean, x <- wrap(x - mean), std = population std of the wrapped values;
+ *   other columns:    mean / population std;     std clipped at 1e-5;   data = x / std.
+ * mean_std_dev receives mean[d] | std[d] as float32 (the layout nf_affine takes).  Sums run in float64 in a fixed
+ * order (bitwise reproducible).  Asynchronous on `stream`. */
+int nfisam_normalize_training(const double* s_dev, int64_t n_rows, int ld, const int32_t* perm_dev, int64_t row0,
+                              const int32_t* cols_host, const uint8_t* circular_host, int d, float* data_dev,
+                              float* mean_std_dev, int device, void* stream);
 
 #ifdef __cplusplus
 }

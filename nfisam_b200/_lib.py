@@ -60,6 +60,27 @@ class nf_factor_desc(ctypes.Structure):
     ]
 
 
+NF_SIM_SE2_PRIOR, NF_SIM_GAUSS_PRIOR, NF_SIM_SE2_GEN_FWD, NF_SIM_SE2_GEN_BWD, NF_SIM_SE2_OBS, NF_SIM_RANGE_GEN, \
+    NF_SIM_RANGE_OBS, NF_SIM_COPY_F32 = range(8)
+
+
+class nf_sim_op(ctypes.Structure):
+    _fields_ = [
+        ("type", ctypes.c_int32),
+        ("row_lo", ctypes.c_int32),
+        ("row_hi", ctypes.c_int32),
+        ("in_a", ctypes.c_int32),
+        ("in_b", ctypes.c_int32),
+        ("out", ctypes.c_int32),
+        ("n_out", ctypes.c_int32),
+        ("slot", ctypes.c_int32),
+        ("obs", ctypes.c_double * 3),
+        ("chol", ctypes.c_double * 6),
+        ("src_dev", ctypes.c_void_p),
+        ("src_ld", ctypes.c_int64),
+    ]
+
+
 # every symbol include/nfisam_b200.h declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -91,6 +112,9 @@ SYMBOLS = {
     "nfisam_flow_loss_grad": (_INT, [_P, _P, _I64, _P, _P, _P]),
     "nfisam_factor_logpdf": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _P, _INT, _P]),
     "nfisam_mixture_posterior_weights": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _INT, _P]),
+    "nfisam_simulate": (_INT, [ctypes.POINTER(nf_sim_op), _INT, ctypes.c_uint64, _P, _I64, _INT, _INT, _P]),
+    "nfisam_sim_noise": (_INT, [ctypes.c_uint64, _INT, _INT, _P, _I64, _INT, _P]),
+    "nfisam_normalize_training": (_INT, [_P, _I64, _INT, _P, _I64, _P, _P, _INT, _P, _P, _INT, _P]),
 }
 
 _lib = None
@@ -122,7 +146,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
-        for which, st in enumerate((nf_train_cfg, nf_factor_desc, nf_affine)):
+        for which, st in enumerate((nf_train_cfg, nf_factor_desc, nf_affine, nf_sim_op)):
             if lib.nfisam_struct_size(which) != ctypes.sizeof(st):
                 raise NfisamError(NF_ERR_BAD_ARG, f"ABI mismatch: sizeof({st.__name__}) differs between header and binding")
         _lib = lib

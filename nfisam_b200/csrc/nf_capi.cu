@@ -143,6 +143,7 @@ int nfisam_struct_size(int which) {
         case 0: return (int)sizeof(nf_train_cfg);
         case 1: return (int)sizeof(nf_factor_desc);
         case 2: return (int)sizeof(nf_affine);
+        case 3: return (int)sizeof(nf_sim_op);
         default: return -1;
     }
 }
@@ -640,6 +641,59 @@ int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_des
     }
     for (int c = 0; c < n_desc; ++c) weights_out_host[c] /= total;
     return NF_OK;
+}
+
+// ---- training-set simulator (nf_sim_kernels.cu) ----------------------------------------------------------------------
+int nfisam_simulate(const nf_sim_op* ops_host, int n_ops, uint64_t seed, double* s_dev, int64_t n, int ld, int device,
+                    void* stream) {
+    if (!ops_host || n_ops < 0 || (!s_dev && n > 0) || n < 0 || ld < 1) return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    for (int k = 0; k < n_ops; ++k) {
+        const nf_sim_op& op = ops_host[k];
+        int width = 3, need_a = 0, need_b = 0;
+        switch (op.type) {
+            case NF_SIM_SE2_PRIOR: break;
+            case NF_SIM_GAUSS_PRIOR: width = op.n_out; break;
+            case NF_SIM_SE2_GEN_FWD:
+            case NF_SIM_SE2_GEN_BWD: need_a = 3; break;
+            case NF_SIM_SE2_OBS: need_a = 3; need_b = 3; break;
+            case NF_SIM_RANGE_GEN: width = 2; need_a = 2; break;
+            case NF_SIM_RANGE_OBS: width = 1; need_a = 2; need_b = 2; break;
+            case NF_SIM_COPY_F32:
+                width = op.n_out;
+                if (!op.src_dev || op.src_ld < op.n_out) return nf_set_error(NF_ERR_BAD_ARG, "op %d: bad source matrix", k);
+                break;
+            default: return nf_set_error(NF_ERR_BAD_ARG, "op %d: unknown type %d", k, op.type);
+        }
+        if (width < 1 || ((op.type == NF_SIM_GAUSS_PRIOR) && width > 3) || op.out < 0 || op.out + width > ld)
+            return nf_set_error(NF_ERR_BAD_ARG, "op %d: output columns outside the sample matrix", k);
+        if ((need_a && (op.in_a < 0 || op.in_a + need_a > ld)) || (need_b && (op.in_b < 0 || op.in_b + need_b > ld)))
+            return nf_set_error(NF_ERR_BAD_ARG, "op %d: input columns outside the sample matrix", k);
+        if (op.row_lo < 0 || op.row_hi < op.row_lo || op.row_hi > n) return nf_set_error(NF_ERR_BAD_ARG, "op %d: bad row range", k);
+        if (op.slot < 0) return nf_set_error(NF_ERR_BAD_ARG, "op %d: negative noise slot", k);
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    return nf_launch_simulate(ops_host, n_ops, seed, s_dev, n, ld, (cudaStream_t)stream);
+}
+
+int nfisam_sim_noise(uint64_t seed, int slot, int normal, double* out_dev, int64_t n, int device, void* stream) {
+    if ((!out_dev && n > 0) || n < 0 || slot < 0) return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    return nf_launch_sim_noise(seed, slot, normal, out_dev, n, (cudaStream_t)stream);
+}
+
+int nfisam_normalize_training(const double* s_dev, int64_t n_rows, int ld, const int32_t* perm_dev, int64_t row0,
+                              const int32_t* cols_host, const uint8_t* circular_host, int d, float* data_dev,
+                              float* mean_std_dev, int device, void* stream) {
+    if (!s_dev || !cols_host || !data_dev || !mean_std_dev || n_rows < 1 || ld < 1 || d < 1 || row0 < 0)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    for (int j = 0; j < d; ++j)
+        if (cols_host[j] < 0 || cols_host[j] >= ld) return nf_set_error(NF_ERR_BAD_ARG, "column %d outside the sample matrix", j);
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    return nf_launch_normalize(s_dev, n_rows, ld, perm_dev, row0, cols_host, circular_host, d, data_dev, mean_std_dev,
+                               (cudaStream_t)stream);
 }
 
 }  // extern "C"

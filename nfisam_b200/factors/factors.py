@@ -17,6 +17,7 @@ from typing import Dict, Iterable, List
 import numpy as np
 
 from ..slam.variables import R1Variable, SE2Variable, Variable, VariableType
+from .. import _lib
 from . import _gpu
 from .geometry import SE2Pose, se2_compose, se2_exp, se2_inverse
 
@@ -133,6 +134,10 @@ class UnarySE2ApproximateGaussianPriorFactor(PriorFactor):
         noise = np.random.standard_normal((num_samples, 3)) @ self._chol.T
         return se2_compose(self._prior_pose.array, se2_exp(noise))
 
+    def sim_prior(self, prog):
+        """Device form of `sample` (one op of the simulator kernel, slam/simulation_sampler.py)."""
+        prog.add(_lib.NF_SIM_SE2_PRIOR, out=prog.col(self._var), obs=self._prior_pose.array, chol=self._chol, slots=2)
+
     @classmethod
     def construct_from_text(cls, line, variables):
         tok = line.strip().split()
@@ -174,6 +179,11 @@ class UnaryR2GaussianPriorFactor(PriorFactor):
 
     def sample(self, num_samples: int, **kwargs):
         return self._mu + np.random.standard_normal((num_samples, self._var.dim)) @ self._chol.T
+
+    def sim_prior(self, prog):
+        if self._var.dim > 3:
+            raise NotImplementedError("device simulation of Gaussian priors is limited to dim <= 3")
+        prog.add(_lib.NF_SIM_GAUSS_PRIOR, out=prog.col(self._var), n_out=self._var.dim, obs=self._mu, chol=self._chol, slots=2)
 
     @classmethod
     def construct_from_text(cls, line, variables):
@@ -237,6 +247,15 @@ class SE2RelativeGaussianLikelihoodFactor(LikelihoodFactor, BinaryFactor):
             return se2_compose(var1, z)
         return se2_compose(se2_compose(se2_inverse(var1), var2), self._noisy(var1.shape[0]))
 
+    def sim_gen(self, prog, given, new, rows=None, slot=None):
+        kind = _lib.NF_SIM_SE2_GEN_FWD if given == self._vars[0] else _lib.NF_SIM_SE2_GEN_BWD
+        prog.add(kind, in_a=prog.col(given), out=prog.col(new), obs=self._observation.array, chol=self._chol, slots=2,
+                 rows=rows, slot=slot)
+
+    def sim_obs(self, prog, out_col, rows=None, slot=None):
+        prog.add(_lib.NF_SIM_SE2_OBS, in_a=prog.col(self._vars[0]), in_b=prog.col(self._vars[1]), out=out_col,
+                 chol=self._chol, slots=2, rows=rows, slot=slot)
+
     @classmethod
     def construct_from_text(cls, line, variables):
         tok = line.strip().split()
@@ -293,6 +312,17 @@ class SE2R2RangeGaussianLikelihoodFactor(LikelihoodFactor, BinaryFactor):
         r = np.sqrt(np.sum((var2[:, :2] - var1[:, :2]) ** 2, axis=1, keepdims=True))
         return r + self._sigma * np.random.standard_normal((var1.shape[0], 1))
 
+    def sim_gen(self, prog, given, new, rows=None, slot=None):
+        """Ring around the given end; like `_ring` only the translation of `new` is produced (2 columns)."""
+        if new.dim != 2:
+            raise NotImplementedError("range factors only generate R2 variables")
+        prog.add(_lib.NF_SIM_RANGE_GEN, in_a=prog.col(given), out=prog.col(new), n_out=2, obs=[self._observation[0]],
+                 chol=[[self._sigma]], slots=2, rows=rows, slot=slot)
+
+    def sim_obs(self, prog, out_col, rows=None, slot=None):
+        prog.add(_lib.NF_SIM_RANGE_OBS, in_a=prog.col(self._vars[0]), in_b=prog.col(self._vars[1]), out=out_col, n_out=1,
+                 chol=[[self._sigma]], slots=1, rows=rows, slot=slot)
+
     @classmethod
     def construct_from_text(cls, line, variables):
         tok = line.strip().split()
@@ -348,6 +378,14 @@ class BinaryFactorMixture(LikelihoodFactor):
                 arr[lo:hi] = comp.sample(var1=var_samples[comp.var1][lo:hi], var2=var_samples[comp.var2][lo:hi])
         return arr
 
+    def sim_observations(self, prog, out_col):
+        """Device form of sample_observations: component c simulates rows [lo_c, hi_c) of the host's multinomial split.
+        Components own disjoint rows, so they share one block of noise slots."""
+        slot = prog.reserve(2)
+        for rows, comp in zip(self._split(prog.n), self.components_):
+            if rows[1] > rows[0]:
+                comp.sim_obs(prog, out_col, rows=rows, slot=slot)
+
     def posterior_weights(self, var2x: Dict[Variable, np.ndarray]):
         x = np.concatenate([var2x[v] for v in self.vars], axis=1)
         return _gpu.mixture_posterior_weights(self.components(_local_cols(self.vars)), x)
@@ -375,6 +413,13 @@ class AmbiguousDataAssociationFactor(BinaryFactorMixture, KWayFactor):
                 else:
                     arr[lo:hi] = comp.sample(var1=var2sample[comp.var1][lo:hi])
         return arr
+
+    def sim_observer(self, prog):
+        slot = prog.reserve(2)
+        for rows, comp in zip(self._split(prog.n), self.components_):
+            if rows[1] > rows[0]:
+                given = comp.var2 if comp.var1 == self.observer_var else comp.var1
+                comp.sim_gen(prog, given, self.observer_var, rows=rows, slot=slot)
 
     @classmethod
     def construct_from_text(cls, line, variables):
@@ -418,6 +463,15 @@ class BinaryFactorWithNullHypo(BinaryFactorMixture, BinaryFactor):
             if hi > lo:
                 arr[lo:hi] = comp.sample(var1=None if var1 is None else var1[lo:hi], var2=None if var2 is None else var2[lo:hi])
         return arr
+
+    def sim_gen(self, prog, given, new, rows=None, slot=None):
+        slot = prog.reserve(2)
+        for r, comp in zip(self._split(prog.n), self.components_):
+            if r[1] > r[0]:
+                comp.sim_gen(prog, given, new, rows=r, slot=slot)
+
+    def sim_obs(self, prog, out_col, rows=None, slot=None):
+        self.sim_observations(prog, out_col)
 
     @classmethod
     def construct_from_text(cls, line, variables):

@@ -12,6 +12,7 @@ New relative to the reference: `fit_tree_density_models` / `sample_posterior` ru
 schedule of scheduler.py (cliques of one Bayes-tree level train concurrently on CUDA streams and, under
 torch.distributed, on different GPUs; NCCL only moves trained parameters up and separator samples down).
 """
+import ctypes
 import math
 import os
 import time
@@ -21,6 +22,7 @@ import numpy as np
 import torch
 from scipy.stats import norm
 
+from .. import _lib
 from ..flows import NSF_AR, CustomMultivariateNormal, NormalizingFlowModel
 from ..factors.factors import Factor
 from .bayes_tree import BayesTreeNode
@@ -51,7 +53,7 @@ class NFiSAMArgs(SolverArgs):
                  average_window=50, loss_delta_tol=1e-2, training_set_frac=1.0, validation_interval=10,
                  slower_stop_rate=2.0, data_parallel=False, training_loss_dir=None,
                  clique_parallel: bool = True, deterministic_cliques: bool = False, seed: int = 0, device=None,
-                 *args, **kwargs):
+                 device_simulation: bool = True, *args, **kwargs):
         super().__init__(elimination_method=elimination_method, posterior_sample_num=posterior_sample_num,
                          local_sample_num=local_sample_num, store_clique_samples=store_clique_samples,
                          local_sampling_method=local_sampling_method, *args, **kwargs)
@@ -78,6 +80,7 @@ class NFiSAMArgs(SolverArgs):
         self.deterministic_cliques = deterministic_cliques  # per-clique RNG seeding: same result on 1/2/4/8 GPUs
         self.seed = seed
         self.device = device
+        self.device_simulation = device_simulation          # build clique training sets with the simulator kernel
 
 
 class NormalizingFlowModelWithSeparator(NormalizingFlowModel, ConditionalSampler):
@@ -96,6 +99,16 @@ class NormalizingFlowModelWithSeparator(NormalizingFlowModel, ConditionalSampler
 
     dim = property(lambda self: len(self.circular_dim_list))
     is_cpu = property(lambda self: self.prior.is_cpu())
+
+    def pull_normalisation(self):
+        """Device pipeline: the normalisation constants were computed by nfisam_normalize_training and are fetched
+        once the clique's stream has drained (after fit_finish)."""
+        ms = self.__dict__.pop("_mean_std_dev", None)
+        if ms is not None:
+            host = ms.cpu()
+            d = host.numel() // 2
+            self.samples_mean, self.samples_std = host[:d].clone(), host[d:].clone()
+            self._norm_cache = None
 
     def _norm(self):
         if self._norm_cache is None:
@@ -212,6 +225,22 @@ class FlowsPriorFactor(CliqueSeparatorFactor):
         obs = np.tile(self._true_obs, (num_samples, 1))
         return self._flow_model.conditional_sample_given_observation(conditional_dim=self.dim, obs_samples=obs)
 
+    def sim_prior(self, prog):
+        """Device form of `sample`: same CPU latent draw, the inverse flow writes float32 samples into a staging matrix
+        on the current stream and the simulator kernel copies them into the clique's sample matrix."""
+        fm = self._flow_model
+        flow = fm.flows[0]
+        dev = flow._dev()
+        z_dev = fm.draw_latent(prog.n, self._obs_dim, self.dim).contiguous().to(dev, non_blocking=True)
+        stage = torch.empty((prog.n, self.dim), dtype=torch.float32, device=dev)
+        flow.inverse_gather(z_dev, 0, stage, [-1] * self._obs_dim, [float(o) for o in self._true_obs], list(range(self.dim)),
+                            norm=fm._norm(), counter=prog.counter)
+        prog.keep += [z_dev, stage]
+        off = 0
+        for v in self._vars:
+            prog.add(_lib.NF_SIM_COPY_F32, out=prog.col(v), n_out=v.dim, src=stage.data_ptr() + 4 * off, src_ld=self.dim)
+            off += v.dim
+
     def unif_to_sample(self, u) -> np.ndarray:
         z = torch.as_tensor(np.array([norm.ppf(u)]).astype(np.float32))
         obs = None if self._obs_dim == 0 else np.tile(self._true_obs, (1, 1))
@@ -269,6 +298,57 @@ class NFiSAM(FactorGraphSolver):
         sep_prior = CustomMultivariateNormal(dim=aug_sep_dim) if aug_sep_dim > 0 else None
         model = NormalizingFlowModelWithSeparator([flow], prior, sep_prior, circular, means, stds)
         model._validation_data = val
+        return model, data
+
+    def _prepare_clique_model_device(self, clique: BayesTreeNode, sampler, var_ordering: List[Variable], seed: int,
+                                     counter=None):
+        """Device pipeline of one clique up to the Adam loop ("next" row N1): simulator kernel -> normalisation kernel ->
+        float32 training matrix, all enqueued on the current CUDA stream; no host copy of the samples, no
+        synchronisation.  Raises NotImplementedError if a factor of the clique has no device simulator."""
+        a = self._args
+        if a.flow_number != 1 or a.flow_type != "NSF_AR":
+            raise NotImplementedError("only flow_type='NSF_AR' with flow_number=1 exists in the reference")
+        n = a.local_sample_num
+        prog = sampler.program(n, counter)
+        flow = NSF_AR(dim=prog.ld, K=a.num_knots, hidden_dim=a.hidden_dim, device=a.device)
+        dev = flow._dev()
+        # flow-backed priors were enqueued by program(); now the simulator itself
+        s_mat = prog.run(seed, dev)
+        circular = []
+        for var in var_ordering:
+            circular += var.circular_dim_list
+        d = len(circular)
+        assert d == prog.ld
+        train_size = min(int(n * a.training_set_frac), n)
+        perm = None
+        if train_size < n:
+            # mixture components own contiguous row blocks: the reference's shuffle before the split matters
+            perm = torch.as_tensor(np.random.permutation(n).astype(np.int32)).to(dev, non_blocking=True)
+        lib = _lib.load()
+        cols = (ctypes.c_int32 * d)(*range(d))
+        circ = (ctypes.c_uint8 * d)(*[1 if c else 0 for c in circular])
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+
+        def normalised(rows, row0):
+            data = torch.empty((rows, d), dtype=torch.float32, device=dev)
+            ms = torch.empty(2 * d, dtype=torch.float32, device=dev)
+            _lib.check(lib.nfisam_normalize_training(s_mat.data_ptr(), rows, d, perm.data_ptr() if perm is not None else None,
+                                                     row0, cols, circ, d, data.data_ptr(), ms.data_ptr(), dev_index, st))
+            return data, ms
+
+        data, mean_std = normalised(train_size, 0)
+        # like the reference, the held-out rows are normalised with their OWN statistics (NFiSAM.py:381-384)
+        val = normalised(n - train_size, train_size)[0] if train_size < n else None
+        aug_sep_dim = d - clique.frontal_dim
+        prior = CustomMultivariateNormal(dim=d)
+        sep_prior = CustomMultivariateNormal(dim=aug_sep_dim) if aug_sep_dim > 0 else None
+        model = NormalizingFlowModelWithSeparator([flow], prior, sep_prior, circular, None, None)
+        model._mean_std_dev = mean_std
+        model._validation_data = val
+        model._sim_keep = (s_mat, prog.keep, perm)
+        if a.store_clique_samples:
+            self._clique_samples[clique] = s_mat.cpu().numpy()
         return model, data
 
     def _record_loss(self, clique, hist):

@@ -103,6 +103,8 @@ class CliqueScheduler:
                 plans[id(c)] = (sampler, var_order, true_obs)
             mine = [(k, c) for k, c in enumerate(todo) if k % world == rank]
             launched = []
+            on_device = bool(getattr(a, "device_simulation", False)) and torch.cuda.is_available()
+            counter = torch.zeros(1, dtype=torch.int64, device="cuda") if on_device else None
             t0 = time.time()
             for slot, (k, c) in enumerate(mine):
                 sampler, var_order, true_obs = plans[id(c)]
@@ -110,14 +112,26 @@ class CliqueScheduler:
                     seed = self._seed_for(c, 1)
                     np.random.seed(seed)
                     torch.manual_seed(seed)
-                samples, _, _ = sampler.sample(a.local_sample_num)
-                if a.store_clique_samples:
-                    s._clique_samples[c] = samples
-                model, data = s._prepare_clique_model(c, samples, var_order)
+                stream = self._stream(slot)
+                model = None
+                if on_device:
+                    # simulator -> normalisation -> training, all on the clique's stream ("next" row N1)
+                    sim_seed = seed if reseed else int(np.random.randint(0, 2 ** 31 - 1))
+                    stream.wait_stream(torch.cuda.current_stream())
+                    try:
+                        with torch.cuda.stream(stream):
+                            model, data = s._prepare_clique_model_device(c, sampler, var_order, sim_seed, counter)
+                    except NotImplementedError:
+                        model = None          # a factor type without a device simulator: host simulation below
+                if model is None:
+                    samples, _, _ = sampler.sample(a.local_sample_num)
+                    if a.store_clique_samples:
+                        s._clique_samples[c] = samples
+                    model, data = s._prepare_clique_model(c, samples, var_order)
                 t1 = time.time()
                 sim_time += t1 - t0
                 model.flows[0].fit_launch(data, a.flow_iterations, a.learning_rate, average_window=a.average_window,
-                                          loss_delta_tol=a.loss_delta_tol, stream=self._stream(slot),
+                                          loss_delta_tol=a.loss_delta_tol, stream=stream,
                                           val=model._validation_data, validation_interval=a.validation_interval,
                                           slower_stop_rate=a.slower_stop_rate)
                 launched.append((k, c, model))
@@ -126,7 +140,11 @@ class CliqueScheduler:
             t1 = time.time()
             for k, c, model in launched:
                 hist, ran = model.flows[0].fit_finish(pull=True)
+                model.pull_normalisation()
+                model.__dict__.pop("_sim_keep", None)
                 results[k] = (model, hist)
+            if counter is not None and int(counter.item()):
+                raise AssertionError("negative discriminant in the inverse spline while sampling a separator factor")
             train_time += time.time() - t1
             for k, c in enumerate(todo):
                 sampler, var_order, true_obs = plans[id(c)]

@@ -9,13 +9,64 @@ contributes a simulated observation; data-association mixtures come last.
 
 `plan()` resolves the schedule without drawing anything (it is deterministic), so that ranks that do
 not own a clique still learn its column order and observation vector."""
+import ctypes
 from typing import Dict, List, Tuple
 
 import numpy as np
 
+from .. import _lib
+
 from ..factors.factors import (AmbiguousDataAssociationFactor, BinaryFactor, BinaryFactorWithNullHypo, Factor,
                                PriorFactor)
 from .variables import Variable
+
+
+class SimProgram:
+    """Op list of the device simulator (nfisam_simulate, include/nfisam_b200.h): factors append ops through
+    `add`, `run` executes them with one kernel launch on the current CUDA stream."""
+
+    def __init__(self, n: int, col_of: Dict[Variable, int], ld: int, counter=None):
+        self.n, self.col_of, self.ld = int(n), dict(col_of), int(ld)
+        self.counter = counter              # optional device int64 tensor counting bad spline discriminants
+        self.ops: List[_lib.nf_sim_op] = []
+        self.next_slot = 0
+        self.keep = []                      # device tensors the ops point into
+
+    def col(self, var: Variable) -> int:
+        return self.col_of[var]
+
+    def reserve(self, k: int) -> int:
+        slot = self.next_slot
+        self.next_slot += k
+        return slot
+
+    def add(self, kind, out, in_a=-1, in_b=-1, n_out=3, obs=(), chol=(), slots=0, rows=None, slot=None, src=None, src_ld=0):
+        op = _lib.nf_sim_op()
+        op.type = int(kind)
+        op.row_lo, op.row_hi = (0, self.n) if rows is None else (int(rows[0]), int(rows[1]))
+        op.in_a, op.in_b, op.out, op.n_out = int(in_a), int(in_b), int(out), int(n_out)
+        op.slot = self.reserve(slots) if slot is None else int(slot)
+        for i, v in enumerate(np.asarray(obs, float).ravel()[:3]):
+            op.obs[i] = float(v)
+        low = np.atleast_2d(np.asarray(chol, float)) if len(chol) else np.zeros((0, 0))
+        k = 0
+        for i in range(3):
+            for j in range(i + 1):
+                op.chol[k] = float(low[i, j]) if i < low.shape[0] and j < low.shape[1] else 0.0
+                k += 1
+        op.src_dev = src
+        op.src_ld = int(src_ld)
+        self.ops.append(op)
+
+    def run(self, seed: int, device):
+        import torch
+
+        s_mat = torch.zeros((self.n, self.ld), dtype=torch.float64, device=device)
+        arr = (_lib.nf_sim_op * max(len(self.ops), 1))(*self.ops)
+        st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(_lib.load().nfisam_simulate(arr, len(self.ops), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), s_mat.data_ptr(),
+                                               self.n, self.ld, device.index if device.index is not None else 0, st))
+        return s_mat
 
 
 class SimulationBasedSampler:
@@ -127,3 +178,43 @@ class SimulationBasedSampler:
         cols = obs_cols + [drawn[v] for v in self.vars]
         local = np.hstack(cols) if cols else np.empty((num_samples, 0))
         return local, var_ordering, unused_obs
+
+    # ------------------------------------------------------------------------------------------
+    def program(self, num_samples: int, counter=None) -> SimProgram:
+        """The schedule of `plan()` as a device op list ("next" row N1).  Columns of the device sample matrix are the
+        training columns [observations | separator | frontal] in order.  Raises NotImplementedError when a factor has
+        no device simulator (the caller then uses `sample`).  Draws the mixtures' multinomial splits from np.random."""
+        steps, var_ordering, _ = self.plan()
+        col_of, off = {}, 0
+        for v in var_ordering:
+            col_of[v] = off
+            off += v.dim
+        obs_cols = [col_of[v] for v in var_ordering[:len(var_ordering) - len(self.vars)]]
+        prog = SimProgram(num_samples, col_of, off, counter)
+        k_obs = 0
+        for st in steps:
+            kind, f = st[0], st[1]
+            try:
+                if kind == "prior":
+                    f.sim_prior(prog)
+                elif kind == "gen":
+                    f.sim_gen(prog, st[2], st[3])
+                elif kind == "obs":
+                    f.sim_obs(prog, obs_cols[k_obs])
+                    k_obs += 1
+                elif kind == "da_obs":
+                    f.sim_observations(prog, obs_cols[k_obs])
+                    k_obs += 1
+                elif kind == "da_gen":
+                    f.sim_observer(prog)
+            except AttributeError as e:
+                raise NotImplementedError(f"{type(f).__name__} has no device simulator") from e
+        return prog
+
+    def sample_device(self, num_samples: int, seed: int, device, counter=None):
+        """Device-resident `sample`: (n, D) float64 CUDA tensor whose columns follow `plan()`'s variable ordering.
+        Enqueued on the current CUDA stream; nothing synchronises."""
+        prog = self.program(num_samples, counter)
+        s_mat = prog.run(seed, device)
+        s_mat._sim_keep = prog.keep          # flow-prior staging buffers stay alive with the result
+        return s_mat
