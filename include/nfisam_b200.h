@@ -268,6 +268,12 @@ int nfisam_simulate(const nf_sim_op* ops_host, int n_ops, uint64_t seed, double*
  * Exposes the generator for parity tests. */
 int nfisam_sim_noise(uint64_t seed, int slot, int normal, double* out_dev, int64_t n, int device, void* stream);
 
+/* Standard-normal float32 matrix out_dev (n, cols) with row stride ld: entry (row, c) is normal number (c & 1) of noise
+ * slot slot0 + c / 2 of `seed`.  Replaces the latent draw torch.randn((n, dim)) of
+ * NormalizingFlowModelWithSeparator.conditional_sample_given_observation (src/slam/NFiSAM.py:120-155) where the
+ * samples stay on the device (flow-backed separator factors inside the simulator). */
+int nfisam_randn_f32(uint64_t seed, int slot0, float* out_dev, int64_t n, int cols, int ld, int device, void* stream);
+
 /* NFiSAM.normalize_training_samples (src/slam/NFiSAM.py:515-548) on the device.  Column j of the (n_rows, d)
  * float32 training matrix is column cols_host[j] of s_dev, rows taken through perm_dev (int32 row indices; NULL =
  * rows row0 .. row0 + n_rows - 1):

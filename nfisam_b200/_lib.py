@@ -114,6 +114,7 @@ SYMBOLS = {
     "nfisam_mixture_posterior_weights": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _INT, _P]),
     "nfisam_simulate": (_INT, [ctypes.POINTER(nf_sim_op), _INT, ctypes.c_uint64, _P, _I64, _INT, _INT, _P]),
     "nfisam_sim_noise": (_INT, [ctypes.c_uint64, _INT, _INT, _P, _I64, _INT, _P]),
+    "nfisam_randn_f32": (_INT, [ctypes.c_uint64, _INT, _P, _I64, _INT, _INT, _INT, _P]),
     "nfisam_normalize_training": (_INT, [_P, _I64, _INT, _P, _I64, _P, _P, _INT, _P, _P, _INT, _P]),
 }
 

@@ -683,6 +683,13 @@ int nfisam_sim_noise(uint64_t seed, int slot, int normal, double* out_dev, int64
     return nf_launch_sim_noise(seed, slot, normal, out_dev, n, (cudaStream_t)stream);
 }
 
+int nfisam_randn_f32(uint64_t seed, int slot0, float* out_dev, int64_t n, int cols, int ld, int device, void* stream) {
+    if ((!out_dev && n > 0) || n < 0 || cols < 0 || ld < cols || slot0 < 0) return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    return nf_launch_randn_f32(seed, slot0, out_dev, n, cols, ld, (cudaStream_t)stream);
+}
+
 int nfisam_normalize_training(const double* s_dev, int64_t n_rows, int ld, const int32_t* perm_dev, int64_t row0,
                               const int32_t* cols_host, const uint8_t* circular_host, int d, float* data_dev,
                               float* mean_std_dev, int device, void* stream) {

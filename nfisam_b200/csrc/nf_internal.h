@@ -94,5 +94,6 @@ int nf_launch_mixture_weights(const nf_factor_desc* descs_dev, int n_desc, const
 // nf_sim_kernels.cu
 int nf_launch_simulate(const nf_sim_op* ops, int n_ops, uint64_t seed, double* s_mat, int64_t n, int ld, cudaStream_t st);
 int nf_launch_sim_noise(uint64_t seed, int slot, int normal, double* out, int64_t n, cudaStream_t st);
+int nf_launch_randn_f32(uint64_t seed, int slot0, float* out, int64_t n, int cols, int ld, cudaStream_t st);
 int nf_launch_normalize(const double* s_mat, int64_t n_rows, int ld, const int32_t* perm, int64_t row0, const int32_t* cols,
                         const uint8_t* circular, int d, float* data, float* mean_std, cudaStream_t st);

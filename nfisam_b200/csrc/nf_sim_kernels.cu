@@ -226,6 +226,19 @@ __global__ void nf_sim_noise_kernel(uint64_t seed, int slot, int normal, double*
     out[2 * row + 1] = b;
 }
 
+// standard-normal float32 matrix: entry (row, c) is normal (c & 1) of slot slot0 + c / 2
+__global__ void nf_randn_f32_kernel(uint64_t seed, int slot0, float* __restrict__ out, int64_t n, int cols, int ld) {
+    const int pairs = (cols + 1) / 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * pairs) return;
+    const int64_t row = t / pairs;
+    const int p = (int)(t - row * pairs);
+    double a, b;
+    normal2(seed, (uint64_t)row, (uint32_t)(slot0 + p), a, b);
+    out[row * ld + 2 * p] = (float)a;
+    if (2 * p + 1 < cols) out[row * ld + 2 * p + 1] = (float)b;
+}
+
 // ---- training-set normalisation: one block per training column ------------------------------------------------
 constexpr int NORM_TPB = 256;
 constexpr int NORM_MAX_COLS = NF_MAX_DIM;
@@ -331,6 +344,14 @@ int nf_launch_sim_noise(uint64_t seed, int slot, int normal, double* out, int64_
     nf_sim_noise_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, slot, normal, out, n);
     nf_count_launch();
     return nf_check_launch("nf_sim_noise_kernel");
+}
+
+int nf_launch_randn_f32(uint64_t seed, int slot0, float* out, int64_t n, int cols, int ld, cudaStream_t st) {
+    if (n == 0 || cols == 0) return NF_OK;
+    const int64_t total = n * ((cols + 1) / 2);
+    nf_randn_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(seed, slot0, out, n, cols, ld);
+    nf_count_launch();
+    return nf_check_launch("nf_randn_f32_kernel");
 }
 
 int nf_launch_normalize(const double* s_mat, int64_t n_rows, int ld, const int32_t* perm, int64_t row0, const int32_t* cols,

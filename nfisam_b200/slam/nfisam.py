@@ -226,12 +226,13 @@ class FlowsPriorFactor(CliqueSeparatorFactor):
         return self._flow_model.conditional_sample_given_observation(conditional_dim=self.dim, obs_samples=obs)
 
     def sim_prior(self, prog):
-        """Device form of `sample`: same CPU latent draw, the inverse flow writes float32 samples into a staging matrix
-        on the current stream and the simulator kernel copies them into the clique's sample matrix."""
+        """Device form of `sample`: latent draws from the program's device noise stream, the inverse flow writes float32
+        samples into a staging matrix on the current stream and the simulator kernel copies them into the clique's
+        sample matrix."""
         fm = self._flow_model
         flow = fm.flows[0]
         dev = flow._dev()
-        z_dev = fm.draw_latent(prog.n, self._obs_dim, self.dim).contiguous().to(dev, non_blocking=True)
+        z_dev = prog.randn_f32(self.dim, dev)
         stage = torch.empty((prog.n, self.dim), dtype=torch.float32, device=dev)
         flow.inverse_gather(z_dev, 0, stage, [-1] * self._obs_dim, [float(o) for o in self._true_obs], list(range(self.dim)),
                             norm=fm._norm(), counter=prog.counter)
@@ -309,11 +310,11 @@ class NFiSAM(FactorGraphSolver):
         if a.flow_number != 1 or a.flow_type != "NSF_AR":
             raise NotImplementedError("only flow_type='NSF_AR' with flow_number=1 exists in the reference")
         n = a.local_sample_num
-        prog = sampler.program(n, counter)
+        prog = sampler.program(n, counter, seed)
         flow = NSF_AR(dim=prog.ld, K=a.num_knots, hidden_dim=a.hidden_dim, device=a.device)
         dev = flow._dev()
         # flow-backed priors were enqueued by program(); now the simulator itself
-        s_mat = prog.run(seed, dev)
+        s_mat = prog.run(dev)
         circular = []
         for var in var_ordering:
             circular += var.circular_dim_list

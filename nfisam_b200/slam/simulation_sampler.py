@@ -25,8 +25,9 @@ class SimProgram:
     """Op list of the device simulator (nfisam_simulate, include/nfisam_b200.h): factors append ops through
     `add`, `run` executes them with one kernel launch on the current CUDA stream."""
 
-    def __init__(self, n: int, col_of: Dict[Variable, int], ld: int, counter=None):
+    def __init__(self, n: int, col_of: Dict[Variable, int], ld: int, counter=None, seed: int = 0):
         self.n, self.col_of, self.ld = int(n), dict(col_of), int(ld)
+        self.seed = int(seed) & (2 ** 64 - 1)
         self.counter = counter              # optional device int64 tensor counting bad spline discriminants
         self.ops: List[_lib.nf_sim_op] = []
         self.next_slot = 0
@@ -58,13 +59,24 @@ class SimProgram:
         op.src_ld = int(src_ld)
         self.ops.append(op)
 
-    def run(self, seed: int, device):
+    def randn_f32(self, cols: int, device):
+        """(n, cols) float32 standard normals on the device from this program's noise stream (fresh slots)."""
+        import torch
+
+        out = torch.empty((self.n, cols), dtype=torch.float32, device=device)
+        slot = self.reserve((cols + 1) // 2)
+        st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(_lib.load().nfisam_randn_f32(ctypes.c_uint64(self.seed), slot, out.data_ptr(), self.n, cols, cols,
+                                                device.index if device.index is not None else 0, st))
+        return out
+
+    def run(self, device):
         import torch
 
         s_mat = torch.zeros((self.n, self.ld), dtype=torch.float64, device=device)
         arr = (_lib.nf_sim_op * max(len(self.ops), 1))(*self.ops)
         st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        _lib.check(_lib.load().nfisam_simulate(arr, len(self.ops), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), s_mat.data_ptr(),
+        _lib.check(_lib.load().nfisam_simulate(arr, len(self.ops), ctypes.c_uint64(self.seed), s_mat.data_ptr(),
                                                self.n, self.ld, device.index if device.index is not None else 0, st))
         return s_mat
 
@@ -180,7 +192,7 @@ class SimulationBasedSampler:
         return local, var_ordering, unused_obs
 
     # ------------------------------------------------------------------------------------------
-    def program(self, num_samples: int, counter=None) -> SimProgram:
+    def program(self, num_samples: int, counter=None, seed: int = 0) -> SimProgram:
         """The schedule of `plan()` as a device op list ("next" row N1).  Columns of the device sample matrix are the
         training columns [observations | separator | frontal] in order.  Raises NotImplementedError when a factor has
         no device simulator (the caller then uses `sample`).  Draws the mixtures' multinomial splits from np.random."""
@@ -190,7 +202,7 @@ class SimulationBasedSampler:
             col_of[v] = off
             off += v.dim
         obs_cols = [col_of[v] for v in var_ordering[:len(var_ordering) - len(self.vars)]]
-        prog = SimProgram(num_samples, col_of, off, counter)
+        prog = SimProgram(num_samples, col_of, off, counter, seed)
         k_obs = 0
         for st in steps:
             kind, f = st[0], st[1]
@@ -214,7 +226,7 @@ class SimulationBasedSampler:
     def sample_device(self, num_samples: int, seed: int, device, counter=None):
         """Device-resident `sample`: (n, D) float64 CUDA tensor whose columns follow `plan()`'s variable ordering.
         Enqueued on the current CUDA stream; nothing synchronises."""
-        prog = self.program(num_samples, counter)
-        s_mat = prog.run(seed, device)
+        prog = self.program(num_samples, counter, seed)
+        s_mat = prog.run(device)
         s_mat._sim_keep = prog.keep          # flow-prior staging buffers stay alive with the result
         return s_mat

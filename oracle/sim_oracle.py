@@ -66,6 +66,18 @@ def normal2(seed, rows, slot):
     return r * np.cos(TWO_PI * u1), r * np.sin(TWO_PI * u1)
 
 
+def randn_f32(seed, n, cols, slot0):
+    """(n, cols) float32: entry (row, c) is normal (c & 1) of slot slot0 + c // 2 (nfisam_randn_f32)."""
+    rows = np.arange(n)
+    out = np.empty((n, cols), np.float32)
+    for p in range((cols + 1) // 2):
+        a, b = normal2(seed, rows, slot0 + p)
+        out[:, 2 * p] = a
+        if 2 * p + 1 < cols:
+            out[:, 2 * p + 1] = b
+    return out
+
+
 # ---- SE(2) --------------------------------------------------------------------------------------------------------
 def wrap(t):
     return (t + np.pi) % TWO_PI - np.pi

