@@ -58,7 +58,7 @@ int64_t nfisam_launch_count(void);
  * operands, [1] packed FFMA2 (fma.rn.f32x2), [2] FFMA with constant-bank operands, all in TFLOP/s
  * (2 flops per FMA); [3] MUFU ex2 in Gop/s.  Synchronous, ~30 ms. */
 int nfisam_probe_pipe_peaks(int device, double* peaks4);
-/* sizeof of an ABI struct, for binding validation: 0 nf_train_cfg, 1 nf_factor_desc, 2 nf_affine, 3 nf_sim_op. */
+/* sizeof of an ABI struct, for binding validation: 0 nf_train_cfg, 1 nf_factor_desc, 2 nf_affine, 3 nf_sim_op, 4 nf_gather_item. */
 int nfisam_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -130,6 +130,26 @@ int nfisam_flow_set_bad_counter(nf_flow_t* f, unsigned long long* counter_dev);
 int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z_col0, float* s_dev, int ld_s,
                                const int32_t* sep_cols_host, const float* sep_const_host, int sep_dim,
                                const int32_t* out_cols_host, int out_dim, int64_t n, const nf_affine* norm, void* stream);
+
+/* The whole posterior down-pass in one call: item k is one nfisam_flow_inverse_gather on flow k's handle (cliques in
+ * root-to-leaf order, so that a clique's given columns were generated by an earlier item).  All flows must live on the
+ * device of items[0].flow.  Negative spline discriminants of every item are added to *bad_counter_dev (may be NULL).
+ * Replaces the per-clique Python loop of FactorGraphSolver.sample_posterior (src/slam/FactorGraphSolver.py:497-550).
+ * When all flows share (K, hidden, tail bound) and the items' column dependencies form a forest (a Bayes tree does),
+ * the pass runs as at most two kernel launches: the trunk (root and its only-child descendants), then every subtree
+ * below the first branching clique concurrently, a warp walking its 32 rows through the cliques of its subtree.
+ * Otherwise one kernel per item is enqueued.  Results are bit-identical either way.
+ * Asynchronous on `stream`; the host arrays are consumed before the call returns. */
+typedef struct nf_gather_item {
+    nf_flow_t* flow;
+    int32_t z_col0, sep_dim, out_dim, pad_;
+    const int32_t* sep_cols_host;   /* sep_dim entries; < 0 = constant */
+    const float* sep_const_host;    /* sep_dim entries (used where sep_cols < 0) */
+    const int32_t* out_cols_host;   /* out_dim entries */
+    nf_affine norm;                 /* all three pointers NULL = normalised space */
+} nf_gather_item;
+int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float* z_dev, int ld_z, float* s_dev, int ld_s,
+                          int64_t n, unsigned long long* bad_counter_dev, void* stream);
 
 /* Host-buffer convenience used for the end-to-end numbers: pinned staging, chunked
  * H2D -> kernel -> D2H pipelining on two internal streams.  Synchronous. */

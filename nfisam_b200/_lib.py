@@ -81,6 +81,20 @@ class nf_sim_op(ctypes.Structure):
     ]
 
 
+class nf_gather_item(ctypes.Structure):
+    _fields_ = [
+        ("flow", ctypes.c_void_p),
+        ("z_col0", ctypes.c_int32),
+        ("sep_dim", ctypes.c_int32),
+        ("out_dim", ctypes.c_int32),
+        ("pad_", ctypes.c_int32),
+        ("sep_cols_host", ctypes.c_void_p),
+        ("sep_const_host", ctypes.c_void_p),
+        ("out_cols_host", ctypes.c_void_p),
+        ("norm", nf_affine),
+    ]
+
+
 # every symbol include/nfisam_b200.h declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -104,6 +118,7 @@ SYMBOLS = {
     "nfisam_flow_set_bad_counter": (_INT, [_P, _P]),
     "nfisam_flow_inverse_gather": (_INT, [_P, _P, _INT, _INT, _P, _INT, _P, _P, _INT, _P, _INT, _I64,
                                           ctypes.POINTER(nf_affine), _P]),
+    "nfisam_posterior_pass": (_INT, [ctypes.POINTER(nf_gather_item), _INT, _P, _INT, _P, _INT, _I64, _P, _P]),
     "nfisam_flow_log_prob_host": (_INT, [_P, _P, _I64, _INT, _P]),
     "nfisam_flow_inverse_host": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _P, _P, _P]),
     "nfisam_flow_train": (_INT, [_P, _P, _I64, ctypes.POINTER(nf_train_cfg), _P, ctypes.POINTER(ctypes.c_int32), _P]),
@@ -147,7 +162,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the export is missing
             fn.restype = res
             fn.argtypes = args
-        for which, st in enumerate((nf_train_cfg, nf_factor_desc, nf_affine, nf_sim_op)):
+        for which, st in enumerate((nf_train_cfg, nf_factor_desc, nf_affine, nf_sim_op, nf_gather_item)):
             if lib.nfisam_struct_size(which) != ctypes.sizeof(st):
                 raise NfisamError(NF_ERR_BAD_ARG, f"ABI mismatch: sizeof({st.__name__}) differs between header and binding")
         _lib = lib

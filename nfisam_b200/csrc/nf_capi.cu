@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "nf_internal.h"
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------------
 // error / bookkeeping helpers
@@ -144,6 +145,7 @@ int nfisam_struct_size(int which) {
         case 1: return (int)sizeof(nf_factor_desc);
         case 2: return (int)sizeof(nf_affine);
         case 3: return (int)sizeof(nf_sim_op);
+        case 4: return (int)sizeof(nf_gather_item);
         default: return -1;
     }
 }
@@ -302,6 +304,170 @@ int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z
     return nf_launch_inverse_gather(f->fd, f->d_pk, z_dev, ld_z, z_col0, s_dev, ld_s, sep_cols_host, sep_const_host, sep_dim,
                                     out_cols_host, out_dim, n, mean, stdv, circ, f->d_bad_ext ? f->d_bad_ext : f->d_bad,
                                     f->device, (cudaStream_t)stream);
+}
+
+int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float* z_dev, int ld_z, float* s_dev, int ld_s,
+                          int64_t n, unsigned long long* bad_counter_dev, void* stream) {
+    if (n_items < 0 || (n_items > 0 && (!items || !z_dev || !s_dev)) || n < 0) return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    if (n_items == 0 || n == 0) return NF_OK;
+    bool uniform = true;      // one (K, hidden, tail bound) for every clique: the fused kernel applies
+    int max_wcount = 0, max_d = 0;
+    std::vector<NfPassItem> host((size_t)n_items);
+    for (int k = 0; k < n_items; ++k) {
+        const nf_gather_item& it = items[k];
+        if (!it.flow || !it.out_cols_host) return nf_set_error(NF_ERR_BAD_ARG, "item %d: NULL flow / columns", k);
+        const nf_flow* f = it.flow;
+        if (f->device != items[0].flow->device) return nf_set_error(NF_ERR_BAD_ARG, "item %d: flow on another device", k);
+        if (it.sep_dim < 0 || it.out_dim < 1 || it.sep_dim + it.out_dim > f->fd.d)
+            return nf_set_error(NF_ERR_BAD_ARG, "item %d: bad sep_dim / out_dim", k);
+        if (it.sep_dim > 0 && !it.sep_cols_host) return nf_set_error(NF_ERR_BAD_ARG, "item %d: sep_cols_host is NULL", k);
+        if (it.z_col0 < 0 || it.z_col0 + it.out_dim > ld_z) return nf_set_error(NF_ERR_BAD_ARG, "item %d: latent columns out of range", k);
+        const bool any = it.norm.mean_dev || it.norm.std_dev || it.norm.circular_dev;
+        if (any && !(it.norm.mean_dev && it.norm.std_dev && it.norm.circular_dev))
+            return nf_set_error(NF_ERR_BAD_ARG, "item %d: incomplete nf_affine", k);
+        uniform = uniform && f->fd.K == items[0].flow->fd.K && f->fd.H == items[0].flow->fd.H && f->fd.B == items[0].flow->fd.B;
+        NfPassItem& h = host[(size_t)k];
+        memset(&h, 0, sizeof(h));
+        h.pk = f->d_pk;
+        h.mean = it.norm.mean_dev; h.stdv = it.norm.std_dev; h.circ = it.norm.circular_dev;
+        h.d = it.sep_dim + it.out_dim; h.sep = it.sep_dim; h.z_col0 = it.z_col0;
+        h.w_first = nf_block_off(h.sep, f->fd.H, f->fd.Pp);
+        h.wcount = nf_block_off(h.d, f->fd.H, f->fd.Pp) - h.w_first;
+        for (int j = 0; j < it.sep_dim; ++j) {
+            h.sep_cols[j] = it.sep_cols_host[j];
+            if (h.sep_cols[j] >= ld_s || (h.sep_cols[j] < 0 && !it.sep_const_host))
+                return nf_set_error(NF_ERR_BAD_ARG, "item %d: given column %d out of range / constant missing", k, j);
+            h.sep_const[j] = it.sep_const_host ? it.sep_const_host[j] : 0.0f;
+        }
+        for (int c = 0; c < it.out_dim; ++c) {
+            h.out_cols[c] = it.out_cols_host[c];
+            if (h.out_cols[c] < 0 || h.out_cols[c] >= ld_s) return nf_set_error(NF_ERR_BAD_ARG, "item %d: output column %d out of range", k, c);
+        }
+        max_wcount = h.wcount > max_wcount ? h.wcount : max_wcount;
+        max_d = h.d > max_d ? h.d : max_d;
+    }
+    // Dependency forest of the items: item k hangs below the latest earlier item that produced one of its given columns
+    // (in a Bayes tree: its parent clique).  The trunk (single root and its only-child descendants) is one launch; the
+    // subtrees below the first branching item are mutually independent GROUPS that one second launch walks concurrently.
+    // Any dependency that crosses two groups (not a tree: arbitrary caller input) disables the fused path.
+    bool fusable = uniform;
+    std::vector<int> parent((size_t)n_items, -1), gid((size_t)n_items, -1);
+    std::vector<std::vector<int>> deps((size_t)n_items);
+    if (fusable) {
+        std::vector<int> producer((size_t)ld_s, -1);
+        for (int k = 0; k < n_items; ++k) {
+            const NfPassItem& h = host[(size_t)k];
+            for (int j = 0; j < h.sep; ++j)
+                if (h.sep_cols[j] >= 0 && producer[(size_t)h.sep_cols[j]] >= 0) deps[(size_t)k].push_back(producer[(size_t)h.sep_cols[j]]);
+            for (int c = 0; c < h.d - h.sep; ++c) {
+                int& p = producer[(size_t)h.out_cols[c]];
+                if (p >= 0) deps[(size_t)k].push_back(p);      // column rewritten: order against the earlier writer
+                p = k;
+            }
+            for (int p : deps[(size_t)k]) parent[(size_t)k] = p > parent[(size_t)k] ? p : parent[(size_t)k];
+        }
+    }
+    std::vector<int> order;                 // trunk first, then the groups, each in caller order
+    std::vector<int2> groups;               // [first, count) into `order`; groups[0] = trunk (may be empty)
+    if (fusable) {
+        std::vector<int> n_child((size_t)n_items, 0);
+        int n_roots = 0, root = -1;
+        for (int k = 0; k < n_items; ++k) {
+            if (parent[(size_t)k] < 0) { ++n_roots; if (root < 0) root = k; }
+            else ++n_child[(size_t)parent[(size_t)k]];
+        }
+        const int TRUNK = -2;
+        if (n_roots == 1) {
+            int t = root;
+            gid[(size_t)t] = TRUNK;
+            while (n_child[(size_t)t] == 1) {
+                int c = -1;
+                for (int k = t + 1; k < n_items; ++k) if (parent[(size_t)k] == t) { c = k; break; }
+                gid[(size_t)c] = TRUNK;
+                t = c;
+            }
+        }
+        int n_groups = 0;
+        for (int k = 0; k < n_items; ++k) {
+            if (gid[(size_t)k] == TRUNK) continue;
+            const int p = parent[(size_t)k];
+            gid[(size_t)k] = (p < 0 || gid[(size_t)p] == TRUNK) ? n_groups++ : gid[(size_t)p];
+        }
+        for (int k = 0; k < n_items && fusable; ++k) {
+            for (int p : deps[(size_t)k]) {
+                const bool ok = gid[(size_t)p] == TRUNK ? true : gid[(size_t)p] == gid[(size_t)k];
+                if (!ok || (gid[(size_t)k] == TRUNK && gid[(size_t)p] != TRUNK)) { fusable = false; break; }
+            }
+        }
+        if (n_groups > 65535) fusable = false;
+        if (fusable) {
+            std::vector<int> count((size_t)n_groups + 1, 0);
+            for (int k = 0; k < n_items; ++k) ++count[gid[(size_t)k] == TRUNK ? 0 : (size_t)gid[(size_t)k] + 1];
+            groups.resize((size_t)n_groups + 1);
+            int at = 0;
+            for (int g = 0; g <= n_groups; ++g) { groups[(size_t)g] = make_int2(at, 0); at += count[(size_t)g]; }
+            order.resize((size_t)n_items);
+            for (int k = 0; k < n_items; ++k) {
+                int2& g = groups[gid[(size_t)k] == TRUNK ? 0 : (size_t)gid[(size_t)k] + 1];
+                order[(size_t)(g.x + g.y++)] = k;
+            }
+        }
+    }
+    const nf_flow* f0 = items[0].flow;
+    DeviceGuard g(f0->device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", f0->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    static const bool fused_env = !(getenv("NFISAM_PASS_FUSED") && getenv("NFISAM_PASS_FUSED")[0] == '0');
+    if (fusable && fused_env) {
+        // Descriptor staging: one grow-only pinned + device buffer pair per device, reused by every pass.  (Stream-ordered
+        // allocation was measured at 1-15 ms per call here: the default pool trims at every synchronisation.)  The
+        // event orders reuse against the previous pass, on whichever stream it ran.
+        struct PassStage { unsigned char* dev = nullptr; unsigned char* host = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; };
+        static PassStage stages[64];
+        static std::mutex stage_mu;
+        if (f0->device < 0 || f0->device >= 64) return nf_set_error(NF_ERR_BAD_ARG, "device index out of range");
+        std::lock_guard<std::mutex> lk(stage_mu);
+        PassStage& sg = stages[f0->device];
+        const size_t item_bytes = sizeof(NfPassItem) * (size_t)n_items, group_bytes = sizeof(int2) * groups.size();
+        const size_t bytes = item_bytes + group_bytes;
+        if (!sg.done) NF_CUDA(cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
+        NF_CUDA(cudaEventSynchronize(sg.done));          // previous pass has consumed the staging buffers
+        if (bytes > sg.cap) {
+            if (sg.dev) cudaFree(sg.dev);
+            if (sg.host) cudaFreeHost(sg.host);
+            sg.dev = sg.host = nullptr;
+            sg.cap = 0;
+            const size_t cap = bytes * 2 > (size_t)(64 << 10) ? bytes * 2 : (size_t)(64 << 10);
+            NF_CUDA(cudaMalloc(&sg.dev, cap));
+            NF_CUDA(cudaMallocHost(&sg.host, cap));
+            sg.cap = cap;
+        }
+        for (int k = 0; k < n_items; ++k) memcpy(sg.host + sizeof(NfPassItem) * (size_t)k, &host[(size_t)order[(size_t)k]], sizeof(NfPassItem));
+        memcpy(sg.host + item_bytes, groups.data(), group_bytes);
+        NF_CUDA(cudaMemcpyAsync(sg.dev, sg.host, bytes, cudaMemcpyHostToDevice, st));
+        const NfPassItem* d_items = reinterpret_cast<const NfPassItem*>(sg.dev);
+        const int2* d_groups = reinterpret_cast<const int2*>(sg.dev + item_bytes);
+        int rc = NF_OK;
+        if (groups[0].y > 0)                         // trunk
+            rc = nf_launch_posterior_pass(f0->fd, d_items, d_groups, 1, max_wcount, max_d, z_dev, ld_z, s_dev, ld_s, n,
+                                          bad_counter_dev, f0->device, st);
+        if (rc == NF_OK && groups.size() > 1)        // independent subtrees
+            rc = nf_launch_posterior_pass(f0->fd, d_items, d_groups + 1, (int)groups.size() - 1, max_wcount, max_d, z_dev, ld_z,
+                                          s_dev, ld_s, n, bad_counter_dev, f0->device, st);
+        cudaEventRecord(sg.done, st);
+        return rc;
+    }
+    for (int k = 0; k < n_items; ++k) {            // mixed flow shapes / not a forest: one launch per clique
+        const nf_gather_item& it = items[k];
+        const bool has_norm = it.norm.mean_dev != nullptr;
+        unsigned long long* saved = it.flow->d_bad_ext;
+        if (bad_counter_dev) it.flow->d_bad_ext = bad_counter_dev;
+        const int rc = nfisam_flow_inverse_gather(it.flow, z_dev, ld_z, it.z_col0, s_dev, ld_s, it.sep_cols_host, it.sep_const_host,
+                                                  it.sep_dim, it.out_cols_host, it.out_dim, n, has_norm ? &it.norm : nullptr, stream);
+        it.flow->d_bad_ext = saved;
+        if (rc != NF_OK) return rc;
+    }
+    return NF_OK;
 }
 
 int nfisam_flow_set_bad_counter(nf_flow_t* f, unsigned long long* counter_dev) {

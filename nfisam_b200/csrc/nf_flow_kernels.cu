@@ -94,7 +94,7 @@ struct NfGather {
 
 template <int K, int H, bool GATHER>
 __global__ void __launch_bounds__(TPB)
-nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, float B, const float* __restrict__ zin,  // d = sep + generated dims
+nf_inverse_kernel(const float* __restrict__ pk, int w_first, int wcount, int d, int sep, float B, const float* __restrict__ zin,  // d = sep + generated dims
                   const float* __restrict__ xsep, int64_t n, float* __restrict__ xout, float* __restrict__ logdet,
                   const float* __restrict__ mean, const float* __restrict__ stdv, const uint8_t* __restrict__ circ,
                   unsigned long long* __restrict__ bad_count, const __grid_constant__ NfGather ga) {
@@ -105,7 +105,8 @@ nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, floa
     const int f = d - sep;
     float* xs = sw + wcount;                       // [TPB][dp]  separator columns then generated ones
     float* zs = xs + TPB * dp;                     // [TPB][dp]  latent draws (first f columns used)
-    load_weights(sw, pk, wcount);
+    load_weights(sw, pk + w_first, wcount);        // only the conditioners of the generated dims sep .. d-1
+    const float* wbase = sw - w_first;             // conditioner i sits at wbase + nf_block_off(i)
     const bool has_norm = mean != nullptr;
     const int64_t tiles = (n + TPB - 1) / TPB;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -136,7 +137,7 @@ nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, floa
             bool bad = false;
             for (int i = sep; i < d; ++i) {
                 float ld;
-                const float xi = nf_inverse_dim<K, H>(sw, i, xrow, B, zrow[i - sep], ld, bad);
+                const float xi = nf_inverse_dim<K, H>(wbase, i, xrow, B, zrow[i - sep], ld, bad);
                 ld_acc += ld;
                 xrow[i] = xi;
             }
@@ -155,6 +156,92 @@ nf_inverse_kernel(const float* __restrict__ pk, int wcount, int d, int sep, floa
             else xout[s0 * f + t] = v;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole posterior down-pass in ONE or TWO launches (nfisam_posterior_pass).  Rows of the sample matrix are independent:
+// row r of every clique's frontal block depends only on row r of the latent matrix and on earlier columns of row r.
+// A block is ONE warp that owns 32 rows (lane = row) and walks a list of cliques root -> leaves on its own: per clique
+// it stages the descriptor, the weights of the conditioners it needs (dims sep..d-1 only) and the normalisation
+// constants in shared memory, every lane gathers the given columns of its own row, inverts the frontal dims and
+// scatters them back.  A lane only ever reads columns of its own row that it wrote itself (or that an earlier launch
+// wrote): no block-level barrier, no grid synchronisation, no launch gap between cliques (a chain-shaped Bayes tree of
+// 100 cliques was 100 dependent launches before).  blockIdx.y selects a GROUP of cliques: independent subtrees below the
+// first branching clique run concurrently (second launch), the trunk above it is the first launch.
+// ---------------------------------------------------------------------------------------------
+constexpr int PASS_ROWS = 32;
+
+template <int K, int H>
+__global__ void __launch_bounds__(PASS_ROWS)
+nf_posterior_pass_kernel(const NfPassItem* __restrict__ items, const int2* __restrict__ groups, float B,
+                         const float* __restrict__ zin, int ld_z, float* s_mat, int ld_s, int64_t n,
+                         unsigned long long* __restrict__ bad_count, int w_floats, int dp_max) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ NfPassItem it;
+    __shared__ float s_mean[NF_MAX_DIM], s_std[NF_MAX_DIM];
+    __shared__ int s_circ[NF_MAX_DIM];
+    float* sw = smem;
+    float* xs = sw + w_floats;
+    float* zs = xs + PASS_ROWS * dp_max;
+    const int lane = threadIdx.x;
+    const int64_t row = (int64_t)blockIdx.x * PASS_ROWS + lane;
+    const bool live = row < n;
+    const int2 grp = groups[blockIdx.y];
+    bool bad = false;
+    for (int k = grp.x; k < grp.x + grp.y; ++k) {
+        __syncwarp();                                  // previous clique: every lane is done with the staged data
+        {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(items + k);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(&it);
+            for (int t = lane; t < (int)(sizeof(NfPassItem) / 4); t += PASS_ROWS) dst[t] = src[t];
+        }
+        __syncwarp();
+        const int d = it.d, sep = it.sep, f = d - sep, dp = d | 1;
+        const bool has_norm = it.mean != nullptr;
+        {
+            const float4* src = reinterpret_cast<const float4*>(it.pk + it.w_first);
+            float4* dst = reinterpret_cast<float4*>(sw);
+            for (int t = lane; t < it.wcount / 4; t += PASS_ROWS) dst[t] = src[t];
+        }
+        if (has_norm && lane < d) {
+            s_mean[lane] = it.mean[lane];
+            s_std[lane] = it.stdv[lane];
+            s_circ[lane] = it.circ[lane];
+        }
+        float* xrow = xs + lane * dp;
+        float* zrow = zs + lane * dp;
+        if (live) {
+            for (int c = 0; c < sep; ++c) {
+                const int col = it.sep_cols[c];
+                xrow[c] = col >= 0 ? s_mat[row * ld_s + col] : it.sep_const[c];
+            }
+            for (int c = 0; c < f; ++c) zrow[c] = zin[row * ld_z + it.z_col0 + c];
+        }
+        __syncwarp();
+        if (live) {
+            if (has_norm) {
+                for (int c = 0; c < sep; ++c) {
+                    float v = xrow[c] - s_mean[c];
+                    if (s_circ[c]) v = nf_wrap_pipi(v);
+                    xrow[c] = v / s_std[c];
+                }
+            }
+            const float* wbase = sw - it.w_first;      // conditioner i sits at wbase + nf_block_off(i); only i >= sep is touched
+            for (int i = sep; i < d; ++i) {
+                float ld;
+                xrow[i] = nf_inverse_dim<K, H>(wbase, i, xrow, B, zrow[i - sep], ld, bad);
+            }
+            for (int c = 0; c < f; ++c) {
+                float v = xrow[sep + c];
+                if (has_norm) {
+                    v = fmaf(v, s_std[sep + c], s_mean[sep + c]);
+                    if (s_circ[sep + c]) v = nf_wrap_pipi(v);
+                }
+                s_mat[row * ld_s + it.out_cols[c]] = v;
+            }
+        }
+    }
+    if (bad && bad_count) atomicAdd(bad_count, 1ULL);
 }
 
 template <typename KernelT>
@@ -193,7 +280,8 @@ int launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, cons
                    int out_dim, float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ,
                    unsigned long long* bad, const NfGather& ga, int device, cudaStream_t st) {
     const int d_end = sep + out_dim;
-    const int wcount = nf_block_off(d_end, H, fd.Pp);
+    const int w_first = nf_block_off(sep, H, fd.Pp);
+    const int wcount = nf_block_off(d_end, H, fd.Pp) - w_first;
     const int dp = d_end | 1;
     const size_t smem = sizeof(float) * ((size_t)wcount + 2 * (size_t)TPB * dp);
     auto kern = nf_inverse_kernel<K, H, GATHER>;
@@ -203,7 +291,7 @@ int launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, cons
     }
     const int64_t tiles = (n + TPB - 1) / TPB;
     const int grid = grid_for(kern, smem, tiles, device);
-    kern<<<grid, TPB, smem, st>>>(pk, wcount, d_end, sep, fd.B, zin, xsep, n, xout, logdet, mean, stdv, circ, bad, ga);
+    kern<<<grid, TPB, smem, st>>>(pk, w_first, wcount, d_end, sep, fd.B, zin, xsep, n, xout, logdet, mean, stdv, circ, bad, ga);
     nf_count_launch();
     return nf_check_launch("nf_inverse_kernel");
 }
@@ -248,6 +336,29 @@ int nf_launch_inverse_gather(const NfFlowDims& fd, const float* pk, const float*
     if (fd.K == KK && fd.H == HH) \
         return launch_inverse<KK, HH, true>(fd, pk, z, nullptr, n, sep, out_dim, s_mat, nullptr, mean, stdv, circ, bad, ga, \
                                             device, st);
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
+}
+
+int nf_launch_posterior_pass(const NfFlowDims& fd, const NfPassItem* items_dev, const int2* groups_dev, int n_groups,
+                             int max_wcount, int max_d, const float* z, int ld_z, float* s_mat, int ld_s, int64_t n,
+                             unsigned long long* bad, int device, cudaStream_t st) {
+    if (n == 0 || n_groups == 0) return NF_OK;
+    const int dp_max = max_d | 1;
+    const int w_floats = (max_wcount + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)w_floats + 2 * (size_t)PASS_ROWS * dp_max);
+    const dim3 grid((unsigned)((n + PASS_ROWS - 1) / PASS_ROWS), (unsigned)n_groups);
+#define NF_CASE(KK, HH)                                                                                                    \
+    if (fd.K == KK && fd.H == HH) {                                                                                        \
+        auto kern = nf_posterior_pass_kernel<KK, HH>;                                                                      \
+        if (smem > 40 * 1024 &&                                                                                            \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)             \
+            return nf_set_error(NF_ERR_UNSUPPORTED, "flows do not fit in shared memory");                                  \
+        kern<<<grid, PASS_ROWS, smem, st>>>(items_dev, groups_dev, fd.B, z, ld_z, s_mat, ld_s, n, bad, w_floats, dp_max);  \
+        nf_count_launch();                                                                                                 \
+        return nf_check_launch("nf_posterior_pass_kernel");                                                                \
+    }
     NF_FOREACH_KH(NF_CASE)
 #undef NF_CASE
     return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");

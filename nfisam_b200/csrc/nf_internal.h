@@ -91,6 +91,22 @@ int nf_launch_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const 
 int nf_launch_mixture_weights(const nf_factor_desc* descs_dev, int n_desc, const double* x, int64_t n, int D,
                               double* partial_dev, int* n_partial, int device, cudaStream_t st);
 
+// one clique of the fused posterior down-pass (device-resident array, nf_flow_kernels.cu)
+struct NfPassItem {
+    const float* pk;        // packed parameters of the clique's flow
+    const float* mean;      // normalisation constants (NULL: none)
+    const float* stdv;
+    const uint8_t* circ;
+    int w_first, wcount;    // packed floats [w_first, w_first + wcount): the conditioners of dims sep .. d-1
+    int d, sep, z_col0, pad_;
+    int sep_cols[NF_MAX_DIM];
+    float sep_const[NF_MAX_DIM];
+    int out_cols[NF_MAX_DIM];
+};
+int nf_launch_posterior_pass(const NfFlowDims& fd, const NfPassItem* items_dev, const int2* groups_dev, int n_groups,
+                             int max_wcount, int max_d, const float* z, int ld_z, float* s_mat, int ld_s, int64_t n,
+                             unsigned long long* bad, int device, cudaStream_t st);
+
 // nf_sim_kernels.cu
 int nf_launch_simulate(const nf_sim_op* ops, int n_ops, uint64_t seed, double* s_mat, int64_t n, int ld, cudaStream_t st);
 int nf_launch_sim_noise(uint64_t seed, int slot, int normal, double* out, int64_t n, cudaStream_t st);

@@ -430,3 +430,31 @@ class NSF_AR(nn.Module):
 
 
 LOG_2PI = math.log(2.0 * math.pi)
+
+
+def posterior_pass(items, z_dev, s_dev, counter=None):
+    """The whole posterior down-pass in one call (nfisam_posterior_pass): `items` is a root-to-leaf list of
+    (flow, z_col0, sep_cols, sep_const, out_cols, norm) tuples with the meaning of NSF_AR.inverse_gather; the frontal
+    blocks of all cliques are written into the device sample matrix s_dev.  Replaces the per-clique loop of
+    FactorGraphSolver.sample_posterior (src/slam/FactorGraphSolver.py:497-550).  No synchronisation."""
+    lib = _lib.load()
+    arr = (_lib.nf_gather_item * max(len(items), 1))()
+    keep = []
+    for it, (flow, z_col0, sep_cols, sep_const, out_cols, norm) in zip(arr, items):
+        sep, out = len(sep_cols), len(out_cols)
+        sc = (ctypes.c_int32 * max(sep, 1))(*[int(c) for c in sep_cols])
+        sk = (ctypes.c_float * max(sep, 1))(*[float(c) for c in sep_const])
+        oc = (ctypes.c_int32 * max(out, 1))(*[int(c) for c in out_cols])
+        keep.append((sc, sk, oc))
+        it.flow = flow.handle()
+        it.z_col0, it.sep_dim, it.out_dim = int(z_col0), sep, out
+        it.sep_cols_host = ctypes.addressof(sc)
+        it.sep_const_host = ctypes.addressof(sk)
+        it.out_cols_host = ctypes.addressof(oc)
+        if norm is not None:
+            it.norm = flow._affine(norm)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(s_dev.device).cuda_stream)
+    _lib.check(lib.nfisam_posterior_pass(arr, len(items), z_dev.data_ptr(), int(z_dev.shape[1]), s_dev.data_ptr(),
+                                         int(s_dev.shape[1]), int(s_dev.shape[0]),
+                                         counter.data_ptr() if counter is not None else None, stream))
+

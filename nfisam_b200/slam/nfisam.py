@@ -53,7 +53,7 @@ class NFiSAMArgs(SolverArgs):
                  average_window=50, loss_delta_tol=1e-2, training_set_frac=1.0, validation_interval=10,
                  slower_stop_rate=2.0, data_parallel=False, training_loss_dir=None,
                  clique_parallel: bool = True, deterministic_cliques: bool = False, seed: int = 0, device=None,
-                 device_simulation: bool = True, *args, **kwargs):
+                 device_simulation: bool = True, device_latents: bool = True, *args, **kwargs):
         super().__init__(elimination_method=elimination_method, posterior_sample_num=posterior_sample_num,
                          local_sample_num=local_sample_num, store_clique_samples=store_clique_samples,
                          local_sampling_method=local_sampling_method, *args, **kwargs)
@@ -81,6 +81,8 @@ class NFiSAMArgs(SolverArgs):
         self.seed = seed
         self.device = device
         self.device_simulation = device_simulation          # build clique training sets with the simulator kernel
+        self.device_latents = device_latents                # posterior latent draws from the device generator (False:
+        #                                                     torch's CPU generator, clique by clique like the reference)
 
 
 class NormalizingFlowModelWithSeparator(NormalizingFlowModel, ConditionalSampler):

@@ -18,6 +18,7 @@ parameters up and separator samples down, as the north star prescribes.  With
 `deterministic_cliques` every clique seeds its own RNG streams from (seed, step, clique name), which
 makes the result independent of the number of GPUs.
 """
+import ctypes
 import time
 import zlib
 from typing import List
@@ -25,6 +26,7 @@ from typing import List
 import numpy as np
 import torch
 
+from .. import _lib
 from .simulation_sampler import SimulationBasedSampler
 
 
@@ -198,11 +200,12 @@ class CliqueScheduler:
     # -- down-pass: device-resident -------------------------------------------------------------------
     def sample_posterior_device(self, timer: List[float] = None, seeded: bool = False):
         """Root -> leaves like FactorGraphSolver.sample_posterior (src/slam/FactorGraphSolver.py:497-550): same
-        clique order and CPU latent draws (global torch RNG, or one generator per clique when `seeded`), but the
-        separator samples never leave the GPU: one H2D copy of all latent draws, one inverse kernel per clique
-        reading / writing device tensors, one D2H copy of all variables, one discriminant check for the pass.
-        Under torch.distributed (NCCL) a clique is sampled by its owner rank and its frontal samples are broadcast
-        device-to-device to the other ranks (the separator samples of its children)."""
+        clique order, but the separator samples never leave the GPU: latent draws from the device generator (or, with
+        `device_latents=False`, torch's CPU generator clique by clique like the reference, one upload), ONE call
+        (nfisam_posterior_pass) that enqueues one inverse kernel per clique reading / writing a device sample matrix,
+        one D2H copy of all variables, one discriminant check for the pass.  The per-clique index lists are cached
+        across incremental steps (variables keep their columns).  Under torch.distributed (NCCL) whole subtrees are
+        sampled by their owner rank and one all-reduce assembles the matrix."""
         import torch.distributed as dist
 
         s = self.solver
@@ -229,58 +232,87 @@ class CliqueScheduler:
                 owner_of[id(c)] = k % world
                 stack2.extend(c.children)
         owners = [owner_of[id(c)] for c in order]
-        # latent draws on the host, in clique order (RNG parity with the serial loop), one upload
-        spans, zs, width = [], [], 0
-        if seeded:
-            # one generator per step: every rank draws the same (n, total) latent matrix and a clique uses its own
-            # columns, so the draws do not depend on which rank owns the clique (nor on the number of ranks)
-            for clique in order:
-                spans.append((width, clique.frontal_dim))
-                width += clique.frontal_dim
-            gen = torch.Generator()
-            gen.manual_seed((7919 * s._step_counter + 104729 * 2 + int(s._args.seed)) % (2 ** 31 - 1))
-            zall = torch.randn((n, max(width, 1)), dtype=torch.float32, generator=gen).pin_memory()
-        else:
-            for clique, owner in zip(order, owners):
-                model = s._clique_density_model[clique]
-                w = clique.frontal_dim
-                obs_dim = len(s._clique_true_obs[clique]) + clique.separator_dim
-                zs.append(model.draw_latent(n, obs_dim, w))      # the reference's RNG consumption, clique by clique
-                spans.append((width, w))
-                width += w
-            zall = torch.empty((n, max(width, 1)), dtype=torch.float32).pin_memory()
-            for z, (off, w) in zip(zs, spans):
-                zall[:, off:off + w] = z
-        zdev = zall.to(dev, non_blocking=True)
-        counter = torch.zeros(1, dtype=torch.int64, device=dev)
-        # one device matrix holds every variable; each clique's frontal block is a contiguous column range
-        col_of, total = {}, 0
+        rmap = s._reverse_ordering_map
+        frontals = [sorted(c.frontal, key=rmap.__getitem__) for c in order]
+        spans, width = [], 0
         for clique in order:
-            for v in sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v]):
-                col_of[v] = total
-                total += v.dim
-        S = torch.zeros((n, total), dtype=torch.float32, device=dev)
-        for clique, owner, (off, w) in zip(order, owners, spans):
-            frontal = sorted(clique.frontal, key=lambda v: s._reverse_ordering_map[v])
-            separator = sorted(clique.separator, key=lambda v: s._reverse_ordering_map[v])
-            out_cols = [col_of[v] + k for v in frontal for k in range(v.dim)]
-            if owner == rank or owner < 0:
-                model = s._clique_density_model[clique]
+            spans.append((width, clique.frontal_dim))
+            width += clique.frontal_dim
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        lib = _lib.load()
+        if seeded or getattr(s._args, "device_latents", False):
+            # latent draws from the device generator (Philox keyed by a seed; slot = latent column pair): one launch, no
+            # upload.  Seeded: one seed per step, every rank generates the same (n, total) matrix and a clique uses its
+            # own columns, so the draws do not depend on which rank owns the clique (nor on the number of ranks).
+            if seeded:
+                z_seed = (7919 * s._step_counter + 104729 * 2 + int(s._args.seed)) % (2 ** 31 - 1)
+            else:
+                z_seed = int(np.random.randint(0, 2 ** 31 - 1))
+            zdev = torch.empty((n, max(width, 1)), dtype=torch.float32, device=dev)
+            _lib.check(lib.nfisam_randn_f32(ctypes.c_uint64(z_seed), 0, zdev.data_ptr(), n, width, max(width, 1), dev_index, stream))
+        else:
+            # latent draws on the host, in clique order (the reference's RNG consumption, clique by clique), one upload
+            zall = torch.empty((n, max(width, 1)), dtype=torch.float32).pin_memory()
+            for clique, (off, w) in zip(order, spans):
+                obs_dim = len(s._clique_true_obs[clique]) + clique.separator_dim
+                zall[:, off:off + w] = s._clique_density_model[clique].draw_latent(n, obs_dim, w)
+            zdev = zall.to(dev, non_blocking=True)
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        # one device matrix holds every variable.  A variable keeps its columns for the life of the solver, so the
+        # per-clique index lists below can be cached across incremental steps.
+        col_of = self.__dict__.setdefault("_posterior_cols", {})
+        for frontal in frontals:
+            for v in frontal:
+                if v not in col_of:
+                    col_of[v] = self.__dict__.get("_posterior_total", 0)
+                    self._posterior_total = col_of[v] + v.dim
+        total = self.__dict__.get("_posterior_total", 0)
+        S = torch.zeros((n, max(total, 1)), dtype=torch.float32, device=dev)
+        old_cache = self.__dict__.get("_gather_cache", {})
+        cache = {}
+        mine = [k for k, owner in enumerate(owners) if owner == rank or owner < 0]
+        items = (_lib.nf_gather_item * max(len(mine), 1))()
+        for slot, k in enumerate(mine):
+            clique, frontal = order[k], frontals[k]
+            model = s._clique_density_model[clique]
+            separator = sorted(clique.separator, key=rmap.__getitem__)
+            key = (id(model), tuple(map(id, frontal)), tuple(map(id, separator)))
+            entry = old_cache.get(id(model))
+            if entry is None or entry[0] != key:
                 obs = [float(o) for o in s._clique_true_obs[clique]]
-                sep_cols = [-1] * len(obs) + [col_of[v] + k for v in separator for k in range(v.dim)]
-                sep_const = obs + [0.0] * (len(sep_cols) - len(obs))
-                model.flows[0].inverse_gather(zdev, off, S, sep_cols, sep_const, out_cols, norm=model._norm(), counter=counter)
+                sep_cols = [-1] * len(obs) + [col_of[v] + j for v in separator for j in range(v.dim)]
+                out_cols = [col_of[v] + j for v in frontal for j in range(v.dim)]
+                sc = (ctypes.c_int32 * max(len(sep_cols), 1))(*sep_cols)
+                sk = (ctypes.c_float * max(len(sep_cols), 1))(*(obs + [0.0] * (len(sep_cols) - len(obs))))
+                oc = (ctypes.c_int32 * len(out_cols))(*out_cols)
+                flow = model.flows[0]
+                norm = model._norm()
+                aff = flow._affine(norm)
+                keep = flow.__dict__["_norm_dev"][id(norm)]       # device copies of mean / std / circular: kept alive here
+                entry = (key, sc, sk, oc, len(sep_cols), len(out_cols), aff, keep, flow.handle(), model)
+            cache[id(model)] = entry
+            it = items[slot]
+            it.flow = entry[8]
+            it.z_col0, it.sep_dim, it.out_dim = spans[k][0], entry[4], entry[5]
+            it.sep_cols_host = ctypes.addressof(entry[1])
+            it.sep_const_host = ctypes.addressof(entry[2])
+            it.out_cols_host = ctypes.addressof(entry[3])
+            it.norm = entry[6]
+        self._gather_cache = cache
+        _lib.check(lib.nfisam_posterior_pass(items, len(mine), zdev.data_ptr(), int(zdev.shape[1]), S.data_ptr(), int(S.shape[1]), n,
+                                             counter.data_ptr(), stream))
         if world > 1:
             if rank != 0:     # the redundantly sampled root block is contributed by rank 0 only
-                root_cols = [col_of[v] + k for v in s._physical_bayes_tree.root.frontal for k in range(v.dim)]
-                S[:, min(root_cols):max(root_cols) + 1] = 0.0
+                root_cols = [col_of[v] + j for v in s._physical_bayes_tree.root.frontal for j in range(v.dim)]
+                S[:, root_cols] = 0.0
             dist.all_reduce(S, op=dist.ReduceOp.SUM)       # x + 0 + ... + 0 is exact: identical on every rank
             dist.all_reduce(counter, op=dist.ReduceOp.SUM)
         host = S.cpu().numpy()
         bad = int(counter.item())
         if bad:
             raise AssertionError(f"negative discriminant in the inverse spline for {bad} samples")   # src/flows/utils.py:133
-        samples = {v: host[:, c:c + v.dim] for v, c in col_of.items()}
+        samples = {v: host[:, col_of[v]:col_of[v] + v.dim] for frontal in frontals for v in frontal}
         if timer is not None:
             timer.append(time.time() - start)
         return samples

@@ -376,3 +376,79 @@ def test_validation_set_slower_stop_matches_reference_loop():
                                    validation_interval=10, slower_stop_rate=2.0)
     assert ran2 == rano
     assert np.allclose(hist2[:10], ho[:10], rtol=2e-5)
+
+
+def _random_clique_tree(seed, trunk, branches, depth, K=9, cross=False):
+    """A Bayes-tree-shaped list of posterior-pass items with randomly initialised flows: `trunk` cliques in a chain, then
+    `branches` chains of `depth` cliques below the last trunk clique.  Every clique has one constant observation column,
+    the 3 frontal columns of its parent (and 2 of its grandparent) as given columns, 3 frontal columns of its own."""
+    from nfisam_b200.flows import NSF_AR
+
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    items, cols, total, zoff = [], {}, 0, 0
+
+    def add(name, parent, grand):
+        nonlocal total, zoff
+        sep_cols, sep_const = [-1], [float(rng.normal())]
+        if parent is not None:
+            sep_cols += cols[parent]
+            sep_const += [0.0] * 3
+        if grand is not None:
+            sep_cols += cols[grand][:2]
+            sep_const += [0.0] * 2
+        d = len(sep_cols) + 3
+        flow = NSF_AR(dim=d, K=K, hidden_dim=8)
+        mean = rng.normal(size=d).astype(np.float32)
+        std = rng.uniform(0.5, 2.0, size=d).astype(np.float32)
+        circ = (rng.uniform(size=d) < 0.3).astype(np.uint8)
+        cols[name] = [total, total + 1, total + 2]
+        total += 3
+        items.append((flow, zoff, sep_cols, sep_const, cols[name], (mean, std, circ)))
+        zoff += 3
+
+    prev, prev2 = None, None
+    for t in range(trunk):
+        add(("t", t), prev, prev2)
+        prev, prev2 = ("t", t), prev
+    for b in range(branches):
+        p, g = prev, prev2
+        for k in range(depth):
+            add((b, k), p, g)
+            p, g = (b, k), p
+    if cross and branches >= 2:
+        # not a forest: the last clique of branch 1 also reads a column generated inside branch 0
+        flow, z0, sc, sk, oc, norm = items[-1]
+        sc = list(sc)
+        sc[-1] = cols[(0, depth - 1)][0]
+        items[-1] = (flow, z0, sc, sk, oc, norm)
+    return items, total, zoff
+
+
+@pytest.mark.parametrize("shape", [(3, 0, 0, False), (2, 3, 4, False), (0, 2, 3, False), (1, 3, 2, True)])
+@pytest.mark.parametrize("n", [1, 1000])
+def test_posterior_pass_equals_per_clique_launches(shape, n):
+    """nfisam_posterior_pass (trunk launch + concurrent subtree launch, warp = 32 rows walking its cliques) is
+    bit-identical to one nfisam_flow_inverse_gather per clique, for chains, branching trees, forests and for column
+    dependencies that are not a forest (per-item fallback)."""
+    from nfisam_b200.flows import posterior_pass
+
+    trunk, branches, depth, cross = shape
+    items, total, zw = _random_clique_tree(11, trunk, branches, depth, cross=cross)
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn((n, zw), generator=g).to(dev)
+    z[0, 0] = 7.5                                        # linear tail
+    a = torch.zeros((n, total), device=dev)
+    b = torch.zeros((n, total), device=dev)
+    ca = torch.zeros(1, dtype=torch.int64, device=dev)
+    cb = torch.zeros(1, dtype=torch.int64, device=dev)
+    for flow, z0, sc, sk, oc, norm in items:
+        flow.inverse_gather(z, z0, a, sc, sk, oc, norm=norm, counter=ca)
+    posterior_pass(items, z, b, counter=cb)
+    torch.cuda.synchronize()
+    assert int(ca.item()) == 0 and int(cb.item()) == 0
+    assert torch.isfinite(a).all()
+    assert float(a.abs().max()) > 0
+    assert torch.equal(a, b)
+

@@ -186,7 +186,7 @@ def test_device_resident_posterior_equals_host_loop():
     bit-identical samples to the reference-shaped host loop under the same torch seed."""
     from nfisam_b200.slam.solver import FactorGraphSolver
 
-    solver = solve("small_case1_da", flow_iterations=100)[-1][3]
+    solver = solve("small_case1_da", flow_iterations=100, device_latents=False)[-1][3]
     torch.manual_seed(5)
     a = FactorGraphSolver.sample_posterior(solver)
     torch.manual_seed(5)
