@@ -305,6 +305,21 @@ int nfisam_normalize_training(const double* s_dev, int64_t n_rows, int ld, const
                               const int32_t* cols_host, const uint8_t* circular_host, int d, float* data_dev,
                               float* mean_std_dev, int device, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Two-sample statistics of the parity report (src/utils/Statistics.py, float64)
+ * ---------------------------------------------------------------------------------------- */
+typedef enum nf_mmd_kind {
+    NF_MMD_BIASED = 0,          /* MMDb(X, Y, sigma), Statistics.py:68-84: sqrt(sum KXX / m^2 - 2 sum KXY / (m n) + sum KYY / n^2) */
+    NF_MMD_UNBIASED_SQ = 1,     /* MMDu2(X, Y, sigma), Statistics.py:46-66: diagonals of KXX, KYY skipped, m(m-1), n(n-1), no sqrt */
+    NF_MMD_UNBIASED_SQRT = 2    /* mmd(samples1, samples2, k_sigma2 = sigma^2), Statistics.py:13-44: sqrt of the above */
+} nf_mmd_kind;
+
+/* K(a, b) = exp(-|a - b|^2 / (2 sigma^2)).  x_dev (m, d), y_dev (n, d) row-major float64 on `device`.
+ * sums_host (may be NULL) receives sum KXX, sum KXY, sum KYY (diagonals excluded for the unbiased kinds).
+ * Replaces the dense n x n host matrices of the reference.  Synchronous (the result is a host scalar). */
+int nfisam_mmd(const double* x_dev, int64_t m, const double* y_dev, int64_t n, int d, double sigma, int kind,
+               double* result_host, double* sums_host, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

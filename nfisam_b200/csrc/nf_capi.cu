@@ -1,5 +1,6 @@
 // C ABI of libnfisam_b200 (see include/nfisam_b200.h): handles, parameter (de)serialisation between
 // the reference's state_dict order and the kernels' packed layout, stream plumbing.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -867,6 +868,42 @@ int nfisam_normalize_training(const double* s_dev, int64_t n_rows, int ld, const
     if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
     return nf_launch_normalize(s_dev, n_rows, ld, perm_dev, row0, cols_host, circular_host, d, data_dev, mean_std_dev,
                                (cudaStream_t)stream);
+}
+
+int nfisam_mmd(const double* x_dev, int64_t m, const double* y_dev, int64_t n, int d, double sigma, int kind,
+               double* result_host, double* sums_host, int device, void* stream) {
+    if (!x_dev || !y_dev || !result_host || m < 1 || n < 1 || d < 1 || !(sigma > 0.0) || kind < 0 || kind > 2)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    const bool unbiased = kind != NF_MMD_BIASED;
+    if (unbiased && (m < 2 || n < 2)) return nf_set_error(NF_ERR_BAD_ARG, "the unbiased estimators need two rows per set");
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t w_xx = nf_rbf_sum_workspace(m, m), w_xy = nf_rbf_sum_workspace(m, n), w_yy = nf_rbf_sum_workspace(n, n);
+    unsigned char* ws = nullptr;
+    NF_CUDA(cudaMalloc(&ws, w_xx + w_xy + w_yy + 3 * sizeof(double)));
+    double* p_xx = reinterpret_cast<double*>(ws);
+    double* p_xy = reinterpret_cast<double*>(ws + w_xx);
+    double* p_yy = reinterpret_cast<double*>(ws + w_xx + w_xy);
+    double* out = reinterpret_cast<double*>(ws + w_xx + w_xy + w_yy);
+    int rc = nf_launch_rbf_sum(x_dev, m, x_dev, m, d, sigma, unbiased ? 1 : 0, p_xx, out + 0, st);
+    if (rc == NF_OK) rc = nf_launch_rbf_sum(x_dev, m, y_dev, n, d, sigma, 0, p_xy, out + 1, st);
+    if (rc == NF_OK) rc = nf_launch_rbf_sum(y_dev, n, y_dev, n, d, sigma, unbiased ? 1 : 0, p_yy, out + 2, st);
+    double s[3] = {0.0, 0.0, 0.0};
+    cudaError_t e = cudaSuccess;
+    if (rc == NF_OK) {
+        e = cudaMemcpyAsync(s, out, sizeof(s), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(ws);
+    if (rc != NF_OK) return rc;
+    if (e != cudaSuccess) return nf_cuda_fail(e, "nfisam_mmd");
+    if (sums_host) { sums_host[0] = s[0]; sums_host[1] = s[1]; sums_host[2] = s[2]; }
+    const double dm = (double)m, dn = (double)n;
+    const double v = unbiased ? s[0] / (dm * (dm - 1.0)) - 2.0 * s[1] / (dm * dn) + s[2] / (dn * (dn - 1.0))
+                              : s[0] / (dm * dm) - 2.0 * s[1] / (dm * dn) + s[2] / (dn * dn);
+    *result_host = kind == NF_MMD_UNBIASED_SQ ? v : sqrt(v);     // sqrt of a negative estimate is NaN, like numpy's
+    return NF_OK;
 }
 
 }  // extern "C"

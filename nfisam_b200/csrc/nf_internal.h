@@ -113,3 +113,9 @@ int nf_launch_sim_noise(uint64_t seed, int slot, int normal, double* out, int64_
 int nf_launch_randn_f32(uint64_t seed, int slot0, float* out, int64_t n, int cols, int ld, cudaStream_t st);
 int nf_launch_normalize(const double* s_mat, int64_t n_rows, int ld, const int32_t* perm, int64_t row0, const int32_t* cols,
                         const uint8_t* circular, int d, float* data, float* mean_std, cudaStream_t st);
+
+// nf_stats_kernels.cu
+size_t nf_rbf_sum_workspace(int64_t m, int64_t n);
+int nf_launch_rbf_sum(const double* x, int64_t m, const double* y, int64_t n, int d, double sigma, int skip_diag,
+                      double* partial, double* out, cudaStream_t st);
+

@@ -1,0 +1,104 @@
+// Two-sample statistics of the parity report on the device ("next" row N4): Gaussian-kernel sums behind the
+// maximum-mean-discrepancy estimators.
+//
+// Reference behaviour restated here (file:line in the NF-iSAM checkout):
+//   mmd     (unbiased, sqrt, Gaussian pdf ratio)      src/utils/Statistics.py:13-44
+//   MMDu2   (unbiased squared estimator)              src/utils/Statistics.py:46-66
+//   MMDb    (biased estimator)                        src/utils/Statistics.py:68-84
+//
+// All three are built from  S(X, Y) = sum_i sum_j exp(-|x_i - y_j|^2 / (2 sigma^2))  (optionally without i == j).
+// The reference forms three dense n x n matrices on the host (sklearn pairwise distances + numpy exp); here a
+// block owns a tile of x rows (thread = row, staged column-major in shared memory) and sweeps a tile of y rows read
+// as shared-memory broadcasts; squared distances are accumulated from the differences in float64 (no |x|^2 + |y|^2
+// - 2 x.y cancellation), block partials are reduced in a fixed order by a second kernel: deterministic results.
+// Bound: FP64 pipe (2 d + ~30 FP64 instructions per pair); HBM traffic is O((m + n) d).
+#include "nf_internal.h"
+
+namespace {
+
+constexpr int XT = 128;      // x rows per block (threads)
+constexpr int YT = 64;       // y rows per block
+
+__global__ void __launch_bounds__(XT)
+nf_rbf_sum_kernel(const double* __restrict__ x, int64_t m, const double* __restrict__ y, int64_t n, int d, double neg_inv_2s2,
+                  int skip_diag, double* __restrict__ partial) {
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;                 // [d][XT]
+    double* ys = xs + (size_t)d * XT;  // [YT][d]
+    __shared__ double warp_sum[XT / 32];
+    const int64_t i0 = (int64_t)blockIdx.x * XT, j0 = (int64_t)blockIdx.y * YT;
+    const int nx = (int)min((int64_t)XT, m - i0), ny = (int)min((int64_t)YT, n - j0);
+    for (int t = threadIdx.x; t < nx * d; t += XT) {
+        const int r = t / d, c = t - r * d;
+        xs[c * XT + r] = x[i0 * d + t];
+    }
+    for (int t = threadIdx.x; t < ny * d; t += XT) ys[t] = y[j0 * d + t];
+    __syncthreads();
+    double acc = 0.0;
+    if (threadIdx.x < nx) {
+        const int64_t i = i0 + threadIdx.x;
+        for (int j = 0; j < ny; j += 2) {
+            // two y rows per step: independent accumulation chains
+            const double* ya = ys + j * d;
+            const bool two = j + 1 < ny;
+            const double* yb = two ? ya + d : ya;
+            double da = 0.0, db = 0.0;
+            for (int c = 0; c < d; ++c) {
+                const double xv = xs[c * XT + threadIdx.x];
+                const double ea = xv - ya[c], eb = xv - yb[c];
+                da = fma(ea, ea, da);
+                db = fma(eb, eb, db);
+            }
+            double ka = exp(da * neg_inv_2s2), kb = exp(db * neg_inv_2s2);
+            if (skip_diag && i == j0 + j) ka = 0.0;
+            if (!two || (skip_diag && i == j0 + j + 1)) kb = 0.0;
+            acc += ka + kb;
+        }
+    }
+    // fixed-order block reduction
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < XT / 32; ++w) s += warp_sum[w];
+        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// out[0] = sum of count partials, pairwise tree in a fixed order
+__global__ void __launch_bounds__(256)
+nf_sum_partials_kernel(const double* __restrict__ partial, int64_t count, double* __restrict__ out) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int64_t t = threadIdx.x; t < count; t += 256) acc += partial[t];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+
+}  // namespace
+
+size_t nf_rbf_sum_workspace(int64_t m, int64_t n) {
+    const int64_t gx = (m + XT - 1) / XT, gy = (n + YT - 1) / YT;
+    return (size_t)(gx * gy) * sizeof(double);
+}
+
+int nf_launch_rbf_sum(const double* x, int64_t m, const double* y, int64_t n, int d, double sigma, int skip_diag,
+                      double* partial, double* out, cudaStream_t st) {
+    const int64_t gx = (m + XT - 1) / XT, gy = (n + YT - 1) / YT;
+    if (gy > 65535) return nf_set_error(NF_ERR_UNSUPPORTED, "second sample set too large (more than %d rows)", 65535 * YT);
+    const size_t smem = sizeof(double) * (size_t)d * (XT + YT);
+    auto kern = nf_rbf_sum_kernel;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return nf_set_error(NF_ERR_UNSUPPORTED, "rows of %d columns do not fit in shared memory", d);
+    kern<<<dim3((unsigned)gx, (unsigned)gy), XT, smem, st>>>(x, m, y, n, d, -0.5 / (sigma * sigma), skip_diag, partial);
+    nf_count_launch();
+    nf_sum_partials_kernel<<<1, 256, 0, st>>>(partial, gx * gy, out);
+    nf_count_launch();
+    return nf_check_launch("nf_rbf_sum_kernel");
+}

@@ -24,11 +24,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def mmd_b(x, y, sigma):
-    """Biased MMD^2 estimate with an RBF kernel (reference: src/utils/Statistics.py:68-84)."""
-    def k(a, b):
-        d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2 * a @ b.T
-        return np.exp(-d2 / (2 * sigma * sigma))
-    return float(np.sqrt(max(k(x, x).mean() + k(y, y).mean() - 2 * k(x, y).mean(), 0.0)))
+    """Biased MMD estimate with an RBF kernel (reference: src/utils/Statistics.py:68-84), on the device (nfisam_mmd)."""
+    from nfisam_b200.utils import MMDb
+
+    v = MMDb(x, y, sigma)
+    return 0.0 if np.isnan(v) else float(v)
 
 
 def test_wrapper_matches_reference_outputs():
