@@ -175,6 +175,9 @@ typedef struct nf_train_cfg {
     int32_t validation_interval;
     float slower_stop_rate;
     int32_t reset_optimizer;    /* non-zero: zero Adam moments and step count first */
+    int32_t concurrency;        /* training runs the caller keeps in flight on this device (clique scheduler: cliques of
+                                 * one tree level).  >= 2 selects the two-blocks-per-SM build of the cluster kernel so
+                                 * that two runs share the SMs; results are bit-identical to the default (0 / 1). */
 } nf_train_cfg;
 
 /* data_dev (n, dim) normalised training rows (device).  loss_hist_host: max_iters floats (host),

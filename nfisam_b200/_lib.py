@@ -42,6 +42,7 @@ class nf_train_cfg(ctypes.Structure):
         ("validation_interval", ctypes.c_int32),
         ("slower_stop_rate", ctypes.c_float),
         ("reset_optimizer", ctypes.c_int32),
+        ("concurrency", ctypes.c_int32),
     ]
 
 

@@ -97,6 +97,17 @@ struct nf_flow {
     cudaStream_t streams[2] = {nullptr, nullptr};
     float* d_norm = nullptr;       // mean | std (2 * dim floats)
     uint8_t* d_circ = nullptr;
+    // memory: the fixed-size buffers above are carved from one pooled arena (nf_pool.cu); `last_op` completes after the
+    // last asynchronous operation enqueued on this handle and orders the reuse of its memory after destroy
+    void* arena = nullptr;
+    NfEventRef last_op;
+    bool need_sync = false;        // an event could not be recorded: destroy falls back to a device synchronisation
+    void touch(cudaStream_t st) {
+        last_op = nf_event_record(device, st);
+        if (!last_op) need_sync = true;
+    }
+    float* pooled(size_t bytes) { return static_cast<float*>(nf_pool_alloc(device, bytes)); }
+    void release(void* p) { nf_pool_free(device, p, last_op); }
 };
 
 // packed column of conditioner output p (reference order: K widths, K heights, K-1 derivatives):
@@ -174,22 +185,29 @@ int nfisam_flow_create(int dim, int K, int hidden, float tail_bound, int device,
     f->n_packed = nf_packed_size(dim, hidden, f->fd.Pp);
     build_index_map(f);
     DeviceGuard g(device);
-    cudaError_t e = cudaSuccess;
-    const size_t bytes = sizeof(float) * (size_t)f->n_packed;
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_pk, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_m, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_v, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_grad, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_bad, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_ctrl, 2 * sizeof(NfTrainCtrl));
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_norm, 2 * sizeof(float) * dim);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_circ, dim);
-    if (e == cudaSuccess) e = cudaMemset(f->d_pk, 0, bytes);
-    if (e == cudaSuccess) e = cudaMemset(f->d_m, 0, bytes);
-    if (e == cudaSuccess) e = cudaMemset(f->d_v, 0, bytes);
-    if (e == cudaSuccess) e = cudaMemset(f->d_bad, 0, sizeof(unsigned long long));
+    // one pooled arena: pk | m | v | grad | bad | ctrl | norm | circ, every piece 256-byte aligned
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t bytes = up(sizeof(float) * (size_t)f->n_packed);
+    const size_t total = 4 * bytes + up(sizeof(unsigned long long)) + up(2 * sizeof(NfTrainCtrl)) + up(2 * sizeof(float) * dim) + up((size_t)dim);
+    unsigned char* base = static_cast<unsigned char*>(nf_pool_alloc(device, total));
+    if (!base) {
+        delete f;
+        return nf_set_error(NF_ERR_OOM, "device allocation of %zu bytes failed", total);
+    }
+    f->arena = base;
+    f->d_pk = reinterpret_cast<float*>(base);
+    f->d_m = reinterpret_cast<float*>(base + bytes);
+    f->d_v = reinterpret_cast<float*>(base + 2 * bytes);
+    f->d_grad = reinterpret_cast<float*>(base + 3 * bytes);
+    unsigned char* q = base + 4 * bytes;
+    f->d_bad = reinterpret_cast<unsigned long long*>(q); q += up(sizeof(unsigned long long));
+    f->d_ctrl = reinterpret_cast<NfTrainCtrl*>(q); q += up(2 * sizeof(NfTrainCtrl));
+    f->d_norm = reinterpret_cast<float*>(q); q += up(2 * sizeof(float) * dim);
+    f->d_circ = q;
+    cudaError_t e = cudaMemsetAsync(base, 0, total, cudaStreamLegacy);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);     // zeros are in place before any stream uses the handle
     if (e != cudaSuccess) {
-        int rc = nf_cuda_fail(e, "flow_create allocation");
+        int rc = nf_cuda_fail(e, "flow_create initialisation");
         nfisam_flow_destroy(f);
         return rc;
     }
@@ -200,11 +218,11 @@ int nfisam_flow_create(int dim, int K, int hidden, float tail_bound, int device,
 int nfisam_flow_destroy(nf_flow_t* f) {
     if (!f) return NF_OK;
     DeviceGuard g(f->device);
-    cudaFree(f->d_pk); cudaFree(f->d_m); cudaFree(f->d_v); cudaFree(f->d_grad); cudaFree(f->d_bad);
-    cudaFree(f->d_loss_part); cudaFree(f->d_ctrl); cudaFree(f->d_norm); cudaFree(f->d_circ);
-    cudaFree(f->d_partials); cudaFree(f->d_loss_partials); cudaFree(f->d_val_part);
+    if (f->need_sync) cudaDeviceSynchronize();
+    f->release(f->arena);
+    f->release(f->d_loss_part); f->release(f->d_partials); f->release(f->d_loss_partials); f->release(f->d_val_part);
     for (int s = 0; s < 2; ++s) {
-        cudaFree(f->d_stage_in[s]); cudaFree(f->d_stage_aux[s]); cudaFree(f->d_stage_out[s]);
+        f->release(f->d_stage_in[s]); f->release(f->d_stage_aux[s]); f->release(f->d_stage_out[s]);
         if (f->streams[s]) cudaStreamDestroy(f->streams[s]);
     }
     cudaGetLastError();
@@ -255,16 +273,20 @@ int nfisam_flow_forward(nf_flow_t* f, const float* x_dev, int64_t n, int d_in, f
     if (layout != 0 && layout != 1) return nf_set_error(NF_ERR_BAD_ARG, "layout must be 0 or 1");
     if (layout == 1 && logdet_dev && !ws_dev) return nf_set_error(NF_ERR_BAD_ARG, "layout 1 with logdet needs ws_dev");
     DeviceGuard g(f->device);
-    return nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, z_dev, logdet_dev,
-                             nullptr, ws_dev, layout, f->device, (cudaStream_t)stream);
+    const int rc = nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, z_dev, logdet_dev,
+                                     nullptr, ws_dev, layout, f->device, (cudaStream_t)stream);
+    f->touch((cudaStream_t)stream);
+    return rc;
 }
 
 int nfisam_flow_log_prob(nf_flow_t* f, const float* x_dev, int64_t n, int d_in, float* logp_dev, void* stream) {
     if (!f || ((!x_dev || !logp_dev) && n > 0)) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
     if (n < 0 || d_in < 1 || d_in > f->fd.d) return nf_set_error(NF_ERR_BAD_ARG, "bad n / d_in");
     DeviceGuard g(f->device);
-    return nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, nullptr, nullptr,
-                             logp_dev, nullptr, 0, f->device, (cudaStream_t)stream);
+    const int rc = nf_launch_forward(f->fd, f->d_pk, x_dev, n, d_in, nullptr, nullptr,
+                                     logp_dev, nullptr, 0, f->device, (cudaStream_t)stream);
+    f->touch((cudaStream_t)stream);
+    return rc;
 }
 
 int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev, int64_t n, int sep_dim, int out_dim,
@@ -279,8 +301,10 @@ int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev
         mean = norm->mean_dev; stdv = norm->std_dev; circ = norm->circular_dev;
     }
     DeviceGuard g(f->device);
-    return nf_launch_inverse(f->fd, f->d_pk, z_dev, x_sep_dev, n, sep_dim, out_dim, x_out_dev, logdet_dev, mean, stdv, circ,
-                             f->d_bad_ext ? f->d_bad_ext : f->d_bad, f->device, (cudaStream_t)stream);
+    const int rc = nf_launch_inverse(f->fd, f->d_pk, z_dev, x_sep_dev, n, sep_dim, out_dim, x_out_dev, logdet_dev, mean, stdv, circ,
+                                     f->d_bad_ext ? f->d_bad_ext : f->d_bad, f->device, (cudaStream_t)stream);
+    f->touch((cudaStream_t)stream);
+    return rc;
 }
 
 int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z_col0, float* s_dev, int ld_s,
@@ -302,9 +326,11 @@ int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z
         mean = norm->mean_dev; stdv = norm->std_dev; circ = norm->circular_dev;
     }
     DeviceGuard g(f->device);
-    return nf_launch_inverse_gather(f->fd, f->d_pk, z_dev, ld_z, z_col0, s_dev, ld_s, sep_cols_host, sep_const_host, sep_dim,
-                                    out_cols_host, out_dim, n, mean, stdv, circ, f->d_bad_ext ? f->d_bad_ext : f->d_bad,
-                                    f->device, (cudaStream_t)stream);
+    const int rc = nf_launch_inverse_gather(f->fd, f->d_pk, z_dev, ld_z, z_col0, s_dev, ld_s, sep_cols_host, sep_const_host, sep_dim,
+                                            out_cols_host, out_dim, n, mean, stdv, circ, f->d_bad_ext ? f->d_bad_ext : f->d_bad,
+                                            f->device, (cudaStream_t)stream);
+    f->touch((cudaStream_t)stream);
+    return rc;
 }
 
 int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float* z_dev, int ld_z, float* s_dev, int ld_s,
@@ -456,6 +482,11 @@ int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float*
             rc = nf_launch_posterior_pass(f0->fd, d_items, d_groups + 1, (int)groups.size() - 1, max_wcount, max_d, z_dev, ld_z,
                                           s_dev, ld_s, n, bad_counter_dev, f0->device, st);
         cudaEventRecord(sg.done, st);
+        NfEventRef after = nf_event_record(f0->device, st);      // every flow of the pass is in use until here
+        for (int k = 0; k < n_items; ++k) {
+            items[k].flow->last_op = after;
+            if (!after) items[k].flow->need_sync = true;
+        }
         return rc;
     }
     for (int k = 0; k < n_items; ++k) {            // mixed flow shapes / not a forest: one launch per clique
@@ -496,14 +527,15 @@ static int ensure_streams(nf_flow* f) {
         if (!f->streams[s]) NF_CUDA(cudaStreamCreateWithFlags(&f->streams[s], cudaStreamNonBlocking));
     return NF_OK;
 }
-static int ensure_cap(float** bufs, size_t* cap, size_t want) {
+static int ensure_cap(nf_flow* f, float** bufs, size_t* cap, size_t want) {
     if (*cap >= want) return NF_OK;
     for (int s = 0; s < 2; ++s) {
-        cudaFree(bufs[s]);
+        f->release(bufs[s]);
         bufs[s] = nullptr;
     }
     *cap = 0;
-    for (int s = 0; s < 2; ++s) NF_CUDA(cudaMalloc(&bufs[s], want * sizeof(float)));
+    for (int s = 0; s < 2; ++s)
+        if (!(bufs[s] = f->pooled(want * sizeof(float)))) return nf_set_error(NF_ERR_OOM, "device allocation failed");
     *cap = want;
     return NF_OK;
 }
@@ -516,8 +548,8 @@ int nfisam_flow_log_prob_host(nf_flow_t* f, const float* x_host, int64_t n, int 
     int rc = ensure_streams(f);
     if (rc != NF_OK) return rc;
     const int64_t chunk = n < (1 << 20) ? (n + 1) / 2 > 0 ? (n + 1) / 2 : 1 : (1 << 20);
-    if ((rc = ensure_cap(f->d_stage_in, &f->stage_in_cap, (size_t)chunk * d_in)) != NF_OK) return rc;
-    if ((rc = ensure_cap(f->d_stage_out, &f->stage_out_cap, (size_t)chunk)) != NF_OK) return rc;
+    if ((rc = ensure_cap(f, f->d_stage_in, &f->stage_in_cap, (size_t)chunk * d_in)) != NF_OK) return rc;
+    if ((rc = ensure_cap(f, f->d_stage_out, &f->stage_out_cap, (size_t)chunk)) != NF_OK) return rc;
     int s = 0;
     for (int64_t o = 0; o < n; o += chunk, s ^= 1) {
         const int64_t m = n - o < chunk ? n - o : chunk;
@@ -553,9 +585,9 @@ int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_s
         NF_CUDA(cudaStreamSynchronize(f->streams[0]));
     }
     const int64_t chunk = n < (1 << 20) ? (n + 1) / 2 > 0 ? (n + 1) / 2 : 1 : (1 << 20);
-    if ((rc = ensure_cap(f->d_stage_in, &f->stage_in_cap, (size_t)chunk * d)) != NF_OK) return rc;
-    if ((rc = ensure_cap(f->d_stage_aux, &f->stage_aux_cap, (size_t)chunk * d)) != NF_OK) return rc;
-    if ((rc = ensure_cap(f->d_stage_out, &f->stage_out_cap, (size_t)chunk * d)) != NF_OK) return rc;
+    if ((rc = ensure_cap(f, f->d_stage_in, &f->stage_in_cap, (size_t)chunk * d)) != NF_OK) return rc;
+    if ((rc = ensure_cap(f, f->d_stage_aux, &f->stage_aux_cap, (size_t)chunk * d)) != NF_OK) return rc;
+    if ((rc = ensure_cap(f, f->d_stage_out, &f->stage_out_cap, (size_t)chunk * d)) != NF_OK) return rc;
     int s = 0;
     for (int64_t o = 0; o < n; o += chunk, s ^= 1) {
         const int64_t m = n - o < chunk ? n - o : chunk;
@@ -591,10 +623,9 @@ static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const n
         return nf_set_error(NF_ERR_BAD_ARG, "bad Adam hyper-parameters");
     const size_t need = nf_train_loss_part_elems(f->fd, cfg->max_iters);
     if (f->loss_part_cap < need) {
-        cudaFree(f->d_loss_part);
-        f->d_loss_part = nullptr;
+        f->release(f->d_loss_part);
         f->loss_part_cap = 0;
-        NF_CUDA(cudaMalloc(&f->d_loss_part, need * sizeof(float)));
+        if (!(f->d_loss_part = f->pooled(need * sizeof(float)))) return nf_set_error(NF_ERR_OOM, "device allocation failed");
         f->loss_part_cap = need;
     }
     if (cfg->reset_optimizer) {
@@ -616,6 +647,7 @@ static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const n
     a->slower_stop_rate = cfg->slower_stop_rate;
     a->step0 = f->adam_steps;
     a->grad_only = 0;
+    a->co_resident = cfg->concurrency >= 2 ? 1 : 0;
     a->grad_out = f->d_grad;
     a->loss_part = f->d_loss_part;
     a->ctrl = f->d_ctrl;
@@ -625,18 +657,18 @@ static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const n
         const int vi = cfg->validation_interval > 0 ? cfg->validation_interval : 1;
         const size_t vneed = ((size_t)cfg->max_iters / vi + 3) * (size_t)f->fd.d;
         if (f->val_part_cap < vneed) {
-            cudaFree(f->d_val_part);
-            f->d_val_part = nullptr;
+            f->release(f->d_val_part);
             f->val_part_cap = 0;
-            NF_CUDA(cudaMalloc(&f->d_val_part, vneed * sizeof(float)));
+            if (!(f->d_val_part = f->pooled(vneed * sizeof(float)))) return nf_set_error(NF_ERR_OOM, "device allocation failed");
             f->val_part_cap = vneed;
         }
         a->val_part = f->d_val_part;
     }
     if (n >= NF_TRAIN_PLAIN_MIN_N && cfg->n_val <= 0) {
         if (!f->d_partials) {
-            NF_CUDA(cudaMalloc(&f->d_partials, sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->n_packed));
-            NF_CUDA(cudaMalloc(&f->d_loss_partials, sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->fd.d));
+            f->d_partials = f->pooled(sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->n_packed);
+            f->d_loss_partials = f->pooled(sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->fd.d);
+            if (!f->d_partials || !f->d_loss_partials) return nf_set_error(NF_ERR_OOM, "device allocation failed");
         }
         a->partials = f->d_partials;
         a->loss_partials = f->d_loss_partials;
@@ -653,6 +685,7 @@ int nfisam_flow_train_launch(nf_flow_t* f, const float* data_dev, int64_t n, con
     int rc = fill_train_args(f, data_dev, n, cfg, &a, (cudaStream_t)stream);
     if (rc != NF_OK) return rc;
     rc = nf_launch_train(f->fd, a, f->device, (cudaStream_t)stream);
+    f->touch((cudaStream_t)stream);
     if (rc < 0) return rc;
     f->pending_launches = rc;
     f->pending_iters = cfg->max_iters;
@@ -786,8 +819,13 @@ int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_des
     nf_factor_desc* d_desc = nullptr;
     double* d_part = nullptr;
     int n_part = 1024;
-    NF_CUDA(cudaMallocAsync(&d_desc, sizeof(nf_factor_desc) * (size_t)n_desc, st));
-    NF_CUDA(cudaMallocAsync(&d_part, sizeof(double) * 16 * (size_t)n_part, st));
+    d_desc = static_cast<nf_factor_desc*>(nf_pool_alloc(device, sizeof(nf_factor_desc) * (size_t)n_desc));
+    d_part = static_cast<double*>(nf_pool_alloc(device, sizeof(double) * 16 * (size_t)n_part));
+    if (!d_desc || !d_part) {
+        nf_pool_free(device, d_desc, nullptr);
+        nf_pool_free(device, d_part, nullptr);
+        return nf_set_error(NF_ERR_OOM, "device allocation failed");
+    }
     NF_CUDA(cudaMemcpyAsync(d_desc, tmp.data(), sizeof(nf_factor_desc) * (size_t)n_desc, cudaMemcpyHostToDevice, st));
     rc = nf_launch_mixture_weights(d_desc, n_desc, x_dev, n, D, d_part, &n_part, device, st);
     std::vector<double> part((size_t)16 * n_part);
@@ -795,9 +833,12 @@ int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_des
         cudaError_t e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) rc = nf_cuda_fail(e, "partial download");
     }
-    cudaFreeAsync(d_desc, st);
-    cudaFreeAsync(d_part, st);
-    NF_CUDA(cudaStreamSynchronize(st));
+    {
+        cudaError_t e = cudaStreamSynchronize(st);
+        nf_pool_free(device, d_desc, nullptr);       // the stream is idle: reusable at once
+        nf_pool_free(device, d_part, nullptr);
+        if (e != cudaSuccess) return nf_cuda_fail(e, "cudaStreamSynchronize");
+    }
     if (rc != NF_OK) return rc;
     double total = 0.0;
     for (int c = 0; c < n_desc; ++c) {
@@ -880,8 +921,8 @@ int nfisam_mmd(const double* x_dev, int64_t m, const double* y_dev, int64_t n, i
     if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t w_xx = nf_rbf_sum_workspace(m, m), w_xy = nf_rbf_sum_workspace(m, n), w_yy = nf_rbf_sum_workspace(n, n);
-    unsigned char* ws = nullptr;
-    NF_CUDA(cudaMalloc(&ws, w_xx + w_xy + w_yy + 3 * sizeof(double)));
+    unsigned char* ws = static_cast<unsigned char*>(nf_pool_alloc(device, w_xx + w_xy + w_yy + 3 * sizeof(double)));
+    if (!ws) return nf_set_error(NF_ERR_OOM, "device allocation failed");
     double* p_xx = reinterpret_cast<double*>(ws);
     double* p_xy = reinterpret_cast<double*>(ws + w_xx);
     double* p_yy = reinterpret_cast<double*>(ws + w_xx + w_xy);
@@ -895,7 +936,8 @@ int nfisam_mmd(const double* x_dev, int64_t m, const double* y_dev, int64_t n, i
         e = cudaMemcpyAsync(s, out, sizeof(s), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
-    cudaFree(ws);
+    if (rc != NF_OK || e != cudaSuccess) cudaStreamSynchronize(st);
+    nf_pool_free(device, ws, nullptr);               // the stream has been synchronised: reusable at once
     if (rc != NF_OK) return rc;
     if (e != cudaSuccess) return nf_cuda_fail(e, "nfisam_mmd");
     if (sums_host) { sums_host[0] = s[0]; sums_host[1] = s[1]; sums_host[2] = s[2]; }

@@ -243,7 +243,8 @@ int nf_launch_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const 
     if (n_desc <= PARAMS_SMALL) return launch_params<PARAMS_SMALL>(descs_host, n_desc, x, n, D, out, per_factor, smem, device, st);
     if (n_desc <= PARAMS_LARGE) return launch_params<PARAMS_LARGE>(descs_host, n_desc, x, n, D, out, per_factor, smem, device, st);
     nf_factor_desc* d_desc = nullptr;
-    NF_CUDA(cudaMallocAsync(&d_desc, sizeof(nf_factor_desc) * (size_t)n_desc, st));
+    d_desc = static_cast<nf_factor_desc*>(nf_pool_alloc(device, sizeof(nf_factor_desc) * (size_t)n_desc));
+    if (!d_desc) return nf_set_error(NF_ERR_OOM, "device allocation failed");
     cudaError_t e = cudaMemcpyAsync(d_desc, descs_host, sizeof(nf_factor_desc) * (size_t)n_desc, cudaMemcpyHostToDevice, st);
     int rc = NF_OK;
     if (e == cudaSuccess) {
@@ -256,9 +257,10 @@ int nf_launch_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const 
             rc = nf_check_launch("nf_factor_logpdf_buf_kernel");
         }
     }
-    cudaFreeAsync(d_desc, st);
+    const cudaError_t es = cudaStreamSynchronize(st);      // descs_host may be pageable and short-lived
+    nf_pool_free(device, d_desc, nullptr);
     if (e != cudaSuccess) return nf_cuda_fail(e, "descriptor upload");
-    NF_CUDA(cudaStreamSynchronize(st));      // descs_host may be pageable and short-lived
+    if (es != cudaSuccess) return nf_cuda_fail(es, "cudaStreamSynchronize");
     return rc;
 }
 

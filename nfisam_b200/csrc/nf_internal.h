@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
+
 #include "../../include/nfisam_b200.h"
 #include "nf_common.cuh"
 
@@ -67,6 +69,7 @@ struct NfTrainArgs {
     int validation_interval;
     float slower_stop_rate;
     int step0;              // Adam steps already taken (bias correction continues from here)
+    int co_resident;        // 1: launch the two-blocks-per-SM build (several training runs share the device)
     int grad_only;          // 1: write the reduced gradient to grad_out (packed order), no update
     float* grad_out;        // packed-size buffer (grad_only)
     float* loss_part;       // (max_iters, d) per-dim loss contributions
@@ -118,4 +121,15 @@ int nf_launch_normalize(const double* s_mat, int64_t n_rows, int ld, const int32
 size_t nf_rbf_sum_workspace(int64_t m, int64_t n);
 int nf_launch_rbf_sum(const double* x, int64_t m, const double* y, int64_t n, int d, double sigma, int skip_diag,
                       double* partial, double* out, cudaStream_t st);
+
+// nf_pool.cu: cached device memory, reuse ordered by events instead of the device-wide synchronisation of cudaFree
+struct NfEvent {
+    cudaEvent_t ev = nullptr;
+    int device = -1;
+    ~NfEvent();
+};
+typedef std::shared_ptr<NfEvent> NfEventRef;
+NfEventRef nf_event_record(int device, cudaStream_t st);          // nullptr when the event could not be recorded
+void* nf_pool_alloc(int device, size_t bytes);                    // current device must be `device`; nullptr = out of memory
+void nf_pool_free(int device, void* p, NfEventRef after);         // reusable once `after` has completed (nullptr: at once)
 

@@ -606,6 +606,9 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         size_t smem = train_smem_bytes<K, H, W>(d - 1, C, mt);
         if (smem > 100 * 1024) { resident = 0; mt = 1; smem = train_smem_bytes<K, H, W>(d - 1, C, 1); }
         if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
+        // several runs in flight (clique scheduler): the <= 128-register build lets two blocks -- two cliques -- share an
+        // SM, which hides the latency chains of one run behind the other; same arithmetic, bit-identical results
+        if (a.co_resident && 2 * (smem + 1024) <= 227 * 1024) kern = kern_big;
         NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(C, d, 1);

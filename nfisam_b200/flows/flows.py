@@ -89,16 +89,27 @@ class NSF_AR(nn.Module):
             out += [((H, i), i), ((H,), i), ((H, H), H), ((H,), H), ((P, H), H), ((P,), H)]
         return out
 
+    _init_plans = {}
+
     def _draw_initial_parameters(self):
         """Same draws, in the same order, as constructing the reference module tree (src/flows/flows.py:51-63):
-        nn.Linear.reset_parameters for every conditioner layer, then reset_parameters() on init_param."""
-        shapes = self._shapes()
-        parts = [None]
-        for shape, fan_in in shapes[1:]:
-            bound = 1.0 / math.sqrt(fan_in)
-            parts.append(torch.empty(shape).uniform_(-bound, bound).numpy().ravel())
-        parts[0] = torch.empty(shapes[0][0]).uniform_(-0.5, 0.5).numpy().ravel()
-        return np.concatenate(parts).astype(np.float32)
+        nn.Linear.reset_parameters for every conditioner layer (U(+-1/sqrt(fan_in))), then reset_parameters() on
+        init_param (U(+-1/2)).  torch's CPU uniform_ consumes one 32-bit draw per element and maps it with
+        u * (to - from) + from, so ONE long U(0, 1) draw followed by that map (evaluated like the fused multiply-add
+        torch's kernel compiles to) reproduces the 6 (dim - 1) + 1 separate calls bit for bit, ~30x faster."""
+        key = (self.dim, self.K, self.hidden_dim)
+        plan = NSF_AR._init_plans.get(key)
+        if plan is None:
+            shapes = self._shapes()
+            sizes = [int(np.prod(shape)) for shape, _ in shapes]
+            bound = np.concatenate([np.full(sz, np.float32(1.0 / math.sqrt(fan_in)), np.float64)
+                                    for (_, fan_in), sz in zip(shapes[1:], sizes[1:])] + [np.full(sizes[0], 0.5, np.float64)])
+            plan = (2.0 * bound, -bound, sizes[0])
+            NSF_AR._init_plans[key] = plan
+        scale, shift, p0 = plan
+        u = torch.empty(scale.size).uniform_(0.0, 1.0).numpy().astype(np.float64)
+        v = (u * scale + shift).astype(np.float32)          # exact product, one rounding: the fused multiply-add
+        return np.concatenate([v[-p0:], v[:-p0]])
 
     def reset_parameters(self):
         if self._materialized:
@@ -366,7 +377,7 @@ class NSF_AR(nn.Module):
 
     # ------------------------------------------------------------------ training on device
     def fit_launch(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
-                   reset_optimizer=True, stream=None, val=None, validation_interval=10, slower_stop_rate=2.0):
+                   reset_optimizer=True, stream=None, val=None, validation_interval=10, slower_stop_rate=2.0, concurrency=1):
         """Enqueue the whole Adam loop (src/slam/NFiSAM.py:451-491) on `stream` (a torch.cuda.Stream, default:
         the current one) and return immediately; several flows launched on different streams / devices train
         concurrently.  Call fit_finish() to collect the loss history."""
@@ -385,7 +396,7 @@ class NSF_AR(nn.Module):
         cfg = _lib.nf_train_cfg(int(iters), float(lr), float(betas[0]), float(betas[1]), float(eps),
                                 int(average_window), float(loss_delta_tol), vd.data_ptr() if vd is not None else None,
                                 int(vd.shape[0]) if vd is not None else 0, int(validation_interval), float(slower_stop_rate),
-                                1 if reset_optimizer else 0)
+                                1 if reset_optimizer else 0, int(concurrency))
         st = stream if stream is not None else torch.cuda.current_stream(self._dev())
         if stream is not None:
             stream.wait_stream(torch.cuda.current_stream(self._dev()))   # data upload happened on the current stream

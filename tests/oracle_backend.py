@@ -74,7 +74,7 @@ def oracle_backend():
         return torch.from_numpy(out), (torch.from_numpy(ld) if want_logdet else None)
 
     def fit_launch(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
-                   reset_optimizer=True, stream=None, val=None, validation_interval=10, slower_stop_rate=2.0):
+                   reset_optimizer=True, stream=None, val=None, validation_interval=10, slower_stop_rate=2.0, concurrency=1):
         th, d, K, H, B = cfg(self)
         if val is not None and len(val):
             th2, hist, ran, _ = orc.train_val(th, d, K, H, B, _np(data).astype(np.float32), _np(val).astype(np.float32), iters, lr,
