@@ -123,6 +123,31 @@ def main():
             print(json.dumps({"bench": "factor", "case": name, "D": D, "n": n, "ms": t * 1e3, "evals_per_s": n / t,
                               "hbm_gbs": gbs, "frac_hbm_peak": gbs / hbm, "l2_resident": n * D * 8 < 100e6}), flush=True)
 
+    # ---------------- posterior down-pass (S2): one nfisam_posterior_pass call over a clique tree
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_flow_gpu import _random_clique_tree
+
+    from nfisam_b200.flows import posterior_pass
+
+    for trunk, branches, depth in ((100, 0, 0), (1, 8, 63)):
+        items, total, zw = _random_clique_tree(11, trunk, branches, depth)
+        for n in (1000, 100_000):
+            z = torch.randn((n, zw), device=dev)
+            S = torch.zeros((n, total), device=dev)
+            t = timed(lambda: posterior_pass(items, z, S))
+            print(json.dumps({"bench": "posterior_pass", "cliques": len(items), "trunk": trunk, "branches": branches, "rows": n,
+                              "clique_dim": items[-1][0].dim, "ms": t * 1e3, "us_per_clique": t / len(items) * 1e6,
+                              "rows_x_cliques_per_s": n * len(items) / t}), flush=True)
+    # ---------------- two-sample statistics (N4): float64 Gaussian-kernel sums
+    from nfisam_b200.utils import MMDb
+
+    for m, d in ((1000, 22), (10_000, 22), (30_000, 12)):
+        xa = torch.randn((m, d), dtype=torch.float64, device=dev)
+        xb = torch.randn((m, d), dtype=torch.float64, device=dev) + 0.1
+        t = timed(lambda: MMDb(xa, xb, float(np.sqrt(d))))
+        print(json.dumps({"bench": "mmd", "m": m, "n": m, "d": d, "ms": t * 1e3, "pairs_per_s": 3.0 * m * m / t,
+                          "fp64_gflops": 3.0 * m * m * (3 * d + 30) / t * 1e-9}), flush=True)
+
 
 if __name__ == "__main__":
     main()

@@ -19,8 +19,11 @@ __device__ __forceinline__ void load_weights(float* sw, const float* __restrict_
 // mode bits
 constexpr int WANT_Z = 1, WANT_LD = 2, WANT_LP = 4, REF_LAYOUT = 8;
 
+#ifndef NF_FWD_MINB
+#define NF_FWD_MINB 8
+#endif
 template <int K, int H>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, NF_FWD_MINB)
 nf_forward_kernel(const float* __restrict__ pk, int wcount, int d_in, float B, const float* __restrict__ x, int64_t n,
                   float* __restrict__ z, float* __restrict__ logdet, float* __restrict__ logp, float* __restrict__ ws,
                   int mode) {
@@ -33,14 +36,21 @@ nf_forward_kernel(const float* __restrict__ pk, int wcount, int d_in, float B, c
     load_weights(sw, pk, wcount);
     const int64_t tiles = (n + TPB - 1) / TPB;
     const bool ref_layout = mode & REF_LAYOUT;
+    const int step_r = TPB / d_in, step_c = TPB - step_r * d_in;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t s0 = tile * TPB;
         const int cnt = (int)min((int64_t)TPB, n - s0);
         __syncthreads();                           // weights ready / previous tile drained
         const float* xg = x + s0 * d_in;
-        for (int t = threadIdx.x; t < cnt * d_in; t += TPB) {
-            const int r = t / d_in, c = t - r * d_in;
-            xs[r * dp + c] = xg[t];
+        {
+            // coalesced read of the row-major tile into padded rows; (row, column) advance incrementally (no division)
+            int r = threadIdx.x / d_in, c = threadIdx.x - r * d_in;
+            for (int t = threadIdx.x; t < cnt * d_in; t += TPB) {
+                xs[r * dp + c] = xg[t];
+                c += step_c;
+                r += step_r;
+                if (c >= d_in) { c -= d_in; ++r; }
+            }
         }
         __syncthreads();
         if (threadIdx.x < cnt) {
@@ -66,9 +76,12 @@ nf_forward_kernel(const float* __restrict__ pk, int wcount, int d_in, float B, c
         if (!ref_layout && (mode & WANT_Z)) {
             __syncthreads();
             float* zg = z + s0 * d_in;
+            int r = threadIdx.x / d_in, c = threadIdx.x - r * d_in;
             for (int t = threadIdx.x; t < cnt * d_in; t += TPB) {
-                const int r = t / d_in, c = t - r * d_in;
                 zg[t] = zs[r * dp + c];
+                c += step_c;
+                r += step_r;
+                if (c >= d_in) { c -= d_in; ++r; }
             }
         }
     }
@@ -171,75 +184,128 @@ nf_inverse_kernel(const float* __restrict__ pk, int w_first, int wcount, int d, 
 // ---------------------------------------------------------------------------------------------
 constexpr int PASS_ROWS = 32;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Software pipeline over the cliques of a group (ncu on the first version: 60 % of the warp's time was long-scoreboard
+// stall on serialised global loads): while clique k is inverted, the weights / normalisation constants of clique k+1
+// stream into the other half of a double buffer with cp.async, and the descriptor of clique k+1 was fetched while the
+// given columns of clique k were gathered (independent loads, eight in flight).  Exposed per clique: one L2 round trip.
 template <int K, int H>
 __global__ void __launch_bounds__(PASS_ROWS)
 nf_posterior_pass_kernel(const NfPassItem* __restrict__ items, const int2* __restrict__ groups, float B,
                          const float* __restrict__ zin, int ld_z, float* s_mat, int ld_s, int64_t n,
                          unsigned long long* __restrict__ bad_count, int w_floats, int dp_max) {
     extern __shared__ __align__(16) float smem[];
-    __shared__ NfPassItem it;
-    __shared__ float s_mean[NF_MAX_DIM], s_std[NF_MAX_DIM];
-    __shared__ int s_circ[NF_MAX_DIM];
-    float* sw = smem;
-    float* xs = sw + w_floats;
+    __shared__ __align__(16) NfPassItem its[2];
+    __shared__ float s_mean[2][NF_MAX_DIM], s_std[2][NF_MAX_DIM];
+    __shared__ int s_circ[2][NF_MAX_DIM];
+    static_assert(sizeof(NfPassItem) % 16 == 0, "descriptors are copied in 16-byte pieces");
+    float* xs = smem + 2 * w_floats;
     float* zs = xs + PASS_ROWS * dp_max;
     const int lane = threadIdx.x;
     const int64_t row = (int64_t)blockIdx.x * PASS_ROWS + lane;
     const bool live = row < n;
     const int2 grp = groups[blockIdx.y];
+    if (grp.y <= 0) return;
+    const int k_end = grp.x + grp.y;
+
+    auto stage_desc = [&](int k, int buf) {
+        const char* src = reinterpret_cast<const char*>(items + k);
+        char* dst = reinterpret_cast<char*>(&its[buf]);
+        for (int t = lane; t < (int)(sizeof(NfPassItem) / 16); t += PASS_ROWS) cp_async16(dst + 16 * t, src + 16 * t);
+    };
+    // weights of conditioners sep .. d-1 and the normalisation constants of the clique staged in its[buf]
+    auto stage_flow = [&](int buf, int& circ_reg) {
+        const float* src = its[buf].pk + its[buf].w_first;
+        float* dst = smem + buf * w_floats;
+        const int n4 = its[buf].wcount / 4;
+        for (int t = lane; t < n4; t += PASS_ROWS) cp_async16(dst + 4 * t, src + 4 * t);
+        if (its[buf].mean != nullptr && lane < its[buf].d) {
+            cp_async4(&s_mean[buf][lane], its[buf].mean + lane);
+            cp_async4(&s_std[buf][lane], its[buf].stdv + lane);
+            circ_reg = its[buf].circ[lane];
+        }
+    };
+
+    stage_desc(grp.x, 0);
+    cp_async_wait_all();
+    __syncwarp();
+    int circ_reg = 0;
+    stage_flow(0, circ_reg);
+    s_circ[0][lane] = circ_reg;
     bool bad = false;
-    for (int k = grp.x; k < grp.x + grp.y; ++k) {
-        __syncwarp();                                  // previous clique: every lane is done with the staged data
-        {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(items + k);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(&it);
-            for (int t = lane; t < (int)(sizeof(NfPassItem) / 4); t += PASS_ROWS) dst[t] = src[t];
-        }
-        __syncwarp();
-        const int d = it.d, sep = it.sep, f = d - sep, dp = d | 1;
+    for (int k = grp.x; k < k_end; ++k) {
+        const int cur = (k - grp.x) & 1, nxt = cur ^ 1;
+        const bool more = k + 1 < k_end;
+        if (more) stage_desc(k + 1, nxt);
+        const NfPassItem& it = its[cur];
+        const int d = it.d, sep = it.sep, f = d - sep, dp = d | 1, z0 = it.z_col0, w_first = it.w_first;
         const bool has_norm = it.mean != nullptr;
-        {
-            const float4* src = reinterpret_cast<const float4*>(it.pk + it.w_first);
-            float4* dst = reinterpret_cast<float4*>(sw);
-            for (int t = lane; t < it.wcount / 4; t += PASS_ROWS) dst[t] = src[t];
-        }
-        if (has_norm && lane < d) {
-            s_mean[lane] = it.mean[lane];
-            s_std[lane] = it.stdv[lane];
-            s_circ[lane] = it.circ[lane];
-        }
         float* xrow = xs + lane * dp;
         float* zrow = zs + lane * dp;
         if (live) {
-            for (int c = 0; c < sep; ++c) {
-                const int col = it.sep_cols[c];
-                xrow[c] = col >= 0 ? s_mat[row * ld_s + col] : it.sep_const[c];
+            const float* srow = s_mat + row * ld_s;
+            for (int c0 = 0; c0 < sep; c0 += 8) {
+                int col[8];
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) col[u] = c0 + u < sep ? it.sep_cols[c0 + u] : -1;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = col[u] >= 0 ? srow[col[u]] : (c0 + u < sep ? it.sep_const[c0 + u] : 0.0f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (c0 + u < sep) xrow[c0 + u] = v[u];
             }
-            for (int c = 0; c < f; ++c) zrow[c] = zin[row * ld_z + it.z_col0 + c];
+            const float* zr = zin + row * ld_z + z0;
+            for (int c0 = 0; c0 < f; c0 += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = c0 + u < f ? __ldg(zr + c0 + u) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (c0 + u < f) zrow[c0 + u] = v[u];
+            }
         }
+        cp_async_wait_all();                           // weights / constants of clique k, descriptor of clique k+1
         __syncwarp();
+        int circ_next = 0;
+        if (more) stage_flow(nxt, circ_next);          // in flight while clique k is inverted
         if (live) {
+            const float* mean = s_mean[cur];
+            const float* stdv = s_std[cur];
+            const int* circ = s_circ[cur];
             if (has_norm) {
                 for (int c = 0; c < sep; ++c) {
-                    float v = xrow[c] - s_mean[c];
-                    if (s_circ[c]) v = nf_wrap_pipi(v);
-                    xrow[c] = v / s_std[c];
+                    float v = xrow[c] - mean[c];
+                    if (circ[c]) v = nf_wrap_pipi(v);
+                    xrow[c] = v / stdv[c];
                 }
             }
-            const float* wbase = sw - it.w_first;      // conditioner i sits at wbase + nf_block_off(i); only i >= sep is touched
+            const float* wbase = smem + cur * w_floats - w_first;   // conditioner i sits at wbase + nf_block_off(i); only i >= sep is touched
             for (int i = sep; i < d; ++i) {
                 float ld;
                 xrow[i] = nf_inverse_dim<K, H>(wbase, i, xrow, B, zrow[i - sep], ld, bad);
             }
+            float* srow = s_mat + row * ld_s;
             for (int c = 0; c < f; ++c) {
                 float v = xrow[sep + c];
                 if (has_norm) {
-                    v = fmaf(v, s_std[sep + c], s_mean[sep + c]);
-                    if (s_circ[sep + c]) v = nf_wrap_pipi(v);
+                    v = fmaf(v, stdv[sep + c], mean[sep + c]);
+                    if (circ[sep + c]) v = nf_wrap_pipi(v);
                 }
-                s_mat[row * ld_s + it.out_cols[c]] = v;
+                srow[it.out_cols[c]] = v;
             }
         }
+        if (more) s_circ[nxt][lane] = circ_next;
+        __syncwarp();                                  // every lane is done with its[cur] / weights[cur] before they are refilled
     }
     if (bad && bad_count) atomicAdd(bad_count, 1ULL);
 }
@@ -258,7 +324,9 @@ int launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_
                    float* logp, float* ws, int mode, int device, cudaStream_t st) {
     const int wcount = nf_block_off(d_in, H, fd.Pp);
     const int dp = d_in | 1;
-    const size_t smem = sizeof(float) * ((size_t)wcount + 2 * (size_t)TPB * dp);
+    // the z staging tile only exists when z is written row-major: log-prob launches get one more block per SM
+    const bool z_tile = (mode & WANT_Z) && !(mode & REF_LAYOUT);
+    const size_t smem = sizeof(float) * ((size_t)wcount + (z_tile ? 2 : 1) * (size_t)TPB * dp);
     auto kern = nf_forward_kernel<K, H>;
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -347,7 +415,7 @@ int nf_launch_posterior_pass(const NfFlowDims& fd, const NfPassItem* items_dev, 
     if (n == 0 || n_groups == 0) return NF_OK;
     const int dp_max = max_d | 1;
     const int w_floats = (max_wcount + 3) & ~3;
-    const size_t smem = sizeof(float) * ((size_t)w_floats + 2 * (size_t)PASS_ROWS * dp_max);
+    const size_t smem = sizeof(float) * (2 * (size_t)w_floats + 2 * (size_t)PASS_ROWS * dp_max);
     const dim3 grid((unsigned)((n + PASS_ROWS - 1) / PASS_ROWS), (unsigned)n_groups);
 #define NF_CASE(KK, HH)                                                                                                    \
     if (fd.K == KK && fd.H == HH) {                                                                                        \

@@ -101,7 +101,7 @@ struct NfPassItem {
     const float* stdv;
     const uint8_t* circ;
     int w_first, wcount;    // packed floats [w_first, w_first + wcount): the conditioners of dims sep .. d-1
-    int d, sep, z_col0, pad_;
+    int d, sep, z_col0, pad_[3];   // sizeof is a multiple of 16 (cp.async pieces)
     int sep_cols[NF_MAX_DIM];
     float sep_const[NF_MAX_DIM];
     int out_cols[NF_MAX_DIM];

@@ -69,6 +69,19 @@ def main(tag="r1"):
         for r in rows:
             if r["bench"] == "factor":
                 md.append(f"| {r['case']} | {r['D']} | {r['n']:.0e} | {r['ms']:.3f} | {r['evals_per_s'] / 1e6:.0f} | {r['hbm_gbs']:.0f} | {r['frac_hbm_peak']:.3f} |")
+        pp = [r for r in rows if r["bench"] == "posterior_pass"]
+        if pp:
+            md += ["", "## Posterior down-pass (S2): one nfisam_posterior_pass call, clique dim 9 (6 given + 3 generated columns)", "",
+                   "| cliques | shape | rows | ms | us / clique | M row-cliques / s |", "|---|---|---|---|---|---|"]
+            for r in pp:
+                shape = "chain" if r["branches"] == 0 else f"{r['branches']} subtrees below a trunk of {r['trunk']}"
+                md.append(f"| {r['cliques']} | {shape} | {r['rows']} | {r['ms']:.3f} | {r['us_per_clique']:.2f} | {r['rows_x_cliques_per_s'] / 1e6:.1f} |")
+        mm = [r for r in rows if r["bench"] == "mmd"]
+        if mm:
+            md += ["", "## Two-sample statistics (N4): MMDb, float64", "", "| m = n | d | ms | G kernel evaluations / s | FP64 GFLOP/s (3 d + 30 per pair) |",
+                   "|---|---|---|---|---|"]
+            for r in mm:
+                md.append(f"| {r['m']} | {r['d']} | {r['ms']:.3f} | {r['pairs_per_s'] / 1e9:.1f} | {r['fp64_gflops']:.0f} |")
         md += [""]
     solves = sorted(glob.glob(os.path.join(OUT, "solve_*.json")))
     if solves:

@@ -25,7 +25,7 @@ from slam.NFiSAM import NFiSAM, NFiSAMArgs  # noqa: E402
 from slam.RunBatch import graph_file_parser, group_nodes_factors_incrementally  # noqa: E402
 from factors.Factors import BinaryFactorMixture  # noqa: E402
 
-ITERS = 600
+ITERS = int(os.environ.get("GOLDEN_ITERS", "600"))
 
 
 def run(case, seed=0):
