@@ -335,8 +335,9 @@ int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z
 
 int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float* z_dev, int ld_z, float* s_dev, int ld_s,
                           int64_t n, unsigned long long* bad_counter_dev, void* stream) {
-    if (n_items < 0 || (n_items > 0 && (!items || !z_dev || !s_dev)) || n < 0) return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
-    if (n_items == 0 || n == 0) return NF_OK;
+    if (n_items < 0 || n < 0) return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    if (n_items == 0 || n == 0) return NF_OK;            // nothing to draw (empty tensors have NULL data pointers)
+    if (!items || !z_dev || !s_dev) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
     bool uniform = true;      // one (K, hidden, tail bound) for every clique: the fused kernel applies
     int max_wcount = 0, max_d = 0;
     std::vector<NfPassItem> host((size_t)n_items);

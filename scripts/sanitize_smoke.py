@@ -38,6 +38,26 @@ def main():
         z = torch.randn(333, 6, device="cuda")
         f.inverse_gather(z, 1, S, [-1, 0], [0.3, 0.0], [4, 5], norm=(np.zeros(d, np.float32), np.ones(d, np.float32),
                                                                     np.zeros(d, np.uint8)))
+    # fused posterior pass (trunk + subtree launches), co-resident training build, MMD kernel sums
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_flow_gpu import _random_clique_tree
+
+    from nfisam_b200.flows import posterior_pass
+    from nfisam_b200.utils import MMDb, MMDu2
+
+    items, total, zw = _random_clique_tree(3, 2, 3, 3)
+    zz = torch.randn((333, zw), device="cuda")
+    SS = torch.zeros((333, total), device="cuda")
+    posterior_pass(items, zz, SS)
+    fl = [NSF_AR(dim=6, K=9, hidden_dim=8) for _ in range(3)]
+    streams = [torch.cuda.Stream() for _ in fl]
+    xd = torch.tensor(rng.standard_normal((700, 6)).astype(np.float32)).cuda()
+    for f, st in zip(fl, streams):
+        f.fit_launch(xd, 10, 0.01, average_window=5, stream=st, concurrency=3)
+    for f in fl:
+        f.fit_finish()
+    MMDb(rng.standard_normal((300, 5)), rng.standard_normal((257, 5)), 1.3)
+    MMDu2(rng.standard_normal((130, 22)), rng.standard_normal((64, 22)), 4.0)
     nodes, truth, factors = read_factor_graph_from_file(os.path.join(ROOT, "tests", "data", "small_case1_da.fg"))
     jf = JointFactor(factors, nodes)
     xx = np.concatenate([truth[v] for v in nodes]) + rng.standard_normal((500, 22)) * 0.3

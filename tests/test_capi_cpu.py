@@ -71,3 +71,21 @@ def test_no_cpu_fallback_in_flow_module():
     f = NSF_AR(dim=3, K=5, hidden_dim=8)
     with pytest.raises(Exception):
         f.forward(torch.zeros(2, 3))
+
+
+def test_no_cpu_fallback_in_statistics():
+    import torch
+
+    from nfisam_b200.utils import MMDb
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(Exception):
+        MMDb(np.zeros((4, 2)), np.ones((4, 2)), 1.0)
+
+
+def test_new_abi_structs_match_header(built_lib):
+    lib = built_lib.load()
+    assert ctypes.sizeof(built_lib.nf_gather_item) == lib.nfisam_struct_size(4)
+    assert ctypes.sizeof(built_lib.nf_train_cfg) == 64        # ... reset_optimizer, concurrency
+    assert lib.nfisam_struct_size(99) == -1

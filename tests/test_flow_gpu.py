@@ -486,3 +486,24 @@ def test_posterior_pass_equals_per_clique_launches(shape, n):
     assert float(a.abs().max()) > 0
     assert torch.equal(a, b)
 
+
+def test_posterior_pass_edge_cases():
+    """No rows / no cliques are no-ops; bad column lists fail loudly with a status code, nothing is launched."""
+    from nfisam_b200 import _lib
+    from nfisam_b200.flows import posterior_pass
+
+    items, total, zw = _random_clique_tree(5, 2, 0, 0)
+    dev = torch.device("cuda")
+    z = torch.randn((0, zw), device=dev)
+    S = torch.zeros((0, total), device=dev)
+    posterior_pass(items, z, S)                                    # n = 0
+    z = torch.randn((8, zw), device=dev)
+    S = torch.zeros((8, total), device=dev)
+    posterior_pass([], z, S)                                       # no cliques
+    assert float(S.abs().sum()) == 0.0
+    flow, z0, sc, sk, oc, norm = items[1]
+    with pytest.raises(_lib.NfisamError):
+        posterior_pass([items[0], (flow, z0, sc, sk, [total + 3, 1, 2], norm)], z, S)      # output column out of range
+    with pytest.raises(_lib.NfisamError):
+        posterior_pass([items[0], (flow, zw, sc, sk, oc, norm)], z, S)                     # latent columns out of range
+

@@ -142,6 +142,85 @@ def test_incremental_solve_matches_reference_posterior(case):
         assert np.all(np.abs(w - g[key]) < 0.2)
 
 
+def _step_distance(x, names, g, i, rows=500):
+    """(mean excess, std ratio, MMD_b) of our posterior x at step i against one stored reference run g: the statistics of
+    test_incremental_solve_matches_reference_posterior (means / stds only where the reference's marginal is concentrated)."""
+    ref = g[f"step{i}_samples"]
+    mr = g[f"step{i}_mean"] if f"step{i}_mean" in g else ref.mean(0)
+    sr = g[f"step{i}_std"] if f"step{i}_std" in g else ref.std(0)
+    m, s_ = x.mean(0), x.std(0)
+    col, excess, stdr, stdr_lm = 0, 0.0, 1.0, 1.0
+    for nm in names:
+        w = 2 if nm.startswith("L") else 3
+        sl = slice(col, col + w)
+        col += w
+        if np.all(sr[sl] < 5.0):
+            tol = (1.5 if nm.startswith("L") else 0.75) * sr[sl] + 0.5
+            excess = max(excess, float(np.max(np.abs(m[sl] - mr[sl]) / tol)))
+            r = s_[sl] / np.maximum(sr[sl], 1e-9)
+            worst = float(np.max(np.maximum(r, 1.0 / np.maximum(r, 1e-9))))
+            if nm.startswith("L"):
+                stdr_lm = max(stdr_lm, worst)
+            else:
+                stdr = max(stdr, worst)
+    k = min(rows, len(ref), len(x))
+    return excess, max(stdr, stdr_lm / 2.0), mmd_b(x[:k].astype(np.float64), ref[:k].astype(np.float64), np.sqrt(x.shape[1]))
+
+
+def test_100_pose_solve_matches_reference_posterior():
+    """BASELINE configs[3]: a 100-pose Manhattan-world range-SLAM graph (4 landmarks, 302 factors, 100 incremental steps)
+    solved by the reference (tests/golden/make_solve_golden.py, ~1 h of CPU) and by this solver; posteriors compared after
+    steps 25, 50, 75 and 100 with the bounds of test_incremental_solve_matches_reference_posterior (median over three
+    seeded runs of the distance to the closest stored reference run)."""
+    case = "manhattan_r1_p100"
+    path = os.path.join(HERE, "golden", f"solve_{case}.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden posterior not generated")
+    refs = [dict(np.load(path))]
+    alt = os.path.join(HERE, "golden", f"solve_{case}_seed1.npz")
+    if os.path.exists(alt):
+        refs.append(dict(np.load(alt)))
+    kept = [int(i) for i in refs[0]["kept_steps"]]
+    runs = [solve_seeded(case, seed, flow_iterations=500) for seed in (0, 1, 2)]
+    assert len(runs[0]) == 100
+    report = []
+    for i in kept:
+        names = runs[0][i][0]
+        assert names == list(refs[0][f"step{i}_order"])
+        solver_tree = None
+        if i == kept[-1]:
+            solver = runs[0][i][3]
+            solver_tree = sorted("".join(sorted(v.name for v in c.frontal)) + "|" + "".join(sorted(v.name for v in c.separator))
+                                 for c in solver.physical_bayes_tree.clique_nodes)
+            assert solver_tree == list(refs[0][f"step{i}_tree"])
+        stats = np.array([[min(_step_distance(run[i][1], names, g, i)[j] for g in refs) for j in range(3)] for run in runs])
+        med = np.median(stats, axis=0)
+        report.append([i + 1] + [round(float(v), 3) for v in med])
+        assert med[0] <= 1.0, (i, stats)
+        assert med[1] <= 3.0, (i, stats)
+        assert med[2] < 0.45, (i, stats)
+    truth = refs[0]["truth"]
+    names_all = [str(n) for n in refs[0]["names"]]
+    print(f"\n[{case}] step, mean excess (<= 1), std ratio (<= 3), joint MMD_b (< 0.45), medians of 3 runs:", report)
+    # absolute accuracy next to the reference's: mean pose error against the ground truth at the last step
+    last = kept[-1]
+    order = list(refs[0][f"step{last}_order"])
+    def pose_err(mean):
+        errs, col = [], 0
+        for nm in order:
+            w = 2 if nm.startswith("L") else 3
+            if not nm.startswith("L"):
+                k = names_all.index(nm)
+                off = sum(2 if n.startswith("L") else 3 for n in names_all[:k])
+                errs.append(np.linalg.norm(mean[col:col + 2] - truth[off:off + 2]))
+            col += w
+        return float(np.mean(errs))
+    ours = np.median([pose_err(run[last][1].mean(0)) for run in runs])
+    theirs = pose_err(refs[0][f"step{last}_mean"])
+    print(f"mean pose error vs ground truth after 100 steps: ours {ours:.2f}, reference {theirs:.2f}")
+    assert ours < 2.0 * theirs + 1.0
+
+
 def test_clique_parallel_equals_serial_loop_statistically():
     """Level-synchronous schedule on streams (device simulator) vs the serial reference-order loop (host simulator): same
     posterior up to the run-to-run spread (median of the per-variable means over three seeds each; the reference's own
