@@ -417,8 +417,13 @@ __device__ __forceinline__ void nf_outputs_wh(const float* __restrict__ wbase, i
     W3t = w + i * H + H + H * H + H;
     b3 = W3t + H * PP;
     nf_load_bias<PPW>(b3, out2w);
+#if defined(NF_EXP_SKIP_L3)
+    // timing experiment only (wrong results): upper bound of what moving the output layer off the FMA pipe could buy
+    out2w[0].x += h2[0] + h2[1] + h2[2] + h2[3] + h2[4] + h2[5] + h2[6] + h2[7];
+#else
 #pragma unroll
     for (int k = 0; k < H; ++k) nf_axpy_row<PPW>(W3t + k * PP, h2[k], out2w);
+#endif
 }
 
 // unnormalised derivative parameter ud_j of this sample: column 2K + j of the output layer

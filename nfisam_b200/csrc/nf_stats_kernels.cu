@@ -66,6 +66,69 @@ nf_rbf_sum_kernel(const double* __restrict__ x, int64_t m, const double* __restr
     }
 }
 
+// Wide rows (joint posteriors of 100+-pose graphs have 150-300 columns: the tiles above no longer fit in shared memory):
+// the columns are processed in chunks of DC; a thread holds its x chunk in registers, y chunks are shared-memory
+// broadcasts, partial squared distances of the 128 x 64 pair tile live in shared memory between chunks.
+constexpr int DC = 32;
+constexpr int XS = XT + 1;   // padded leading dimension of the x chunk: the transposing stores spread over the banks
+
+__global__ void __launch_bounds__(XT)
+nf_rbf_sum_wide_kernel(const double* __restrict__ x, int64_t m, const double* __restrict__ y, int64_t n, int d, double neg_inv_2s2,
+                       int skip_diag, double* __restrict__ partial) {
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;                      // [DC][XS]
+    double* ys = xs + DC * XS;            // [YT][DC] (DC * XS is even: 16-byte aligned rows)
+    double* dist = ys + YT * DC;          // [YT][XT]
+    __shared__ double warp_sum[XT / 32];
+    const int64_t i0 = (int64_t)blockIdx.x * XT, j0 = (int64_t)blockIdx.y * YT;
+    const int nx = (int)min((int64_t)XT, m - i0), ny = (int)min((int64_t)YT, n - j0);
+    for (int j = 0; j < YT; ++j) dist[j * XT + threadIdx.x] = 0.0;
+    for (int c0 = 0; c0 < d; c0 += DC) {
+        const int dc = min(DC, d - c0);
+        __syncthreads();                   // previous chunk consumed
+        for (int t = threadIdx.x; t < XT * DC; t += XT) {
+            const int r = t / DC, c = t - r * DC;
+            xs[c * XS + r] = (r < nx && c < dc) ? x[(i0 + r) * d + c0 + c] : 0.0;        // zero padding: no contribution
+        }
+        for (int t = threadIdx.x; t < YT * DC; t += XT) {
+            const int r = t / DC, c = t - r * DC;
+            ys[t] = (r < ny && c < dc) ? y[(j0 + r) * d + c0 + c] : 0.0;
+        }
+        __syncthreads();
+        double xr[DC];
+#pragma unroll
+        for (int c = 0; c < DC; ++c) xr[c] = xs[c * XS + threadIdx.x];
+        for (int j = 0; j < ny; ++j) {
+            const double* yr = ys + j * DC;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < DC; c += 2) {
+                const double e0 = xr[c] - yr[c], e1 = xr[c + 1] - yr[c + 1];
+                a0 = fma(e0, e0, a0);
+                a1 = fma(e1, e1, a1);
+            }
+            dist[j * XT + threadIdx.x] += a0 + a1;
+        }
+    }
+    double acc = 0.0;
+    if (threadIdx.x < nx) {
+        const int64_t i = i0 + threadIdx.x;
+        for (int j = 0; j < ny; ++j) {
+            double k = exp(dist[j * XT + threadIdx.x] * neg_inv_2s2);
+            if (skip_diag && i == j0 + j) k = 0.0;
+            acc += k;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < XT / 32; ++w) s += warp_sum[w];
+        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
 // out[0] = sum of count partials, pairwise tree in a fixed order
 __global__ void __launch_bounds__(256)
 nf_sum_partials_kernel(const double* __restrict__ partial, int64_t count, double* __restrict__ out) {
@@ -92,8 +155,10 @@ int nf_launch_rbf_sum(const double* x, int64_t m, const double* y, int64_t n, in
                       double* partial, double* out, cudaStream_t st) {
     const int64_t gx = (m + XT - 1) / XT, gy = (n + YT - 1) / YT;
     if (gy > 65535) return nf_set_error(NF_ERR_UNSUPPORTED, "second sample set too large (more than %d rows)", 65535 * YT);
-    const size_t smem = sizeof(double) * (size_t)d * (XT + YT);
-    auto kern = nf_rbf_sum_kernel;
+    size_t smem = sizeof(double) * (size_t)d * (XT + YT);
+    const bool wide = smem > 96 * 1024;              // more than 64 columns: column-chunked kernel
+    if (wide) smem = sizeof(double) * ((size_t)DC * XS + (size_t)YT * DC + (size_t)YT * XT);
+    auto kern = wide ? nf_rbf_sum_wide_kernel : nf_rbf_sum_kernel;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return nf_set_error(NF_ERR_UNSUPPORTED, "rows of %d columns do not fit in shared memory", d);
     kern<<<dim3((unsigned)gx, (unsigned)gy), XT, smem, st>>>(x, m, y, n, d, -0.5 / (sigma * sigma), skip_diag, partial);

@@ -24,7 +24,8 @@ def test_matches_reference_golden(case):
         assert mmd(x, y, sigma ** 2) == pytest.approx(float(G[f"{case}_mmd"]), rel=1e-9)
 
 
-@pytest.mark.parametrize("m,n,d", [(1, 1, 2), (2, 3, 5), (129, 64, 3), (1000, 777, 22), (3000, 2500, 12)])
+@pytest.mark.parametrize("m,n,d", [(1, 1, 2), (2, 3, 5), (129, 64, 3), (1000, 777, 22), (3000, 2500, 12), (400, 400, 64),
+                                   (400, 333, 65), (300, 500, 158), (257, 129, 308)])
 def test_kernel_sums_match_oracle(m, n, d):
     from nfisam_b200.utils.statistics import _mmd
 
@@ -37,7 +38,7 @@ def test_kernel_sums_match_oracle(m, n, d):
             continue
         val, sums = _mmd(x, y, sigma, kind, want_sums=True)
         ref = so.kernel_sums(x, y, sigma, skip)
-        np.testing.assert_allclose(sums, ref, rtol=1e-12)
+        np.testing.assert_allclose(sums, ref, rtol=1e-11)      # wide rows: column-chunked summation order
         want = so.MMDu2(x, y, sigma) if skip else so.MMDb(x, y, sigma)
         assert val == pytest.approx(want, rel=1e-9, abs=1e-13)
 
