@@ -179,6 +179,12 @@ __device__ __forceinline__ void nf_axpy_row(const float* __restrict__ wrow, floa
     }
 }
 
+// unroll factor of the first layer's input loop (runtime trip count i); 0 = the compiler's own choice (it unrolls by 4)
+#ifndef NF_L1_UNROLL
+#define NF_L1_UNROLL 0
+#endif
+constexpr int NF_L1_UNROLL_V = NF_L1_UNROLL;
+
 template <int H>
 __device__ __forceinline__ void nf_mlp_hidden(const float* __restrict__ w, int i, const float* __restrict__ xrow,
                                               float (&h1)[H], float (&h2)[H]) {
@@ -188,6 +194,9 @@ __device__ __forceinline__ void nf_mlp_hidden(const float* __restrict__ w, int i
     const float* b2 = W2t + H * H;
     float2 a[H / 2];
     nf_load_bias<H>(b1, a);
+#if NF_L1_UNROLL > 0
+#pragma unroll NF_L1_UNROLL_V
+#endif
     for (int k = 0; k < i; ++k) nf_axpy_row<H>(W1t + k * H, xrow[k], a);
 #pragma unroll
     for (int j = 0; j < H / 2; ++j) { const float2 t = nf_tanh2(a[j]); h1[2 * j] = t.x; h1[2 * j + 1] = t.y; }
@@ -399,6 +408,19 @@ struct NfLazy {
     static constexpr int PPW = ((2 * K) + 3) & ~3;       // width / height columns, padded to a float4 multiple
 };
 
+// one input's contribution to the 2K interleaved width / height columns.  When 2K is not a multiple of 4 the last float4
+// also holds the first two derivative columns: they are evaluated lazily (nf_ud_lazy), so their FFMA2 is not issued.
+template <int K>
+__device__ __forceinline__ void nf_axpy_row_wh(const float* __restrict__ wrow, float xv, float2 (&acc)[NfLazy<K>::PPW / 2]) {
+    const float2 xx = make_float2(xv, xv);
+#pragma unroll
+    for (int j = 0; j < 2 * K; j += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wrow + j);
+        acc[j / 2] = nf_fma2(make_float2(w4.x, w4.y), xx, acc[j / 2]);
+        if (j + 2 < 2 * K) acc[j / 2 + 1] = nf_fma2(make_float2(w4.z, w4.w), xx, acc[j / 2 + 1]);
+    }
+}
+
 // widths / heights part of the output layer: out2w[0..PPW/2) (entries >= K are derivative / padding columns)
 template <int K, int H>
 __device__ __forceinline__ void nf_outputs_wh(const float* __restrict__ wbase, int i, const float* __restrict__ xrow,
@@ -422,7 +444,7 @@ __device__ __forceinline__ void nf_outputs_wh(const float* __restrict__ wbase, i
     out2w[0].x += h2[0] + h2[1] + h2[2] + h2[3] + h2[4] + h2[5] + h2[6] + h2[7];
 #else
 #pragma unroll
-    for (int k = 0; k < H; ++k) nf_axpy_row<PPW>(W3t + k * PP, h2[k], out2w);
+    for (int k = 0; k < H; ++k) nf_axpy_row_wh<K>(W3t + k * PP, h2[k], out2w);
 #endif
 }
 
