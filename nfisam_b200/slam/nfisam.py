@@ -218,6 +218,9 @@ class FlowsPriorFactor(CliqueSeparatorFactor):
         return (plp + ld).numpy()
 
     def grad_x_log_pdf(self, x, **kwargs):
+        # The reference's own method cannot run (src/slam/NFiSAM.py:254-272): it marks the input as requiring grad and
+        # separator_forward then normalises it IN PLACE (NFiSAM.py:96-106, "a leaf Variable that requires grad is being
+        # used in an in-place operation"); its only callers are the NUTS / KSD baselines, which are out of scope.
         raise NotImplementedError("gradients w.r.t. flow inputs are only used by the reference's NUTS/KSD baselines "
                                   "(out of scope): the training loss needs no input gradient")
 
