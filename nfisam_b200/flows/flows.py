@@ -64,7 +64,8 @@ class NSF_AR(nn.Module):
     flow, more than a whole on-device training run of a clique.
     """
 
-    def __init__(self, dim, K=5, B=5.0, hidden_dim=8, base_network=FCNN, device=None, reference_layout=True):
+    def __init__(self, dim, K=5, B=5.0, hidden_dim=8, base_network=FCNN, device=None, reference_layout=True,
+                 initial_parameters=None):
         super().__init__()
         self.dim = dim
         self.K = K
@@ -74,13 +75,25 @@ class NSF_AR(nn.Module):
         self._base_network = base_network
         self._materialized = False
         self._flat_version = 0
-        self._theta = self._draw_initial_parameters()
+        if initial_parameters is None:
+            self._theta = self._draw_initial_parameters()
+        else:
+            # parameters received from another rank: no random draws (state_dict order, like load_flat_parameters)
+            self._theta = np.ascontiguousarray(initial_parameters, dtype=np.float32).ravel().copy()
+            if self._theta.size != NSF_AR.num_parameters(dim, K, hidden_dim):
+                raise ValueError(f"expected {NSF_AR.num_parameters(dim, K, hidden_dim)} parameters, got {self._theta.size}")
         self._device_index = device
         self._h = None
         self._synced = None
         self._pending = None
 
     # ------------------------------------------------------------------ parameters
+    @staticmethod
+    def num_parameters(dim, K, hidden_dim) -> int:
+        """Number of scalars in state_dict order (src/flows/flows.py:51-63): init_param + (dim - 1) conditioners."""
+        P, H = 3 * K - 1, hidden_dim
+        return P + sum(H * i + H + H * H + H + P * H + P for i in range(1, dim))
+
     def _shapes(self):
         """(shape, fan_in) of every tensor in state_dict order."""
         P, H = 3 * self.K - 1, self.hidden_dim

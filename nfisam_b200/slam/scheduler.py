@@ -149,13 +149,11 @@ class CliqueScheduler:
             if counter is not None and int(counter.item()):
                 raise AssertionError("negative discriminant in the inverse spline while sampling a separator factor")
             train_time += time.time() - t1
+            if world > 1:
+                results = self._exchange_level(todo, plans, results)
             for k, c in enumerate(todo):
                 sampler, var_order, true_obs = plans[id(c)]
-                owner = k % world
-                if world > 1:
-                    model, hist = self._exchange_model(c, var_order, results.get(k), owner)
-                else:
-                    model, hist = results[k]
+                model, hist = results[k]
                 s._clique_true_obs[c] = true_obs
                 s._record_loss(c, hist)
                 s._finish_clique(c, model, true_obs, already_eliminated=True)
@@ -166,37 +164,60 @@ class CliqueScheduler:
             timer.append(sim_time)      # same slots as the reference's [sampler_i, train_i] pairs, aggregated per step
             timer.append(train_time)
 
-    def _exchange_model(self, clique, var_order, local, owner):
-        """Owner -> everyone: flow parameters, normalisation constants and loss curve of one clique."""
+    def _exchange_level(self, todo, plans, local):
+        """Every rank ends up with the trained model of every clique of the level: flow parameters, normalisation constants
+        and loss curve of the cliques a rank owns are packed into one float32 vector and ONE all-gather per level moves
+        them (a broadcast per clique was 8 latency-bound collectives + host synchronisations per level)."""
+        import torch.distributed as dist
+
         from ..flows import NSF_AR, CustomMultivariateNormal
         from .nfisam import NormalizingFlowModelWithSeparator
 
         s = self.solver
         a = s._args
         rank, world = self._world()
-        d = sum(v.dim for v in var_order)
-        circular = []
-        for v in var_order:
-            circular += v.circular_dim_list
-        if rank == owner:
-            model, hist = local
-            theta = model.flows[0].flat_parameters()
-            payload = np.concatenate([theta, np.asarray(model.samples_mean, np.float32), np.asarray(model.samples_std, np.float32),
-                                      np.asarray(hist, np.float32)])
-        else:
-            flow = NSF_AR(dim=d, K=a.num_knots, hidden_dim=a.hidden_dim, device=a.device)
-            n_theta = flow.flat_parameters().size
-            payload = np.zeros(n_theta + 2 * d + a.flow_iterations, np.float32)
-        payload = self._bcast(payload, owner)
-        if rank == owner:
-            return local
-        theta, rest = payload[:n_theta], payload[n_theta:]
-        flow.load_flat_parameters(theta)
-        sep_dim = d - clique.frontal_dim
-        model = NormalizingFlowModelWithSeparator([flow], CustomMultivariateNormal(dim=d),
-                                                  CustomMultivariateNormal(dim=sep_dim) if sep_dim > 0 else None, circular,
-                                                  torch.tensor(rest[:d]), torch.tensor(rest[d:2 * d]))
-        return model, rest[2 * d:]
+        shapes = []                                       # per clique: (d, circular, n_theta, payload length), identical on every rank
+        for c in todo:
+            var_order = plans[id(c)][1]
+            circular = []
+            for v in var_order:
+                circular += v.circular_dim_list
+            d = len(circular)
+            n_theta = NSF_AR.num_parameters(d, a.num_knots, a.hidden_dim)
+            shapes.append((d, circular, n_theta, n_theta + 2 * d + a.flow_iterations))
+        per_rank = [sum(shapes[k][3] for k in range(r, len(todo), world)) for r in range(world)]
+        width = max(max(per_rank), 1)
+        mine = np.zeros(width, np.float32)
+        off = 0
+        for k in range(rank, len(todo), world):
+            model, hist = local[k]
+            d, _, n_theta, length = shapes[k]
+            h = np.zeros(a.flow_iterations, np.float32)
+            h[:len(hist)] = np.asarray(hist, np.float32)[:a.flow_iterations]
+            mine[off:off + length] = np.concatenate([model.flows[0].flat_parameters(), np.asarray(model.samples_mean, np.float32),
+                                                     np.asarray(model.samples_std, np.float32), h])
+            off += length
+        dev = self._comm_device()
+        send = torch.from_numpy(mine).to(dev)
+        gathered = [torch.empty(width, dtype=torch.float32, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, send)
+        rows = [g.cpu().numpy() for g in gathered]
+        out = dict(local)
+        offs = [0] * world
+        for k, c in enumerate(todo):
+            owner = k % world
+            d, circular, n_theta, length = shapes[k]
+            if owner != rank:
+                payload = rows[owner][offs[owner]:offs[owner] + length]
+                flow = NSF_AR(dim=d, K=a.num_knots, hidden_dim=a.hidden_dim, device=a.device, initial_parameters=payload[:n_theta])
+                rest = payload[n_theta:]
+                sep_dim = d - c.frontal_dim
+                model = NormalizingFlowModelWithSeparator([flow], CustomMultivariateNormal(dim=d),
+                                                          CustomMultivariateNormal(dim=sep_dim) if sep_dim > 0 else None, circular,
+                                                          torch.tensor(rest[:d]), torch.tensor(rest[d:2 * d]))
+                out[k] = (model, rest[2 * d:])
+            offs[owner] += length
+        return out
 
     # -- down-pass: device-resident -------------------------------------------------------------------
     def sample_posterior_device(self, timer: List[float] = None, seeded: bool = False):
