@@ -191,8 +191,11 @@ def test_100_pose_solve_matches_reference_posterior():
     below 1; landmark L3 collapses onto a mirror mode 186 units from the truth with std 0.09), and two of its runs differ
     from each other by more than the bounds used for the small graphs.  So the test (a) bounds this solver's error against the
     ground truth by the reference's own, and (b) when a second stored reference run exists, bounds the distance of our posterior
-    to the closest reference run by 1.5x the distance between the two reference runs (+ margins); with a single stored run
-    the distances are only reported."""
+    to the closest reference run by the distance between the two reference runs (2x + 1 for the mean excess and the std ratio,
+    1.25x + 0.1 for MMD_b, which saturates near 1); with a single stored run the distances are only reported.
+    Stored reference runs, seed 0 vs seed 1 (tests/golden/slim_solve_golden.py): mean pose error 3.1 / 4.2, 5.8 / 6.3, 7.3 / 8.9,
+    8.9 / 12.6 after 25 / 50 / 75 / 100 steps; between the two runs MMD_b 0.70, 0.87, 0.92, 1.05 and mean excess 2.9, 196, 236,
+    228 (a landmark collapsed onto different modes)."""
     case = "manhattan_r1_p100"
     path = os.path.join(HERE, "golden", f"solve_{case}.npz")
     if not os.path.exists(path):
@@ -228,9 +231,9 @@ def test_100_pose_solve_matches_reference_posterior():
             spread = np.maximum(_step_distance(b[f"step{i}_mean"], b[f"step{i}_std"], b[f"step{i}_samples"], names, a, i),
                                 _step_distance(a[f"step{i}_mean"], a[f"step{i}_std"], a[f"step{i}_samples"], names, b, i))
             row["reference_seed0_vs_seed1"] = [round(float(v), 3) for v in spread]
-            assert med[0] <= 1.5 * spread[0] + 0.5, row
-            assert med[1] <= 1.5 * spread[1] + 1.0, row
-            assert med[2] <= 1.5 * spread[2] + 0.1, row
+            assert med[0] <= 2.0 * spread[0] + 1.0, row
+            assert med[1] <= 2.0 * spread[1] + 1.0, row
+            assert med[2] <= 1.25 * spread[2] + 0.1, row
         report.append(row)
     print(f"\n[{case}]")
     for row in report:
