@@ -94,6 +94,9 @@ def main():
                        "posterior_samples": args.posterior, "ada_prob": args.ada_prob},
             "s_per_incr_step_mean": float(per_step.mean()), "s_per_incr_step_median": float(np.median(per_step)),
             "s_per_incr_step_last10_mean": float(per_step[-10:].mean()), "total_s": float(per_step.sum()),
+            "s_per_incr_step_first": float(per_step[0]), "s_per_incr_step_max": float(per_step.max()),
+            "s_per_incr_step_p90": float(np.percentile(per_step, 90)),
+            "slowest_steps": [[int(i), round(float(per_step[i]), 4)] for i in np.argsort(per_step)[::-1][:5]],
             "split_mean_graph_sim_train_posterior": [float(x) for x in sp.mean(0)],
             "cliques_trained_per_step_mean": float(np.mean(trained)), "max_level_width": int(max(widths)),
             "pose_mean_error": float(np.mean(pose_err)), "pose_max_error": float(np.max(pose_err)),

@@ -86,13 +86,13 @@ def main(tag="r1"):
     solves = sorted(glob.glob(os.path.join(OUT, "solve_*.json")))
     if solves:
         md += ["## Incremental solves (M3): synthetic Manhattan-world range SLAM", "",
-               "| graph | training rows per clique | GPUs | steps | s / incr step (mean) | split graph / simulate / train / posterior (ms) | cliques per step | max level width | pose mean error | file |",
-               "|---|---|---|---|---|---|---|---|---|---|"]
+               "| graph | training rows per clique | GPUs | steps | s / incr step (mean) | median | split graph / simulate / train / posterior (ms) | cliques per step | max level width | pose mean error | file |",
+               "|---|---|---|---|---|---|---|---|---|---|---|"]
         for p in solves:
             for j in load(p):
                 sp = [round(1e3 * x, 1) for x in j["split_mean_graph_sim_train_posterior"]]
                 md.append(f"| {j['robots']} robot(s) x {j['poses_per_robot']} poses, {j['landmarks']} landmarks | {j['config']['train_samples']} | {j['n_gpus']} | {j['steps']} | "
-                          f"{j['s_per_incr_step_mean']:.4f} | {sp} | {j['cliques_trained_per_step_mean']:.0f} | {j['max_level_width']} | "
+                          f"{j['s_per_incr_step_mean']:.4f} | {j['s_per_incr_step_median']:.4f} | {sp} | {j['cliques_trained_per_step_mean']:.0f} | {j['max_level_width']} | "
                           f"{j['pose_mean_error']:.2f} | {os.path.basename(p)} |")
         md += [""]
     open(os.path.join(ROOT, "profiles", f"{tag}_results.md"), "w").write("\n".join(md) + "\n")
