@@ -47,7 +47,14 @@ def main(tag="r1"):
                    f"({inc['train_us_per_iter']:.2f} us/iteration) + {inc['sample_1000_s'] * 1e3:.2f} ms for 1000 posterior draws",
                    f"* small range graph (reference settings, 6 steps): {[round(x * 1e3, 1) for x in sv.get('s_per_incr_step', [])]} ms per step, "
                    f"mean position error {sv.get('mean_abs_position_error', float('nan')):.2f}; reference stored run: {sv.get('reference_stored_s_per_step')} s per step",
-                   f"* one Adam step over 1e6 x 12 samples: {inc['train_step_1e6_samples_per_s'] / 1e6:.0f} M samples/s", ""]
+                   f"* one Adam step over 1e6 x 12 samples: {inc['train_step_1e6_samples_per_s'] / 1e6:.0f} M samples/s"]
+            ch = inc.get("solve_manhattan_r1_p100")
+            if ch:
+                md += [f"* 100-pose range-SLAM graph (configs[3], settings of the stored reference runs, {ch['steps']} steps): "
+                       f"{ch['s_per_incr_step_mean'] * 1e3:.1f} ms per step (median {ch['s_per_incr_step_median'] * 1e3:.1f}, p90 {ch['s_per_incr_step_p90'] * 1e3:.1f}, "
+                       f"first {ch['s_per_incr_step_first'] * 1e3:.0f}), mean pose error {ch['mean_pose_error']:.2f}; reference: "
+                       f"{ch['reference_s_per_step']} s per step, mean pose error {ch['reference_mean_pose_error']} (two stored runs)"]
+            md += [""]
     for n in (2, 8):
         g = load(os.path.join(OUT, f"bench_{tag}_g{n}.json"))
         if g:
