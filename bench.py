@@ -340,7 +340,7 @@ def run_gpu(args):
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (nf_forward_kernel<9,8>), live CUDA-event timing
+        # ---- roofline of the dominant kernel (nf_log_prob_pair_kernel<9,8>), live CUDA-event timing
         peaks = (ctypes.c_double * 4)()
         _lib.check(lib.nfisam_probe_pipe_peaks(local_rank, peaks))
         fp32_peak = ctypes.c_double(max(peaks[0], peaks[1], peaks[2]))
@@ -351,7 +351,7 @@ def run_gpu(args):
         hbm_peak, hbm_src = measured_peaks()
         hbm_ach = alg_bytes / (per_launch_ms * 1e-3) * 1e-9
         roofline = {
-            "bound": "fp32_fma", "kernel": "nf_forward_kernel<K=9,H=8> (log_prob mode)",
+            "bound": "fp32_fma", "kernel": "nf_log_prob_pair_kernel<K=9,H=8> (log-prob, two samples per thread; batches below 5e5 rows use nf_forward_kernel)",
             "achieved": achieved_tflops, "peak": fp32_peak.value, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak.value if fp32_peak.value > 0 else None,
             "peak_source": "measured live: best of the FFMA / FFMA2 probe kernels (nfisam_probe_pipe_peaks); "
@@ -363,7 +363,10 @@ def run_gpu(args):
             "mufu": {"achieved_gops": sfu_fwd(D, HID, K_BINS) * n / (per_launch_ms * 1e-3) * 1e-9, "peak_gops": mufu_peak.value},
             "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                     "algorithmic_bytes_per_sample": 4 * D + 4, "peak_source": hbm_src},
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the `ncu --set full` capture of this
+            # same command (profiles/r1_forward_kernel.md, capture F: 480.2 + 38.4 MB); algorithmic bytes: (4 d + 4) n = 520 MB
+            "traffic": 518.6e6 * (n / 1.0e7), "traffic_unit": "bytes per launch",
+            "traffic_source": "ncu capture F (profiles/r1_forward_kernel.md), scaled by n / 1e7", "algorithmic_bytes_per_launch": alg_bytes,
             "launch_ms": per_launch_ms,
         }
         extra = secondary_measurements(lib, _lib, dev, local_rank) if not args.no_extra else None

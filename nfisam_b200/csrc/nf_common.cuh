@@ -578,6 +578,106 @@ __device__ __forceinline__ float nf_inverse_dim(const float* __restrict__ wbase,
     return inside ? root * wk + xk : yin;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two samples per thread (log-prob of large batches, nf_log_prob_pair_kernel).  The shared-memory data pipe is the most
+// utilised unit of the forward kernel (75 %: every weight is a broadcast load, two wavefronts per LDS.128); evaluating the
+// conditioner of dim i for TWO samples with one set of weight loads halves those wavefronts per sample at the price of
+// ~2x the registers (half the resident warps, twice the independent work per warp).
+// ---------------------------------------------------------------------------------------------
+template <int NOUT>
+__device__ __forceinline__ void nf_axpy_row2(const float* __restrict__ wrow, float xa, float xb, float2 (&accA)[NOUT / 2],
+                                             float2 (&accB)[NOUT / 2]) {
+    const float2 xxa = make_float2(xa, xa), xxb = make_float2(xb, xb);
+#pragma unroll
+    for (int j = 0; j < NOUT; j += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wrow + j);
+        const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);
+        accA[j / 2] = nf_fma2(w01, xxa, accA[j / 2]);
+        accB[j / 2] = nf_fma2(w01, xxb, accB[j / 2]);
+        accA[j / 2 + 1] = nf_fma2(w23, xxa, accA[j / 2 + 1]);
+        accB[j / 2 + 1] = nf_fma2(w23, xxb, accB[j / 2 + 1]);
+    }
+}
+
+template <int K, int H>
+__device__ __forceinline__ void nf_outputs_wh_pair(const float* __restrict__ wbase, int i, const float* __restrict__ xrowA,
+                                                   const float* __restrict__ xrowB, float2 (&oA)[NfLazy<K>::PPW / 2],
+                                                   float2 (&oB)[NfLazy<K>::PPW / 2], float (&h2A)[H], float (&h2B)[H],
+                                                   const float*& b3, const float*& W3t) {
+    constexpr int PP = NfLazy<K>::PP, PPW = NfLazy<K>::PPW;
+    if (i == 0) {
+        nf_load_bias<PPW>(wbase, oA);
+#pragma unroll
+        for (int j = 0; j < PPW / 2; ++j) oB[j] = oA[j];
+        b3 = wbase;
+        W3t = nullptr;
+        return;
+    }
+    const float* w = wbase + nf_block_off(i, H, PP);
+    const float* W1t = w;
+    const float* b1 = W1t + i * H;
+    const float* W2t = b1 + H;
+    const float* b2 = W2t + H * H;
+    float2 aA[H / 2], aB[H / 2];
+    float h1A[H], h1B[H];
+    nf_load_bias<H>(b1, aA);
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) aB[j] = aA[j];
+    for (int k = 0; k < i; ++k) nf_axpy_row2<H>(W1t + k * H, xrowA[k], xrowB[k], aA, aB);
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) {
+        const float2 ta = nf_tanh2(aA[j]), tb = nf_tanh2(aB[j]);
+        h1A[2 * j] = ta.x; h1A[2 * j + 1] = ta.y;
+        h1B[2 * j] = tb.x; h1B[2 * j + 1] = tb.y;
+    }
+    nf_load_bias<H>(b2, aA);
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) aB[j] = aA[j];
+#pragma unroll
+    for (int k = 0; k < H; ++k) nf_axpy_row2<H>(W2t + k * H, h1A[k], h1B[k], aA, aB);
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) {
+        const float2 ta = nf_tanh2(aA[j]), tb = nf_tanh2(aB[j]);
+        h2A[2 * j] = ta.x; h2A[2 * j + 1] = ta.y;
+        h2B[2 * j] = tb.x; h2B[2 * j + 1] = tb.y;
+    }
+    W3t = w + i * H + H + H * H + H;
+    b3 = W3t + H * PP;
+    nf_load_bias<PPW>(b3, oA);
+#pragma unroll
+    for (int j = 0; j < PPW / 2; ++j) oB[j] = oA[j];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        const float* wrow = W3t + k * PP;
+        const float2 xxa = make_float2(h2A[k], h2A[k]), xxb = make_float2(h2B[k], h2B[k]);
+#pragma unroll
+        for (int j = 0; j < 2 * K; j += 4) {           // like nf_axpy_row_wh: the half float4 past 2K is not evaluated
+            const float4 w4 = *reinterpret_cast<const float4*>(wrow + j);
+            const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);
+            oA[j / 2] = nf_fma2(w01, xxa, oA[j / 2]);
+            oB[j / 2] = nf_fma2(w01, xxb, oB[j / 2]);
+            if (j + 2 < 2 * K) {
+                oA[j / 2 + 1] = nf_fma2(w23, xxa, oA[j / 2 + 1]);
+                oB[j / 2 + 1] = nf_fma2(w23, xxb, oB[j / 2 + 1]);
+            }
+        }
+    }
+}
+
+// z_i and log|dz_i/dx_i| of dim i for two samples
+template <int K, int H>
+__device__ __forceinline__ void nf_forward_dim_pair(const float* __restrict__ wbase, int i, const float* __restrict__ xrowA,
+                                                    const float* __restrict__ xrowB, float B, float& zA, float& zB, float& ldA,
+                                                    float& ldB) {
+    float2 oA[NfLazy<K>::PPW / 2], oB[NfLazy<K>::PPW / 2];
+    float h2A[H], h2B[H];
+    const float* b3;
+    const float* W3t;
+    nf_outputs_wh_pair<K, H>(wbase, i, xrowA, xrowB, oA, oB, h2A, h2B, b3, W3t);
+    zA = nf_forward_tail<K>(oA, B, xrowA[i], ldA, [&](int bin, float& dk, float& dk1) { nf_bin_derivs<K, H>(b3, W3t, h2A, bin, dk, dk1); });
+    zB = nf_forward_tail<K>(oB, B, xrowB[i], ldB, [&](int bin, float& dk, float& dk1) { nf_bin_derivs<K, H>(b3, W3t, h2B, bin, dk, dk1); });
+}
+
 // theta_to_pipi (src/utils/Functions.py:20-21): (t + pi) mod 2pi - pi with Python's modulo sign.
 __device__ __forceinline__ float nf_wrap_pipi(float t) {
     const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
