@@ -150,6 +150,10 @@ typedef struct nf_gather_item {
 } nf_gather_item;
 int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float* z_dev, int ld_z, float* s_dev, int ld_s,
                           int64_t n, unsigned long long* bad_counter_dev, void* stream);
+/* Host-only view of the launch plan nfisam_posterior_pass derives from the column lists (the `flow` and `norm` fields are
+ * not read; no device needed): group_of[k] = -1 for items of the trunk launch, else the index of the subtree group the item
+ * is walked in; *n_groups = number of groups, or -1 when the dependencies are not a forest (per-item launches). */
+int nfisam_posterior_pass_plan(const nf_gather_item* items, int n_items, int ld_s, int32_t* group_of, int32_t* n_groups);
 
 /* Host-buffer convenience used for the end-to-end numbers: pinned staging, chunked
  * H2D -> kernel -> D2H pipelining on two internal streams.  Synchronous. */

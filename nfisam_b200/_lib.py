@@ -119,6 +119,8 @@ SYMBOLS = {
     "nfisam_flow_set_bad_counter": (_INT, [_P, _P]),
     "nfisam_flow_inverse_gather": (_INT, [_P, _P, _INT, _INT, _P, _INT, _P, _P, _INT, _P, _INT, _I64,
                                           ctypes.POINTER(nf_affine), _P]),
+    "nfisam_posterior_pass_plan": (_INT, [ctypes.POINTER(nf_gather_item), _INT, _INT, ctypes.POINTER(ctypes.c_int32),
+                                         ctypes.POINTER(ctypes.c_int32)]),
     "nfisam_posterior_pass": (_INT, [ctypes.POINTER(nf_gather_item), _INT, _P, _INT, _P, _INT, _I64, _P, _P]),
     "nfisam_mmd": (_INT, [_P, _I64, _P, _I64, _INT, ctypes.c_double, _INT, _P, _P, _INT, _P]),
     "nfisam_flow_log_prob_host": (_INT, [_P, _P, _I64, _INT, _P]),

@@ -140,6 +140,84 @@ static void build_index_map(nf_flow* f) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Posterior-pass planner (host logic, no device): dependency forest of the items.  Item k hangs below the latest earlier
+// item that produced one of its given columns (in a Bayes tree: its parent clique).  The trunk (single root and its
+// only-child descendants) is one launch; the subtrees below the first branching item are mutually independent GROUPS
+// that a second launch walks concurrently.  A dependency that crosses two groups (not a forest: arbitrary caller input)
+// makes the pass non-fusable (one launch per item, stream order).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct PassCols {
+    const int* sep_cols;
+    int sep;
+    const int* out_cols;
+    int out;
+};
+constexpr int PASS_TRUNK = -2;
+
+// gid[k]: PASS_TRUNK or group index 0..n_groups-1.  Returns false when the dependencies are not a forest.
+bool plan_pass_groups(const std::vector<PassCols>& items, int ld_s, std::vector<int>* gid_out, std::vector<int>* order,
+                      std::vector<int2>* groups) {
+    const int n_items = (int)items.size();
+    std::vector<int> parent((size_t)n_items, -1);
+    std::vector<int>& gid = *gid_out;
+    gid.assign((size_t)n_items, -1);
+    std::vector<std::vector<int>> deps((size_t)n_items);
+    std::vector<int> producer((size_t)ld_s, -1);
+    for (int k = 0; k < n_items; ++k) {
+        const PassCols& h = items[(size_t)k];
+        for (int j = 0; j < h.sep; ++j)
+            if (h.sep_cols[j] >= 0 && producer[(size_t)h.sep_cols[j]] >= 0) deps[(size_t)k].push_back(producer[(size_t)h.sep_cols[j]]);
+        for (int c = 0; c < h.out; ++c) {
+            int& p = producer[(size_t)h.out_cols[c]];
+            if (p >= 0 && p != k) deps[(size_t)k].push_back(p);      // column rewritten: order against the earlier writer
+            p = k;
+        }
+        for (int p : deps[(size_t)k]) parent[(size_t)k] = p > parent[(size_t)k] ? p : parent[(size_t)k];
+    }
+    std::vector<int> n_child((size_t)n_items, 0);
+    int n_roots = 0, root = -1;
+    for (int k = 0; k < n_items; ++k) {
+        if (parent[(size_t)k] < 0) { ++n_roots; if (root < 0) root = k; }
+        else ++n_child[(size_t)parent[(size_t)k]];
+    }
+    if (n_roots == 1) {
+        int t = root;
+        gid[(size_t)t] = PASS_TRUNK;
+        while (n_child[(size_t)t] == 1) {
+            int c = -1;
+            for (int k = t + 1; k < n_items; ++k) if (parent[(size_t)k] == t) { c = k; break; }
+            gid[(size_t)c] = PASS_TRUNK;
+            t = c;
+        }
+    }
+    int n_groups = 0;
+    for (int k = 0; k < n_items; ++k) {
+        if (gid[(size_t)k] == PASS_TRUNK) continue;
+        const int p = parent[(size_t)k];
+        gid[(size_t)k] = (p < 0 || gid[(size_t)p] == PASS_TRUNK) ? n_groups++ : gid[(size_t)p];
+    }
+    for (int k = 0; k < n_items; ++k)
+        for (int p : deps[(size_t)k]) {
+            if (gid[(size_t)p] == PASS_TRUNK) continue;                       // the trunk precedes every group
+            if (gid[(size_t)k] == PASS_TRUNK || gid[(size_t)p] != gid[(size_t)k]) return false;
+        }
+    if (n_groups > 65535) return false;
+    std::vector<int> count((size_t)n_groups + 1, 0);
+    for (int k = 0; k < n_items; ++k) ++count[gid[(size_t)k] == PASS_TRUNK ? 0 : (size_t)gid[(size_t)k] + 1];
+    groups->resize((size_t)n_groups + 1);
+    int at = 0;
+    for (int g = 0; g <= n_groups; ++g) { (*groups)[(size_t)g] = make_int2(at, 0); at += count[(size_t)g]; }
+    order->resize((size_t)n_items);
+    for (int k = 0; k < n_items; ++k) {
+        int2& g = (*groups)[gid[(size_t)k] == PASS_TRUNK ? 0 : (size_t)gid[(size_t)k] + 1];
+        (*order)[(size_t)(g.x + g.y++)] = k;
+    }
+    return true;
+}
+}  // namespace
+
 extern "C" {
 
 const char* nfisam_version(void) { return "nfisam_b200 0.1 (sm_100a)"; }
@@ -374,72 +452,17 @@ int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float*
         max_wcount = h.wcount > max_wcount ? h.wcount : max_wcount;
         max_d = h.d > max_d ? h.d : max_d;
     }
-    // Dependency forest of the items: item k hangs below the latest earlier item that produced one of its given columns
-    // (in a Bayes tree: its parent clique).  The trunk (single root and its only-child descendants) is one launch; the
-    // subtrees below the first branching item are mutually independent GROUPS that one second launch walks concurrently.
-    // Any dependency that crosses two groups (not a tree: arbitrary caller input) disables the fused path.
-    bool fusable = uniform;
-    std::vector<int> parent((size_t)n_items, -1), gid((size_t)n_items, -1);
-    std::vector<std::vector<int>> deps((size_t)n_items);
-    if (fusable) {
-        std::vector<int> producer((size_t)ld_s, -1);
-        for (int k = 0; k < n_items; ++k) {
-            const NfPassItem& h = host[(size_t)k];
-            for (int j = 0; j < h.sep; ++j)
-                if (h.sep_cols[j] >= 0 && producer[(size_t)h.sep_cols[j]] >= 0) deps[(size_t)k].push_back(producer[(size_t)h.sep_cols[j]]);
-            for (int c = 0; c < h.d - h.sep; ++c) {
-                int& p = producer[(size_t)h.out_cols[c]];
-                if (p >= 0) deps[(size_t)k].push_back(p);      // column rewritten: order against the earlier writer
-                p = k;
-            }
-            for (int p : deps[(size_t)k]) parent[(size_t)k] = p > parent[(size_t)k] ? p : parent[(size_t)k];
-        }
-    }
     std::vector<int> order;                 // trunk first, then the groups, each in caller order
     std::vector<int2> groups;               // [first, count) into `order`; groups[0] = trunk (may be empty)
+    bool fusable = uniform;
     if (fusable) {
-        std::vector<int> n_child((size_t)n_items, 0);
-        int n_roots = 0, root = -1;
+        std::vector<PassCols> cols((size_t)n_items);
         for (int k = 0; k < n_items; ++k) {
-            if (parent[(size_t)k] < 0) { ++n_roots; if (root < 0) root = k; }
-            else ++n_child[(size_t)parent[(size_t)k]];
+            const NfPassItem& h = host[(size_t)k];
+            cols[(size_t)k] = PassCols{h.sep_cols, h.sep, h.out_cols, h.d - h.sep};
         }
-        const int TRUNK = -2;
-        if (n_roots == 1) {
-            int t = root;
-            gid[(size_t)t] = TRUNK;
-            while (n_child[(size_t)t] == 1) {
-                int c = -1;
-                for (int k = t + 1; k < n_items; ++k) if (parent[(size_t)k] == t) { c = k; break; }
-                gid[(size_t)c] = TRUNK;
-                t = c;
-            }
-        }
-        int n_groups = 0;
-        for (int k = 0; k < n_items; ++k) {
-            if (gid[(size_t)k] == TRUNK) continue;
-            const int p = parent[(size_t)k];
-            gid[(size_t)k] = (p < 0 || gid[(size_t)p] == TRUNK) ? n_groups++ : gid[(size_t)p];
-        }
-        for (int k = 0; k < n_items && fusable; ++k) {
-            for (int p : deps[(size_t)k]) {
-                const bool ok = gid[(size_t)p] == TRUNK ? true : gid[(size_t)p] == gid[(size_t)k];
-                if (!ok || (gid[(size_t)k] == TRUNK && gid[(size_t)p] != TRUNK)) { fusable = false; break; }
-            }
-        }
-        if (n_groups > 65535) fusable = false;
-        if (fusable) {
-            std::vector<int> count((size_t)n_groups + 1, 0);
-            for (int k = 0; k < n_items; ++k) ++count[gid[(size_t)k] == TRUNK ? 0 : (size_t)gid[(size_t)k] + 1];
-            groups.resize((size_t)n_groups + 1);
-            int at = 0;
-            for (int g = 0; g <= n_groups; ++g) { groups[(size_t)g] = make_int2(at, 0); at += count[(size_t)g]; }
-            order.resize((size_t)n_items);
-            for (int k = 0; k < n_items; ++k) {
-                int2& g = groups[gid[(size_t)k] == TRUNK ? 0 : (size_t)gid[(size_t)k] + 1];
-                order[(size_t)(g.x + g.y++)] = k;
-            }
-        }
+        std::vector<int> gid;
+        fusable = plan_pass_groups(cols, ld_s, &gid, &order, &groups);
     }
     const nf_flow* f0 = items[0].flow;
     DeviceGuard g(f0->device);
@@ -500,6 +523,31 @@ int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float*
         it.flow->d_bad_ext = saved;
         if (rc != NF_OK) return rc;
     }
+    return NF_OK;
+}
+
+int nfisam_posterior_pass_plan(const nf_gather_item* items, int n_items, int ld_s, int32_t* group_of, int32_t* n_groups) {
+    if (n_items < 0 || ld_s < 1 || (n_items > 0 && (!items || !group_of)) || !n_groups) return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    std::vector<PassCols> cols((size_t)n_items);
+    for (int k = 0; k < n_items; ++k) {
+        const nf_gather_item& it = items[k];
+        if (it.sep_dim < 0 || it.out_dim < 1 || it.sep_dim + it.out_dim > NF_MAX_DIM || !it.out_cols_host || (it.sep_dim > 0 && !it.sep_cols_host))
+            return nf_set_error(NF_ERR_BAD_ARG, "item %d: bad sep_dim / out_dim / column lists", k);
+        for (int j = 0; j < it.sep_dim; ++j)
+            if (it.sep_cols_host[j] >= ld_s) return nf_set_error(NF_ERR_BAD_ARG, "item %d: given column %d out of range", k, j);
+        for (int c = 0; c < it.out_dim; ++c)
+            if (it.out_cols_host[c] < 0 || it.out_cols_host[c] >= ld_s) return nf_set_error(NF_ERR_BAD_ARG, "item %d: output column %d out of range", k, c);
+        cols[(size_t)k] = PassCols{it.sep_cols_host, it.sep_dim, it.out_cols_host, it.out_dim};
+    }
+    std::vector<int> gid, order;
+    std::vector<int2> groups;
+    if (!plan_pass_groups(cols, ld_s, &gid, &order, &groups)) {
+        *n_groups = -1;                                   // not a forest: the pass runs one launch per item
+        for (int k = 0; k < n_items; ++k) group_of[k] = -1;
+        return NF_OK;
+    }
+    *n_groups = (int)groups.size() - 1;
+    for (int k = 0; k < n_items; ++k) group_of[k] = gid[(size_t)k] == PASS_TRUNK ? -1 : gid[(size_t)k];
     return NF_OK;
 }
 

@@ -89,3 +89,57 @@ def test_new_abi_structs_match_header(built_lib):
     assert ctypes.sizeof(built_lib.nf_gather_item) == lib.nfisam_struct_size(4)
     assert ctypes.sizeof(built_lib.nf_train_cfg) == 64        # ... reset_optimizer, concurrency
     assert lib.nfisam_struct_size(99) == -1
+
+
+def _plan(built_lib, cliques, ld_s):
+    """cliques: list of (given columns, generated columns); returns (group_of, n_groups) of nfisam_posterior_pass_plan."""
+    lib = built_lib.load()
+    n = len(cliques)
+    items = (built_lib.nf_gather_item * max(n, 1))()
+    keep = []
+    for it, (sep, out) in zip(items, cliques):
+        sc = (ctypes.c_int32 * max(len(sep), 1))(*sep)
+        oc = (ctypes.c_int32 * max(len(out), 1))(*out)
+        keep.append((sc, oc))
+        it.sep_dim, it.out_dim = len(sep), len(out)
+        it.sep_cols_host, it.out_cols_host = ctypes.addressof(sc), ctypes.addressof(oc)
+    group_of = (ctypes.c_int32 * max(n, 1))()
+    n_groups = ctypes.c_int32(-7)
+    built_lib.check(lib.nfisam_posterior_pass_plan(items, n, ld_s, group_of, ctypes.byref(n_groups)))
+    return list(group_of[:n]), n_groups.value
+
+
+def test_posterior_pass_plan_trunk_groups_and_fallback(built_lib):
+    """Host logic of nfisam_posterior_pass: trunk = root and its only-child descendants, one group per subtree below the
+    first branching clique, forests have no trunk, cross-subtree dependencies are not fusable."""
+    # chain of 4 cliques (3 columns each; a clique reads its parent's columns and a constant): everything is trunk
+    chain = [([-1], [0, 1, 2])] + [([-1, 3 * k - 3, 3 * k - 2, 3 * k - 1], [3 * k, 3 * k + 1, 3 * k + 2]) for k in range(1, 4)]
+    assert _plan(built_lib, chain, 12) == ([-1, -1, -1, -1], 0)
+    # trunk of 2, then 3 branches of depth 2 hanging below the second trunk clique (columns 3-5); DFS order
+    tree = [([-1], [0, 1, 2]), ([0, 1, 2], [3, 4, 5])]
+    col = 6
+    for b in range(3):
+        tree.append(([3, 4, 5, 0], [col, col + 1]))                      # also reads a grandparent column
+        tree.append(([col, col + 1, 4], [col + 2, col + 3]))
+        col += 4
+    g, n = _plan(built_lib, tree, col)
+    assert n == 3 and g == [-1, -1, 0, 0, 1, 1, 2, 2]
+    # the same tree in breadth-first order: groups follow the items, not their positions
+    bfs = tree[:2] + [tree[2], tree[4], tree[6], tree[3], tree[5], tree[7]]
+    g, n = _plan(built_lib, bfs, col)
+    assert n == 3 and g == [-1, -1, 0, 1, 2, 0, 1, 2]
+    # forest: two independent roots, no trunk
+    forest = [([-1], [0, 1]), ([0], [2, 3]), ([], [4, 5]), ([5], [6])]
+    assert _plan(built_lib, forest, 7) == ([0, 0, 1, 1], 2)
+    # a clique of the last branch also reads a column generated inside the first branch: not a forest
+    cross = list(tree)
+    cross[7] = ([14, 15, 6], [16, 17])
+    g, n = _plan(built_lib, cross, col)
+    assert n == -1 and g == [-1] * 8
+    # a column written twice orders the writers: second writer hangs below the first
+    rewrite = [([-1], [0, 1]), ([0], [2]), ([1], [2])]
+    g, n = _plan(built_lib, rewrite, 3)
+    assert n in (0, -1) or g[1] == g[2]
+    assert _plan(built_lib, [], 4) == ([], 0)
+    with pytest.raises(built_lib.NfisamError):
+        _plan(built_lib, [([-1], [9])], 4)                                # output column out of range
