@@ -137,11 +137,12 @@ class FactorGraphSolver:
 
         physical_cliques = self._physical_bayes_tree.clique_nodes
         stale = [c for c in list(self._clique_density_model.keys()) if c not in physical_cliques]
+        working_cliques = [(c, c.vars) for c in self._working_bayes_tree.clique_ordering()] if stale else []
         for old_clique in stale:
-            for new_clique in self._working_bayes_tree.clique_ordering():
-                same_vars = old_clique.vars == new_clique.vars
-                if same_vars and [v for v in old_ordering if v in old_clique.vars] == \
-                        [v for v in self._elimination_ordering if v in new_clique.vars]:
+            old_vars = old_clique.vars
+            for new_clique, new_vars in working_cliques:
+                if old_vars == new_vars and [v for v in old_ordering if v in old_vars] == \
+                        [v for v in self._elimination_ordering if v in new_vars]:
                     self._clique_true_obs[new_clique] = self._clique_true_obs[old_clique]
                     if old_clique in self._clique_variable_pattern:
                         self._clique_variable_pattern[new_clique] = self._clique_variable_pattern[old_clique]

@@ -18,6 +18,7 @@ class Variable:
         if rot and not (0 <= min(rot) and max(rot) < dim):
             raise ValueError("rotational_dims is incorrect")
         self._name, self._dim, self._type, self._rot = name, int(dim), variable_type, rot
+        self._hash = hash(name)          # the name never changes: hashed once (set / dict operations dominate the graph updates)
 
     @classmethod
     def construct_from_text(cls, line: str) -> "Variable":
@@ -49,10 +50,10 @@ class Variable:
     __repr__ = __str__
 
     def __hash__(self):
-        return hash(self._name)
+        return self._hash
 
     def __eq__(self, other):
-        return isinstance(other, Variable) and self._name == other._name
+        return self is other or (isinstance(other, Variable) and self._name == other._name)
 
     def __ne__(self, other):
         return not self == other
