@@ -89,7 +89,15 @@ class SimulationBasedSampler:
     # ------------------------------------------------------------------------------------------
     def plan(self):
         """Returns (steps, var_ordering, observation vector).  A step is a tuple
-        ('prior', f) | ('gen', f, given_var, new_var) | ('obs', f) | ('da_obs', f) | ('da_gen', f)."""
+        ('prior', f) | ('gen', f, given_var, new_var) | ('obs', f) | ('da_obs', f) | ('da_gen', f).
+        The schedule only depends on the factor / variable lists given at construction: computed once."""
+        cached = self.__dict__.get("_plan")
+        if cached is None:
+            cached = self.__dict__["_plan"] = self._make_plan()
+        steps, var_ordering, unused_obs = cached
+        return list(steps), list(var_ordering), unused_obs.copy()
+
+    def _make_plan(self):
         priors = [f for f in self.factors if isinstance(f, PriorFactor)]
         null_h = [f for f in self.factors if isinstance(f, BinaryFactorWithNullHypo)]
         das = [f for f in self.factors if isinstance(f, AmbiguousDataAssociationFactor)]
