@@ -40,8 +40,9 @@ def flops_fwd(d, H, K):
 
 def flops_fwd_executed(d, H, K):
     """FLOPs the kernel actually issues: only the two derivative columns of the bin that holds the input are
-    evaluated (nf_common.cuh, lazy derivative rows), the 2K width / height columns are padded to a multiple of 4."""
-    ppw = (2 * K + 3) // 4 * 4
+    evaluated (nf_common.cuh, lazy derivative rows); the 2K width / height columns are evaluated in pairs (packed FFMA2),
+    the half float4 past them is skipped."""
+    ppw = (2 * K + 1) // 2 * 2
     macs = H * d * (d - 1) // 2 + (d - 1) * (H * H + H * (ppw + 2))
     return 2 * macs + (d - 1) * (2 * H + ppw + 2) + d * (13 * K + 55)
 
