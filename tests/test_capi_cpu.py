@@ -143,3 +143,43 @@ def test_posterior_pass_plan_trunk_groups_and_fallback(built_lib):
     assert _plan(built_lib, [], 4) == ([], 0)
     with pytest.raises(built_lib.NfisamError):
         _plan(built_lib, [([-1], [9])], 4)                                # output column out of range
+
+
+def test_flow_parameter_count_and_received_parameters():
+    """NSF_AR.num_parameters matches the state_dict size (src/flows/flows.py:51-63); a flow built from parameters received
+    from another rank draws nothing from the RNG and holds exactly those parameters."""
+    import torch
+
+    from nfisam_b200.flows import NSF_AR
+
+    for d, K, H in ((1, 9, 8), (6, 9, 8), (11, 9, 8), (18, 15, 16)):
+        torch.manual_seed(d)
+        f = NSF_AR(dim=d, K=K, hidden_dim=H)
+        assert f.flat_parameters().size == NSF_AR.num_parameters(d, K, H) == sum(p.numel() for p in f.parameters())
+        state = torch.get_rng_state()
+        g = NSF_AR(dim=d, K=K, hidden_dim=H, initial_parameters=f.flat_parameters())
+        assert torch.equal(state, torch.get_rng_state())
+        assert np.array_equal(g.flat_parameters(), f.flat_parameters())
+    assert NSF_AR.num_parameters(11, 9, 8) == 3606            # SURVEY.md section 8, row A2
+    with pytest.raises(ValueError):
+        NSF_AR(dim=4, K=9, hidden_dim=8, initial_parameters=np.zeros(5, np.float32))
+
+
+def test_initial_parameters_reproduce_the_reference_module_tree_draws():
+    """The single-draw initialisation equals, bit for bit, constructing the reference's module tree under the same seed:
+    nn.Linear.reset_parameters per conditioner layer in module order, then init_param ~ U(-1/2, 1/2)."""
+    import torch
+    import torch.nn as nn
+
+    from nfisam_b200.flows import NSF_AR
+
+    for d, K, H in ((2, 5, 8), (7, 9, 8), (12, 12, 16)):
+        torch.manual_seed(100 + d)
+        ours = NSF_AR(dim=d, K=K, hidden_dim=H).flat_parameters()
+        torch.manual_seed(100 + d)
+        P, parts = 3 * K - 1, []
+        for i in range(1, d):
+            for layer in (nn.Linear(i, H), nn.Linear(H, H), nn.Linear(H, P)):
+                parts += [layer.weight.detach().numpy().ravel(), layer.bias.detach().numpy().ravel()]
+        init = torch.empty(P).uniform_(-0.5, 0.5).numpy()
+        assert np.array_equal(ours, np.concatenate([init] + parts))
