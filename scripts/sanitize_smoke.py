@@ -8,6 +8,8 @@
 import os
 import sys
 
+os.environ.setdefault("NFISAM_FWD_PAIR", "1")     # log-prob calls take the two-samples-per-thread kernel at any batch size
+
 import numpy as np
 import torch
 
@@ -58,6 +60,9 @@ def main():
         f.fit_finish()
     MMDb(rng.standard_normal((300, 5)), rng.standard_normal((257, 5)), 1.3)
     MMDu2(rng.standard_normal((130, 22)), rng.standard_normal((64, 22)), 4.0)
+    MMDb(rng.standard_normal((140, 158)), rng.standard_normal((77, 158)), 12.0)       # column-chunked kernel (wide rows)
+    fp = NSF_AR(dim=12, K=9, hidden_dim=8)
+    fp.log_prob(torch.tensor(rng.standard_normal((1001, 12)).astype(np.float32) * 2.0))   # pair kernel, ragged tile
     nodes, truth, factors = read_factor_graph_from_file(os.path.join(ROOT, "tests", "data", "small_case1_da.fg"))
     jf = JointFactor(factors, nodes)
     xx = np.concatenate([truth[v] for v in nodes]) + rng.standard_normal((500, 22)) * 0.3
