@@ -24,7 +24,6 @@ from scipy.stats import norm
 
 from .. import _lib
 from ..flows import NSF_AR, CustomMultivariateNormal, NormalizingFlowModel
-from ..factors.factors import Factor
 from .bayes_tree import BayesTreeNode
 from .run_batch import graph_file_parser, group_nodes_factors_incrementally
 from .scheduler import CliqueScheduler

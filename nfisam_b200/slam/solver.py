@@ -13,8 +13,8 @@ from typing import Dict, List
 
 import numpy as np
 
-from ..factors.factors import BinaryFactorMixture, Factor, ImplicitPriorFactor, KWayFactor
-from .bayes_tree import BayesTree, BayesTreeNode
+from ..factors.factors import BinaryFactorMixture, Factor, ImplicitPriorFactor
+from .bayes_tree import BayesTreeNode
 from .factor_graph import FactorGraph
 from .simulation_sampler import SimulationBasedSampler
 from .variables import Variable, VariableType

@@ -13,7 +13,7 @@ import numpy as np
 
 from ..factors.factors import (AmbiguousDataAssociationFactor, Factor, SE2R2RangeGaussianLikelihoodFactor,
                                SE2RelativeGaussianLikelihoodFactor, UnarySE2ApproximateGaussianPriorFactor)
-from ..factors.geometry import SE2Pose, se2_compose, se2_exp, se2_inverse
+from ..factors.geometry import SE2Pose, se2_compose, se2_exp
 from .variables import R2Variable, SE2Variable, Variable, VariableType
 
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import factor_oracle as fo
-from tests.test_oracle_factors import build_factors, check
+from tests.test_oracle_factors import build_factors
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
