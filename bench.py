@@ -183,27 +183,78 @@ def trained_like_theta(d, K, H, seed=0):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (the reference is Python/torch, nothing to compile into oracle/_ref)
+# CPU arms.  (a) the reference's OWN PyTorch implementation of the path, staged verbatim into oracle/_ref/flows by
+# oracle/make_ref.py at build() time (kind "reference"): NormalizingFlowModel.forward, src/flows/models.py:11-24, with
+# torch.set_num_threads(host cores);  (b) the OpenMP C port of oracle/ (kind "port"), with the thread count set explicitly
+# (torchrun exports OMP_NUM_THREADS=1).  Only these legs may touch oracle/.
 # ------------------------------------------------------------------------------------------------
-def cpu_log_prob_rate(theta, n_sample, seed=123):
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_log_prob_rate(theta, n_sample, seed=123, threads=None):
     from oracle import nsf_oracle as orc
 
+    threads = threads or host_threads()
+    used = orc.set_num_threads(threads)
     x = make_inputs(n_sample, D, seed)
     t0 = time.perf_counter()
     orc.log_prob(theta, D, K_BINS, HID, TAIL, x)
     dt = time.perf_counter() - t0
-    return n_sample / dt, dt
+    return n_sample / dt, dt, used
 
 
 def cpu_baseline_block(theta, target_s=12.0):
-    from oracle import nsf_oracle as orc  # noqa: F401  (build if needed)
-
-    rate, _ = cpu_log_prob_rate(theta, 100_000)
+    rate, _, used = cpu_log_prob_rate(theta, 100_000)
     n = int(min(max(rate * target_s, 100_000), N_PER_GPU))
-    rate, dt = cpu_log_prob_rate(theta, n)
-    return {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"oracle/nsf_oracle.c log_prob (OpenMP, {os.cpu_count()} threads) on {n} of the "
+    rate, dt, used = cpu_log_prob_rate(theta, n)
+    return {"value": rate, "unit": "samples/s", "cores": used, "kind": "port",
+            "sample": f"oracle/nsf_oracle.c log_prob (OpenMP, {used} threads) on {n} of the "
                       f"{N_PER_GPU} samples of the workload, {dt:.1f} s"}
+
+
+def reference_torch_model(theta):
+    """The reference's NormalizingFlowModel (oracle/_ref/flows, staged by oracle/make_ref.py) carrying `theta` (state_dict
+    order).  Returns None when the staged copy is absent."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "flows", "flows.py")):
+        return None
+    import torch
+
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    from flows.flows import NSF_AR as RefNSF
+    from flows.models import NormalizingFlowModel as RefModel
+    from flows.prior_dist import CustomMultivariateNormal as RefPrior
+
+    flow = RefNSF(dim=D, K=K_BINS, B=TAIL, hidden_dim=HID)
+    params = [flow.init_param]
+    for layer in flow.layers:
+        for j in (0, 2, 4):
+            params += [layer.network[j].weight, layer.network[j].bias]
+    off = 0
+    with torch.no_grad():
+        for p in params:
+            k = p.numel()
+            p.copy_(torch.from_numpy(np.asarray(theta[off:off + k], np.float32).reshape(tuple(p.shape)).copy()))
+            off += k
+    assert off == len(theta)
+    return RefModel(RefPrior(dim=D), [flow])       # the prior NFiSAM.fit_clique_density_model builds (src/slam/NFiSAM.py:389-431)
+
+
+def torch_reference_rate(model, n_sample, seed=123):
+    import torch
+
+    x = torch.from_numpy(make_inputs(n_sample, D, seed))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        z, prior_logprob, log_det = model.forward(x)
+        lp = prior_logprob + log_det           # what the training loss of the reference averages (src/slam/NFiSAM.py:470-472)
+        dt = time.perf_counter() - t0
+    return n_sample / dt, dt, float(lp.sum())
 
 
 def run_reference(args):
@@ -211,13 +262,36 @@ def run_reference(args):
     if rank != 0:
         return
     theta = trained_like_theta(D, K_BINS, HID)
-    rate0, _ = cpu_log_prob_rate(theta, 50_000)
-    n = int(min(max(rate0 * 4.0, 50_000), N_PER_GPU))   # ~4 s per step
+    threads = host_threads()
+    model = reference_torch_model(theta)
+    port_rate, _, port_threads = cpu_log_prob_rate(theta, 200_000, threads=threads)
+    if model is not None:
+        import torch
+
+        torch.set_num_threads(threads)
+        kind = "reference"
+        rate0, _, _ = torch_reference_rate(model, 50_000)
+        n = int(min(max(rate0 * 4.0, 50_000), 2_000_000))   # ~4 s per step; the reference materialises (n*d, K) tensors
+
+        def one():
+            return torch_reference_rate(model, n)[0]
+        used = torch.get_num_threads()
+        what = (f"{n} samples per step through the reference's own NormalizingFlowModel.forward (oracle/_ref/flows, unmodified "
+                f"src/flows/*.py, PyTorch CPU, torch.set_num_threads({used}))")
+    else:
+        kind = "port"
+        rate0 = port_rate
+        n = int(min(max(rate0 * 4.0, 50_000), N_PER_GPU))
+
+        def one():
+            return cpu_log_prob_rate(theta, n, threads=threads)[0]
+        used = port_threads
+        what = f"{n} samples per step, oracle/nsf_oracle.c with OpenMP on {used} threads (oracle/_ref absent)"
     for _ in range(args.warmup):
-        cpu_log_prob_rate(theta, n)
+        one()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_log_prob_rate(theta, n)
+        one()
     dt = time.perf_counter() - t0
     rate = n * args.steps / dt
     line = {
@@ -226,9 +300,9 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs[2] synthetic RQS flow microbench: log_prob, dim {D}, K {K_BINS}, hidden {HID}, "
                                f"{N_PER_GPU} samples per GPU (CPU arm: bounded sample of {n} per step)"},
-        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{n} samples per step, oracle/nsf_oracle.c with OpenMP on {os.cpu_count()} threads "
-                                   "(the reference itself is Python/torch and cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": used, "kind": kind, "sample": what,
+                         "c_port_samples_per_s": port_rate, "c_port_threads": port_threads,
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -370,7 +444,6 @@ def run_gpu(args):
             "traffic_source": "ncu capture F (profiles/r1_forward_kernel.md), scaled by n / 1e7", "algorithmic_bytes_per_launch": alg_bytes,
             "launch_ms": per_launch_ms,
         }
-        extra = secondary_measurements(lib, _lib, dev, local_rank) if not args.no_extra else None
         cpu = cpu_baseline_block(theta) if world == 1 and not args.no_cpu else None
         line = {
             "metric": "rqs_flow_log_prob_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -389,13 +462,37 @@ def run_gpu(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if extra is not None:
-            line["incr_step"] = extra
+    # ---- companion metric "clique-flow train+sample s/incr-step".  Everything below that involves the solver runs on
+    # ALL ranks (round 1 ran it on rank 0 only while the other ranks sat in a barrier: mismatched collectives, NCCL abort).
+    extra = None
+    if not args.no_extra:
+        extra = {}
+        if world == 1:
+            extra = secondary_measurements(lib, _lib, dev, local_rank)
+        group = dist.group.WORLD if world > 1 else None
+        extra.update(clique_parallel_solves(group, local_rank))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
+        if extra is not None:
+            line["incr_step"] = extra
         print(json.dumps(line))
+
+
+def clique_parallel_solves(group, local_rank):
+    """configs[4]: synthetic multi-robot range-SLAM graphs (8 robots, shared landmarks, ambiguous associations with
+    probability .4) solved incrementally through the drop-in NFiSAM API; with N > 1 the cliques of a
+    tree level are dealt to the N GPUs (NFiSAMArgs.process_group).  Called by every rank."""
+    from benchmarks.solve_bench import run_solve
+
+    out = {}
+    # warm-up: module loads, kernel attribute set-up, NCCL channels
+    run_solve(robots=8, poses=4, ada_prob=0.4, iters=500, samples=2000, process_group=group, device=local_rank)
+    out["solve_mr8x64"] = run_solve(robots=8, poses=64, ada_prob=0.4, iters=500, samples=2000, process_group=group, device=local_rank)
+    out["solve_mr8x16_n50k"] = run_solve(robots=8, poses=16, ada_prob=0.4, iters=500, samples=50000, process_group=group,
+                                        device=local_rank)
+    return out
 
 
 def secondary_measurements(lib, _lib, dev, local_rank):

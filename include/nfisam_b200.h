@@ -64,7 +64,11 @@ int nfisam_struct_size(int which);
 /* ------------------------------------------------------------------------------------------
  * Flow handle  -- replaces NSF_AR.__init__/state_dict (src/flows/flows.py:43-63)
  * ---------------------------------------------------------------------------------------- */
-/* dim >= 1, K = number of spline bins ("num_knots"), hidden = FCNN width, tail_bound = B. */
+/* Largest flow dimension (= augmented clique dimension: simulated observations + separator + frontal columns).  The
+ * posterior-pass and training kernels size per-lane state for it; nfisam_flow_create returns NF_ERR_UNSUPPORTED above
+ * it (the reference has no limit; its configurations reach 18). */
+#define NFISAM_MAX_DIM 32
+/* 1 <= dim <= NFISAM_MAX_DIM, K = number of spline bins ("num_knots"), hidden = FCNN width, tail_bound = B. */
 int nfisam_flow_create(int dim, int K, int hidden, float tail_bound, int device, nf_flow_t** out);
 int nfisam_flow_destroy(nf_flow_t* f);
 int nfisam_flow_num_params(const nf_flow_t* f, int64_t* n);
@@ -193,6 +197,20 @@ int nfisam_flow_train(nf_flow_t* f, const float* data_dev, int64_t n, const nf_t
  * streams: _launch enqueues, _finish synchronises the stream and collects the history. */
 int nfisam_flow_train_launch(nf_flow_t* f, const float* data_dev, int64_t n, const nf_train_cfg* cfg, void* stream);
 int nfisam_flow_train_finish(nf_flow_t* f, float* loss_hist_host, int32_t max_iters, int32_t* iters_run, void* stream);
+
+/* Device-side hand-over of a trained flow, for schedulers that train many cliques per step and exchange them between
+ * GPUs (the reference moves the trained model back to the host after every clique, src/slam/NFiSAM.py:506-513).
+ * A state record is nfisam_flow_state_floats(f, max_iters) floats:
+ *     [ parameters in the kernels' packed layout | loss history, max_iters entries, 0 after the stop |
+ *       iterations run, status (non-zero: NaN/inf loss), 0, 0 ]
+ * The packed layout only depends on (dim, K, hidden), so a record can be imported by any handle of the same shape on
+ * any device (after an NCCL all-gather of the records, say).
+ *   _train_export ends the pending training run like _train_finish but WITHOUT synchronising: a small kernel on `stream`
+ *                 writes the record to dst_dev once the run has drained.  max_iters >= the run's max_iters.
+ *   _import_state copies the parameters of a record into the handle (device to device, asynchronous) and resets Adam. */
+int nfisam_flow_state_floats(const nf_flow_t* f, int32_t max_iters, int64_t* n_floats);
+int nfisam_flow_train_export(nf_flow_t* f, float* dst_dev, int32_t max_iters, void* stream);
+int nfisam_flow_import_state(nf_flow_t* f, const float* src_dev, void* stream);
 
 /* loss and d loss / d theta (state_dict order, host) at the current parameters, no update:
  * what loss.backward() leaves in .grad (src/slam/NFiSAM.py:470-474).  Synchronous. */

@@ -16,6 +16,7 @@ NF_OK = 0
 NF_ERR_BAD_ARG, NF_ERR_CUDA, NF_ERR_NAN_LOSS, NF_ERR_NEG_DISCRIMINANT, NF_ERR_OOM, NF_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 NF_FACTOR_SE2_PRIOR, NF_FACTOR_SE2_BETWEEN, NF_FACTOR_RANGE, NF_FACTOR_GAUSS_PRIOR = 1, 2, 3, 4
 NF_FACTOR_MAX_COLS = 6
+NFISAM_MAX_DIM = 32      # include/nfisam_b200.h
 
 
 class NfisamError(RuntimeError):
@@ -128,6 +129,9 @@ SYMBOLS = {
     "nfisam_flow_train": (_INT, [_P, _P, _I64, ctypes.POINTER(nf_train_cfg), _P, ctypes.POINTER(ctypes.c_int32), _P]),
     "nfisam_flow_train_launch": (_INT, [_P, _P, _I64, ctypes.POINTER(nf_train_cfg), _P]),
     "nfisam_flow_train_finish": (_INT, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), _P]),
+    "nfisam_flow_state_floats": (_INT, [_P, ctypes.c_int32, ctypes.POINTER(_I64)]),
+    "nfisam_flow_train_export": (_INT, [_P, _P, ctypes.c_int32, _P]),
+    "nfisam_flow_import_state": (_INT, [_P, _P, _P]),
     "nfisam_flow_loss_grad": (_INT, [_P, _P, _I64, _P, _P, _P]),
     "nfisam_factor_logpdf": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _P, _INT, _P]),
     "nfisam_mixture_posterior_weights": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _INT, _P]),

@@ -16,6 +16,7 @@
 // ------------------------------------------------------------------------------------------------
 // error / bookkeeping helpers
 // ------------------------------------------------------------------------------------------------
+static_assert(NF_MAX_DIM == NFISAM_MAX_DIM, "public and internal dim limits differ");
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};
 
@@ -89,6 +90,10 @@ struct nf_flow {
     float* d_loss_partials = nullptr;
     int pending_iters = 0;
     int pending_launches = 0;
+    // nfisam_flow_train_export ended a run without reading its control record back: the number of Adam steps it took is
+    // fetched lazily (only a later launch with reset_optimizer = 0 needs it)
+    int exported_iters = 0;
+    int exported_launches = -1;
     // host-API staging
     float* d_stage_in[2] = {nullptr, nullptr};
     float* d_stage_aux[2] = {nullptr, nullptr};
@@ -682,7 +687,14 @@ static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const n
         NF_CUDA(cudaMemsetAsync(f->d_m, 0, bytes, st));
         NF_CUDA(cudaMemsetAsync(f->d_v, 0, bytes, st));
         f->adam_steps = 0;
+    } else if (f->exported_launches >= 0) {
+        NfTrainCtrl ctrl[2];
+        NF_CUDA(cudaMemcpyAsync(ctrl, f->d_ctrl, sizeof(ctrl), cudaMemcpyDeviceToHost, st));
+        NF_CUDA(cudaStreamSynchronize(st));
+        const NfTrainCtrl& fin = ctrl[f->exported_launches & 1];
+        f->adam_steps += fin.stop ? fin.iters_run : f->exported_iters;
     }
+    f->exported_launches = -1;
     NF_CUDA(cudaMemsetAsync(f->d_ctrl, 0, 2 * sizeof(NfTrainCtrl), st));
     memset(a, 0, sizeof(*a));
     a->pk = f->d_pk; a->adam_m = f->d_m; a->adam_v = f->d_v;
@@ -778,6 +790,73 @@ int nfisam_flow_train(nf_flow_t* f, const float* data_dev, int64_t n, const nf_t
     int rc = nfisam_flow_train_launch(f, data_dev, n, cfg, stream);
     if (rc != NF_OK) return rc;
     return nfisam_flow_train_finish(f, loss_hist_host, cfg->max_iters, iters_run, stream);
+}
+
+// [packed parameters | loss history (iterations summed over dims in ascending order, like train_finish) | iters_run, status, 0, 0]
+__global__ void nf_export_kernel(const float* __restrict__ pk, int n_packed, const float* __restrict__ loss_part, int d, int iters,
+                                 int hist_len, const NfTrainCtrl* __restrict__ ctrl, int launches, float* __restrict__ dst) {
+    const NfTrainCtrl fin = ctrl[launches & 1];
+    const int ran = fin.stop ? fin.iters_run : iters;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int p = t0; p < n_packed; p += stride) dst[p] = pk[p];
+    bool nan = false;
+    for (int t = t0; t < hist_len; t += stride) {
+        float acc = 0.0f;
+        if (t < ran) {
+            for (int i = 0; i < d; ++i) acc += loss_part[(size_t)t * d + i];
+            if (!(acc == acc) || acc > 3.0e38f || acc < -3.0e38f) nan = true;
+        }
+        dst[n_packed + t] = acc;
+    }
+    float* tail = dst + n_packed + hist_len;
+    if (t0 == 0) { tail[0] = (float)ran; tail[2] = 0.0f; tail[3] = 0.0f; }
+    if (t0 == 0 && fin.status != 0) tail[1] = 1.0f;
+    if (nan) tail[1] = 1.0f;                       // tail[1] was zeroed by the memset that precedes the launch
+}
+
+int nfisam_flow_state_floats(const nf_flow_t* f, int32_t max_iters, int64_t* n_floats) {
+    if (!f || !n_floats || max_iters < 0) return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    *n_floats = f->n_packed + (int64_t)max_iters + 4;
+    return NF_OK;
+}
+
+int nfisam_flow_train_export(nf_flow_t* f, float* dst_dev, int32_t max_iters, void* stream) {
+    if (!f || !dst_dev) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (!f->pending_launches) return nf_set_error(NF_ERR_BAD_ARG, "no training run pending on this handle");
+    if (max_iters < f->pending_iters) return nf_set_error(NF_ERR_BAD_ARG, "max_iters smaller than the pending run's");
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int iters = f->pending_iters, launches = f->pending_launches;
+    NF_CUDA(cudaMemsetAsync(dst_dev + f->n_packed + max_iters, 0, 4 * sizeof(float), st));
+    const int threads = 256;
+    const int work = (int)(f->n_packed > max_iters ? f->n_packed : max_iters);
+    int blocks = (work + threads - 1) / threads;
+    if (blocks > 64) blocks = 64;
+    nf_export_kernel<<<blocks, threads, 0, st>>>(f->d_pk, (int)f->n_packed, f->d_loss_part, f->fd.d, iters, max_iters, f->d_ctrl, launches,
+                                                 dst_dev);
+    nf_count_launch();
+    const int rc = nf_check_launch("nf_export_kernel");
+    f->touch(st);
+    f->exported_iters = iters;
+    f->exported_launches = launches;
+    f->pending_launches = 0;
+    f->pending_iters = 0;
+    return rc;
+}
+
+int nfisam_flow_import_state(nf_flow_t* f, const float* src_dev, void* stream) {
+    if (!f || !src_dev) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (f->pending_launches) return nf_set_error(NF_ERR_BAD_ARG, "a training run is pending on this handle");
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bytes = sizeof(float) * (size_t)f->n_packed;
+    NF_CUDA(cudaMemcpyAsync(f->d_pk, src_dev, bytes, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA(cudaMemsetAsync(f->d_m, 0, bytes, st));
+    NF_CUDA(cudaMemsetAsync(f->d_v, 0, bytes, st));
+    f->adam_steps = 0;
+    f->exported_launches = -1;
+    f->touch(st);
+    return NF_OK;
 }
 
 int nfisam_flow_loss_grad(nf_flow_t* f, const float* data_dev, int64_t n, float* loss_host, float* grad_host,

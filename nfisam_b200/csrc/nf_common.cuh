@@ -10,7 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define NF_MAX_DIM 32
+#define NF_MAX_DIM 32      // = NFISAM_MAX_DIM of the public header (static_assert in nf_capi.cu)
 
 // ---------------------------------------------------------------------------------------------
 // Packed parameter layout (device side).  P = 3K-1 outputs per conditioner, Pp = P rounded up

@@ -75,8 +75,12 @@ class NSF_AR(nn.Module):
         self._base_network = base_network
         self._materialized = False
         self._flat_version = 0
+        self._device_newer = False      # the device handle holds parameters the host mirror has not fetched yet
         if initial_parameters is None:
             self._theta = self._draw_initial_parameters()
+        elif isinstance(initial_parameters, str) and initial_parameters == "device":
+            # parameters will arrive through adopt_state() (a state record of another handle / rank): no random draws
+            self._theta = np.zeros(NSF_AR.num_parameters(dim, K, hidden_dim), np.float32)
         else:
             # parameters received from another rank: no random draws (state_dict order, like load_flat_parameters)
             self._theta = np.ascontiguousarray(initial_parameters, dtype=np.float32).ravel().copy()
@@ -93,6 +97,13 @@ class NSF_AR(nn.Module):
         """Number of scalars in state_dict order (src/flows/flows.py:51-63): init_param + (dim - 1) conditioners."""
         P, H = 3 * K - 1, hidden_dim
         return P + sum(H * i + H + H * H + H + P * H + P for i in range(1, dim))
+
+    @staticmethod
+    def packed_size(dim, K, hidden_dim) -> int:
+        """Floats of the kernels' packed parameter layout (csrc/nf_common.cuh, nf_packed_size): conditioner outputs padded
+        to a multiple of 4.  A device state record (nfisam_flow_state_floats) is packed_size + max_iters + 4 floats."""
+        H, Pp = hidden_dim, ((3 * K - 1) + 3) & ~3
+        return Pp + H * ((dim - 1) * dim // 2) + (dim - 1) * (2 * H + H * H + H * Pp + Pp)
 
     def _shapes(self):
         """(shape, fan_in) of every tensor in state_dict order."""
@@ -132,7 +143,13 @@ class NSF_AR(nn.Module):
             self._theta[:P] = torch.empty(P).uniform_(-0.5, 0.5).numpy()
             self._flat_version += 1
 
+    def _fetch_if_device_newer(self):
+        if self.__dict__.get("_device_newer", False):
+            self._device_newer = False
+            self.pull_parameters()
+
     def _materialize(self):
+        self._fetch_if_device_newer()
         if self._materialized:
             return
         self._materialized = True
@@ -183,6 +200,7 @@ class NSF_AR(nn.Module):
 
     def flat_parameters(self) -> np.ndarray:
         """state_dict order, float32 (the order of the C ABI's parameter vector)."""
+        self._fetch_if_device_newer()
         if not self._materialized:
             return self._theta.copy()
         return np.concatenate([p.detach().cpu().numpy().astype(np.float32).ravel() for p in self._ordered_params()])
@@ -200,6 +218,7 @@ class NSF_AR(nn.Module):
         theta = np.ascontiguousarray(theta, dtype=np.float32).ravel()
         if theta.size != self._theta.size:
             raise ValueError(f"expected {self._theta.size} parameters, got {theta.size}")
+        self._device_newer = False
         if self._materialized:
             self._load_into_modules(theta)
         else:
@@ -222,7 +241,7 @@ class NSF_AR(nn.Module):
             self._h = h
             self._synced = None
         ver = self._param_version()
-        if ver != self._synced:
+        if ver != self._synced and not self._device_newer:
             theta = self.flat_parameters()
             _lib.check(lib.nfisam_flow_set_params(self._h, theta.ctypes.data_as(ctypes.c_void_p), theta.size))
             self._synced = ver
@@ -428,7 +447,38 @@ class NSF_AR(nn.Module):
                                                 ctypes.c_void_p(st.cuda_stream)))
         if pull:
             self.pull_parameters()
+        else:
+            self._synced = self._param_version()
+            self._device_newer = True          # fetched on the first access to the host mirror
         return hist, int(ran.value)
+
+    def state_floats(self, iters) -> int:
+        """Length (floats) of this flow's device state record for runs of up to `iters` iterations."""
+        n = ctypes.c_int64(0)
+        _lib.check(_lib.load().nfisam_flow_state_floats(self.handle(), int(iters), ctypes.byref(n)))
+        return int(n.value)
+
+    def fit_export(self, dst_ptr, iters):
+        """Ends the run started by fit_launch WITHOUT synchronising: the state record (packed parameters, loss history,
+        iterations run, status -- nfisam_flow_train_export) is written to device address dst_ptr on the run's stream.
+        The host mirror of the parameters is refreshed lazily (first access to parameters() / flat_parameters())."""
+        xd, _iters, st, _vd = self._pending
+        _lib.check(_lib.load().nfisam_flow_train_export(self._h, ctypes.c_void_p(dst_ptr), int(iters), ctypes.c_void_p(st.cuda_stream)))
+        self._pending = None
+        self._synced = self._param_version()
+        self._device_newer = True
+        return st
+
+    def adopt_state(self, src_ptr, stream=None):
+        """Loads the parameters of a state record (device address; any handle of the same (dim, K, hidden), e.g. received
+        through an all-gather) into this flow's handle, device to device, asynchronously."""
+        self._device_newer = True              # handle() then only creates the handle: nothing to push
+        h = self.handle()
+        st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
+        _lib.check(_lib.load().nfisam_flow_import_state(h, ctypes.c_void_p(src_ptr), st))
+        self._device_newer = False
+        self._synced = self._param_version()
+        self._device_newer = True
 
     def fit(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
             reset_optimizer=True, pull=True, val=None, validation_interval=10, slower_stop_rate=2.0):

@@ -63,11 +63,18 @@ class BayesTreeNode:
         return node
 
     def deep_copy(self) -> "BayesTreeNode":
-        """Copy of the subtree rooted here (parent link of the copy is None)."""
-        node = self.copy_without_parents_children()
-        for ch in self.children:
-            node.append_child(ch.deep_copy())
-        return node
+        """Copy of the subtree rooted here (parent link of the copy is None).  Iterative: chain-shaped trees are as deep
+        as they have cliques (a 1500-pose trajectory would overflow Python's recursion limit)."""
+        root = self.copy_without_parents_children()
+        stack = [(self, root)]
+        while stack:
+            src, dst = stack.pop()
+            for ch in src.children:
+                cp = ch.copy_without_parents_children()
+                cp.parent = dst
+                dst.children.append(cp)
+                stack.append((ch, cp))
+        return root
 
     def __eq__(self, other) -> bool:
         return isinstance(other, BayesTreeNode) and self.frontal == other.frontal and self.separator == other.separator
@@ -123,18 +130,13 @@ class BayesTree:
         """Cliques grouped by height above the leaves: levels()[0] are cliques without children,
         levels()[h] have all children in lower levels.  Cliques inside one level are mutually
         independent during training -- the unit of the clique-parallel schedule."""
+        cliques = self._walk()                 # breadth first: children come after their parent
         height = {}
-
-        def h(c):
-            if id(c) not in height:
-                height[id(c)] = 0 if c.is_leaf else 1 + max(h(ch) for ch in c.children)
-            return height[id(c)]
-
-        cliques = self._walk()
-        top = h(self.root)
-        out = [[] for _ in range(top + 1)]
+        for c in reversed(cliques):            # ... so every child is done before its parent (no recursion)
+            height[id(c)] = 1 + max(height[id(ch)] for ch in c.children) if c.children else 0
+        out = [[] for _ in range(height[id(self.root)] + 1)]
         for c in cliques:
-            out[h(c)].append(c)
+            out[height[id(c)]].append(c)
         return out
 
     def add_node(self, frontal: Variable, parents: Set[Variable] = None) -> "BayesTree":
@@ -166,16 +168,22 @@ class BayesTree:
         parent_clique.append_child(clique)
         return self
 
-    def append_child_bayes_tree(self, child_tree: "BayesTree") -> "BayesTree":
-        for attach_point in self._walk():
+    def append_child_bayes_tree(self, child_tree: "BayesTree", candidates: List[BayesTreeNode] = None) -> "BayesTree":
+        """Hang `child_tree` below the first clique (breadth-first order, or the given candidate list) that contains its
+        root's separator."""
+        for attach_point in (candidates if candidates is not None else self._walk()):
             if child_tree.root.separator.issubset(attach_point.vars):
                 attach_point.append_child(child_tree.root)
                 break
         return self
 
-    def append_child_bayes_trees(self, child_trees: Iterable["BayesTree"]) -> "BayesTree":
+    def append_child_bayes_trees(self, child_trees: Iterable["BayesTree"], among_current: bool = False) -> "BayesTree":
+        """among_current: only the cliques the tree holds NOW are attach points (the incremental update appends the
+        untouched subtrees of the previous tree to the re-eliminated part: their separators live in that part, and the
+        scan then does not grow with the size of the appended subtrees)."""
+        candidates = self._walk() if among_current else None
         for t in child_trees:
-            self.append_child_bayes_tree(t)
+            self.append_child_bayes_tree(t, candidates)
         return self
 
     def __copy__(self) -> "BayesTree":
@@ -184,33 +192,52 @@ class BayesTree:
             new_tree.reverse_elimination_order = list(self.reverse_elimination_order)
         return new_tree
 
-    def get_affected_vars_and_partial_bayes_trees(self, vars: Set[Variable]) -> Tuple[Set[Variable], List["BayesTree"]]:
-        """Cliques holding one of `vars` as frontal, plus all their ancestors, are affected; every
-        maximal unaffected subtree is returned as its own (copied) tree (BayesTree.py:310-356)."""
+    def frontal_owner_map(self) -> dict:
+        """variable -> the clique that holds it as a frontal variable."""
         owner = {}
         for c in self._walk():
             for v in c.frontal:
                 owner[v] = c
+        return owner
+
+    def get_affected_vars_and_partial_bayes_trees(self, vars: Set[Variable]) -> Tuple[Set[Variable], List["BayesTree"]]:
+        """Cliques holding one of `vars` as frontal, plus all their ancestors, are affected; every
+        maximal unaffected subtree is returned as its own (copied) tree (BayesTree.py:310-356)."""
+        affected_vars, sub_trees, _ = self.split_affected(vars, reuse_nodes=False)
+        return affected_vars, sub_trees
+
+    def split_affected(self, vars: Set[Variable], owner: dict = None, reuse_nodes: bool = True):
+        """The incremental form of the above: (affected variables, untouched subtrees, affected cliques).  `owner` is a
+        frontal_owner_map the caller maintains across steps (None: built here, one walk).  With reuse_nodes the untouched
+        subtrees are DETACHED from this tree and handed over as they are, like the reference's shallow subtree copy
+        (BayesTree.py:336-356): the work per step then scales with the affected part, not with the trajectory length --
+        this tree must not be used afterwards."""
+        if owner is None:
+            owner = self.frontal_owner_map()
         affected = set()
         for v in vars:
             c = owner.get(v)
             while c is not None and id(c) not in affected:
                 affected.add(id(c))
                 c = c.parent
-        affected_vars, sub_trees = set(), []
+        affected_vars, sub_trees, removed = set(), [], []
         stack = [self.root]
         while stack:
             c = stack.pop()
             affected_vars |= c.frontal
+            removed.append(c)
             for ch in c.children:
                 if id(ch) in affected:
                     stack.append(ch)
+                elif reuse_nodes:
+                    ch.parent = None
+                    sub_trees.append(BayesTree(root_clique=ch))
                 else:
                     sub_trees.append(BayesTree(root_clique=ch.deep_copy()))
         if id(self.root) not in affected:
             # nothing touched: the reference still treats the root path as affected via the union below
             affected_vars = set(self.root.frontal)
-        return affected_vars, sub_trees
+        return affected_vars, sub_trees, removed
 
     def clique_variable_pattern(self, clique: BayesTreeNode) -> List[Variable]:
         """[separator variables, frontal variables], each in reverse elimination order (BayesTree.py:358-373)."""

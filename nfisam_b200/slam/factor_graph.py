@@ -11,6 +11,8 @@ class FactorGraph:
         self._vars: List[Variable] = []
         self._factors: List[Factor] = []
         self._var_set: Set[Variable] = set()
+        self._var_index: Dict[Variable, int] = {}         # insertion position of a variable
+        self._incident: Dict[Variable, List[int]] = {}    # variable -> indices of the factors that touch it
         self._adjacency = None            # built lazily: sub-graphs are created far more often than eliminated
 
     vars = property(lambda self: self._vars)
@@ -19,6 +21,8 @@ class FactorGraph:
     def add_node(self, var: Variable) -> "FactorGraph":
         if var in self._var_set:
             raise KeyError("The node has already existed in the graph")
+        self._var_index[var] = len(self._vars)
+        self._incident[var] = []
         self._vars.append(var)
         self._var_set.add(var)
         self._adjacency = None
@@ -28,6 +32,8 @@ class FactorGraph:
         for v in factor.vars:
             if v not in self._var_set:
                 raise KeyError(f"factor touches a variable that is not in the graph: {v.name}")
+        for v in factor.vars:
+            self._incident[v].append(len(self._factors))
         self._factors.append(factor)
         self._adjacency = None
         return self
@@ -84,12 +90,24 @@ class FactorGraph:
         """Factors among `variables` that are not already summarised by an untouched subtree, plus the
         separator factors of those subtrees (FactorGraph.py:204-228)."""
         roots = [t.root.vars for t in sub_trees]
-
-        def keep(f):
+        # only the factors incident to the affected variables are looked at (the physical graph grows with the trajectory,
+        # the affected part does not); variables and factors keep their insertion order, as a scan of the whole graph would
+        candidates = set()
+        for v in variables:
+            candidates.update(self._incident[v])
+        g = FactorGraph()
+        for v in sorted(variables, key=self._var_index.__getitem__):
+            g.add_node(v)
+        for fi in sorted(candidates):
+            f = self._factors[fi]
             fv = set(f.vars)
-            return fv.issubset(variables) and not any(fv.issubset(r) for r in roots)
-
-        return self._subgraph(lambda v: v in variables, keep, [clique_prior_dict[t.root] for t in sub_trees])
+            if fv.issubset(variables) and not any(fv.issubset(r) for r in roots):
+                g.add_factor(f)
+        for t in sub_trees:
+            prior = clique_prior_dict.get(t.root)
+            if prior is not None:
+                g.add_factor(prior)
+        return g
 
     def eliminate_clique_variables(self, clique: BayesTreeNode, new_factor: Factor) -> "FactorGraph":
         """Drop the clique's frontal variables and every factor inside the clique; add its separator

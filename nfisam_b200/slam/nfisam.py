@@ -52,7 +52,7 @@ class NFiSAMArgs(SolverArgs):
                  average_window=50, loss_delta_tol=1e-2, training_set_frac=1.0, validation_interval=10,
                  slower_stop_rate=2.0, data_parallel=False, training_loss_dir=None,
                  clique_parallel: bool = True, deterministic_cliques: bool = False, seed: int = 0, device=None,
-                 device_simulation: bool = True, device_latents: bool = True, *args, **kwargs):
+                 device_simulation: bool = True, device_latents: bool = True, process_group=None, *args, **kwargs):
         super().__init__(elimination_method=elimination_method, posterior_sample_num=posterior_sample_num,
                          local_sample_num=local_sample_num, store_clique_samples=store_clique_samples,
                          local_sampling_method=local_sampling_method, *args, **kwargs)
@@ -82,6 +82,13 @@ class NFiSAMArgs(SolverArgs):
         self.device_simulation = device_simulation          # build clique training sets with the simulator kernel
         self.device_latents = device_latents                # posterior latent draws from the device generator (False:
         #                                                     torch's CPU generator, clique by clique like the reference)
+        # clique-parallel over several GPUs: the torch.distributed group (one process per GPU) whose ranks share the
+        # cliques of a tree level; "world" = the default group.  None (default) = this process alone -- the solver never
+        # picks up a process group the application initialised for something else.
+        self.process_group = process_group
+        # Limit of this implementation (not of the reference): the augmented dimension of a clique (simulated observations +
+        # separator + frontal columns) must not exceed nfisam_b200._lib.NFISAM_MAX_DIM = 32; larger cliques raise a
+        # ValueError that names the clique.
 
 
 class NormalizingFlowModelWithSeparator(NormalizingFlowModel, ConditionalSampler):
@@ -287,6 +294,7 @@ class NFiSAM(FactorGraphSolver):
             raise NotImplementedError("only flow_type='NSF_AR' with flow_number=1 exists in the reference")
         train_size = min(int(samples.shape[0] * a.training_set_frac), samples.shape[0])
         aug_dim = samples.shape[-1]
+        self._check_clique_dim(clique, aug_dim)
         aug_sep_dim = aug_dim - clique.frontal_dim
         circular = []
         for var in var_ordering:
@@ -306,7 +314,7 @@ class NFiSAM(FactorGraphSolver):
         return model, data
 
     def _prepare_clique_model_device(self, clique: BayesTreeNode, sampler, var_ordering: List[Variable], seed: int,
-                                     counter=None):
+                                     counter=None, ms_out=None):
         """Device pipeline of one clique up to the Adam loop ("next" row N1): simulator kernel -> normalisation kernel ->
         float32 training matrix, all enqueued on the current CUDA stream; no host copy of the samples, no
         synchronisation.  Raises NotImplementedError if a factor of the clique has no device simulator."""
@@ -314,6 +322,7 @@ class NFiSAM(FactorGraphSolver):
         if a.flow_number != 1 or a.flow_type != "NSF_AR":
             raise NotImplementedError("only flow_type='NSF_AR' with flow_number=1 exists in the reference")
         n = a.local_sample_num
+        self._check_clique_dim(clique, sum(v.dim for v in var_ordering))
         prog = sampler.program(n, counter, seed)
         flow = NSF_AR(dim=prog.ld, K=a.num_knots, hidden_dim=a.hidden_dim, device=a.device)
         dev = flow._dev()
@@ -335,14 +344,15 @@ class NFiSAM(FactorGraphSolver):
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
 
-        def normalised(rows, row0):
+        def normalised(rows, row0, ms=None):
             data = torch.empty((rows, d), dtype=torch.float32, device=dev)
-            ms = torch.empty(2 * d, dtype=torch.float32, device=dev)
+            if ms is None:
+                ms = torch.empty(2 * d, dtype=torch.float32, device=dev)
             _lib.check(lib.nfisam_normalize_training(s_mat.data_ptr(), rows, d, perm.data_ptr() if perm is not None else None,
                                                      row0, cols, circ, d, data.data_ptr(), ms.data_ptr(), dev_index, st))
             return data, ms
 
-        data, mean_std = normalised(train_size, 0)
+        data, mean_std = normalised(train_size, 0, ms_out)     # ms_out: a caller-owned device slice for mean | std
         # like the reference, the held-out rows are normalised with their OWN statistics (NFiSAM.py:381-384)
         val = normalised(n - train_size, train_size)[0] if train_size < n else None
         aug_sep_dim = d - clique.frontal_dim
@@ -355,6 +365,15 @@ class NFiSAM(FactorGraphSolver):
         if a.store_clique_samples:
             self._clique_samples[clique] = s_mat.cpu().numpy()
         return model, data
+
+    @staticmethod
+    def _check_clique_dim(clique, aug_dim):
+        """The kernels hold per-lane state for at most NFISAM_MAX_DIM flow dimensions (include/nfisam_b200.h)."""
+        if aug_dim > _lib.NFISAM_MAX_DIM:
+            names = " ".join(sorted(str(v.name) for v in clique.vars))
+            raise ValueError(f"clique {{{names}}} needs a flow of dimension {aug_dim} (observations + separator {clique.separator_dim} + "
+                             f"frontal {clique.frontal_dim}); libnfisam_b200 supports at most {_lib.NFISAM_MAX_DIM}. "
+                             "Use an elimination ordering with smaller cliques.")
 
     def _record_loss(self, clique, hist):
         name = "".join(str(v.name) for v in clique.vars)
@@ -379,9 +398,11 @@ class NFiSAM(FactorGraphSolver):
         obs_dim = old.dim - old_clique.dim
         sep_dim = new_clique.separator_dim + obs_dim
         sep_prior = CustomMultivariateNormal(dim=sep_dim) if sep_dim > 0 else None
-        return NormalizingFlowModelWithSeparator(flows=list(old.flows), prior=old.prior, separator_prior=sep_prior,
-                                                 circular_dim_list=old.circular_dim_list,
-                                                 samples_mean=old.samples_mean, samples_std=old.samples_std)
+        new = NormalizingFlowModelWithSeparator(flows=list(old.flows), prior=old.prior, separator_prior=sep_prior,
+                                                circular_dim_list=old.circular_dim_list,
+                                                samples_mean=old.samples_mean, samples_std=old.samples_std)
+        new._norm_cache = old._norm()       # same constants: the flow's device copies stay valid
+        return new
 
     def clique_density_to_separator_factor(self, separator_var_list, density_model, true_obs):
         obs_dim = true_obs.shape[-1]

@@ -6,17 +6,25 @@ schedule:
 
   up-pass    levels of the working tree, leaves first.  All cliques of a level only depend on
              separator factors of lower levels, so they are simulated and trained concurrently:
-             on one GPU every clique's persistent training kernel is enqueued on its own CUDA stream;
-             under torch.distributed (one process per GPU) the cliques of a level are dealt
-             round-robin to the ranks and each owner broadcasts the trained flow (parameters,
-             normalisation, loss curve: a few tens of KB) to the other ranks over NCCL.
-  down-pass  root first: the owner of a clique draws its frontal variables given the separator
-             samples and broadcasts them (n x frontal_dim float32) to the ranks that own the children.
+             on one GPU every clique's pipeline (simulator -> normalisation -> persistent training
+             kernel -> state export) is enqueued on its own CUDA stream; with a process group
+             (one process per GPU, NFiSAMArgs.process_group) the cliques of a level are dealt
+             round-robin to the ranks.  Every owner's kernels write the trained flows (packed
+             parameters, normalisation constants, loss curve: a few tens of KB per clique) into ONE
+             device buffer, ONE all-gather per level hands every rank the whole level, and ONE stream
+             synchronisation per level lets the host read the loss curves.  Nothing is staged
+             through host memory and no clique is waited for individually.
+  down-pass  root first: whole child subtrees of the root are sampled by their owner rank with one
+             fused kernel pass over a device sample matrix; one all-reduce assembles the matrix
+             (the negative-discriminant counter rides in a spare column of it).
 
 There is no collective on the training data path itself (cliques are independent): NCCL only moves
 parameters up and separator samples down, as the north star prescribes.  With
 `deterministic_cliques` every clique seeds its own RNG streams from (seed, step, clique name), which
 makes the result independent of the number of GPUs.
+
+The scheduler never looks at the process-global default group: it is distributed only when the caller
+passed `process_group` explicitly ("world" = torch.distributed.group.WORLD, resolved lazily).
 """
 import ctypes
 import time
@@ -27,6 +35,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..flows import NSF_AR, CustomMultivariateNormal
 from .simulation_sampler import SimulationBasedSampler
 
 
@@ -38,41 +47,77 @@ class CliqueScheduler:
     def __init__(self, solver):
         self.solver = solver
         self._streams = {}
+        self._pinned = None               # grow-only pinned staging buffer (float32) of the level exchange
+        self._pinned_s = None             # ... and of the posterior matrix
 
     # -- distributed plumbing -----------------------------------------------------------------------
+    def _group(self):
+        """The process group the caller handed over (NFiSAMArgs.process_group), or None."""
+        pg = getattr(self.solver._args, "process_group", None)
+        if pg is None:
+            return None
+        import torch.distributed as dist
+
+        if isinstance(pg, str):
+            if pg != "world":
+                raise ValueError("process_group must be None, 'world' or a torch.distributed ProcessGroup")
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("process_group='world' but torch.distributed is not initialised")
+            return dist.group.WORLD
+        return pg
+
     @property
     def distributed(self) -> bool:
+        pg = self._group()
+        if pg is None:
+            return False
         import torch.distributed as dist
 
-        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        return dist.get_world_size(pg) > 1
 
     def _world(self):
+        pg = self._group()
+        if pg is None:
+            return 0, 1
         import torch.distributed as dist
 
-        if self.distributed:
-            return dist.get_rank(), dist.get_world_size()
-        return 0, 1
+        return dist.get_rank(pg), dist.get_world_size(pg)
+
+    def _device(self):
+        """The CUDA device the solver's flows compute on (NFiSAMArgs.device, default: the current device)."""
+        dev = getattr(self.solver._args, "device", None)
+        if dev is None:
+            return torch.device("cuda", torch.cuda.current_device())
+        dev = torch.device(dev) if not isinstance(dev, int) else torch.device("cuda", dev)
+        if dev.type != "cuda":
+            raise ValueError("nfisam_b200 computes on CUDA devices only")
+        return dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _comm_on_cuda(self) -> bool:
+        pg = self._group()
+        if pg is None:
+            return torch.cuda.is_available()
+        import torch.distributed as dist
+
+        return "nccl" in str(dist.get_backend(pg))
 
     def _comm_device(self):
-        import torch.distributed as dist
-
-        if self.distributed and dist.get_backend() == "nccl":
-            return torch.device("cuda", torch.cuda.current_device())
-        return torch.device("cpu")
+        return self._device() if self._comm_on_cuda() else torch.device("cpu")
 
     def _bcast(self, array: np.ndarray, src: int, dtype=torch.float32) -> np.ndarray:
-        """Broadcast a (pre-shaped) array from rank `src`; every rank passes an array of the same shape."""
+        """Broadcast a (pre-shaped) array from group rank `src`; every rank passes an array of the same shape."""
         import torch.distributed as dist
 
+        pg = self._group()
         t = torch.as_tensor(np.ascontiguousarray(array)).to(dtype).to(self._comm_device())
-        dist.broadcast(t, src=src)
+        dist.broadcast(t, src=dist.get_global_rank(pg, src), group=pg)
         return t.cpu().numpy()
 
     def _stream(self, slot: int):
         if not torch.cuda.is_available():
             return None                     # host-logic tests with the oracle backend
-        dev = torch.cuda.current_device()
-        key = (dev, slot)
+        dev = self._device()
+        key = (dev.index, slot)
         if key not in self._streams:
             self._streams[key] = torch.cuda.Stream(device=dev)
         return self._streams[key]
@@ -80,6 +125,13 @@ class CliqueScheduler:
     def _seed_for(self, clique, salt: int) -> int:
         a = self.solver._args
         return (zlib.crc32(_clique_name(clique).encode()) + 7919 * self.solver._step_counter + 104729 * salt + int(a.seed)) % (2 ** 31 - 1)
+
+    def _pinned_f32(self, which: str, count: int):
+        buf = getattr(self, which)
+        if buf is None or buf.numel() < count:
+            buf = torch.empty(max(count, 1 << 16), dtype=torch.float32).pin_memory()
+            setattr(self, which, buf)
+        return buf[:count]
 
     # -- up-pass --------------------------------------------------------------------------------------
     def fit_tree(self, timer: List[float] = None, clique_dim_timer=None):
@@ -89,7 +141,8 @@ class CliqueScheduler:
         reseed = a.deterministic_cliques or world > 1
         s._temp_training_loss = {}
         t_begin = time.time()
-        sim_time, train_time = 0.0, 0.0
+        times = [0.0, 0.0]                  # simulation (enqueue), training (wait)
+        on_device = bool(getattr(a, "device_simulation", False)) and torch.cuda.is_available() and self._comm_on_cuda()
         for level in s._working_bayes_tree.levels():
             todo = [c for c in level if c not in s._clique_density_model]
             plans = {}
@@ -103,74 +156,190 @@ class CliqueScheduler:
                 sampler = SimulationBasedSampler(factors=graph.factors, vars=pattern)
                 _, var_order, true_obs = sampler.plan()
                 plans[id(c)] = (sampler, var_order, true_obs)
-            mine = [(k, c) for k, c in enumerate(todo) if k % world == rank]
-            launched = []
-            on_device = bool(getattr(a, "device_simulation", False)) and torch.cuda.is_available()
-            counter = torch.zeros(1, dtype=torch.int64, device="cuda") if on_device else None
-            t0 = time.time()
-            for slot, (k, c) in enumerate(mine):
-                sampler, var_order, true_obs = plans[id(c)]
-                if reseed:
-                    seed = self._seed_for(c, 1)
-                    np.random.seed(seed)
-                    torch.default_generator.manual_seed(seed)     # the CPU generator only (torch.manual_seed also walks
-                    #                                                 every accelerator backend: 0.3 ms per clique)
-                stream = self._stream(slot)
-                model = None
-                if on_device:
+            if todo:
+                fit = self._fit_level_device if on_device else self._fit_level_host
+                results = fit(todo, plans, reseed, times)
+                for k, c in enumerate(todo):
+                    sampler, var_order, true_obs = plans[id(c)]
+                    model, hist = results[k]
+                    s._clique_true_obs[c] = true_obs
+                    s._record_loss(c, hist)
+                    s._finish_clique(c, model, true_obs, already_eliminated=True)
+            if clique_dim_timer is not None:
+                for c in level:
+                    clique_dim_timer.append([c.dim, time.time() - t_begin])
+        if timer is not None:
+            timer.append(times[0])      # same slots as the reference's [sampler_i, train_i] pairs, aggregated per step
+            timer.append(times[1])
+
+    @staticmethod
+    def _circular(var_order):
+        circular = []
+        for v in var_order:
+            circular += v.circular_dim_list
+        return circular
+
+    def _fit_level_device(self, todo, plans, reseed, times):
+        """One tree level on the device pipeline.  Record of clique k inside its owner's send buffer (float32):
+            [ state record of nfisam_flow_train_export: packed parameters | loss curve | iterations, status, 0, 0 ]
+            [ mean (d) | std (d) ]   written by the normalisation kernel
+        rounded up to 16 bytes; float 0 of a rank's buffer is its negative-discriminant count."""
+        import torch.distributed as dist
+
+        from .nfisam import NormalizingFlowModelWithSeparator
+
+        s = self.solver
+        a = s._args
+        rank, world = self._world()
+        pg = self._group()
+        dev = self._device()
+        iters = int(a.flow_iterations)
+        shapes, offs, per_rank = [], [], [4] * world
+        for k, c in enumerate(todo):
+            circular = self._circular(plans[id(c)][1])
+            d = len(circular)
+            n_state = NSF_AR.packed_size(d, a.num_knots, a.hidden_dim) + iters + 4
+            length = (n_state + 2 * d + 3) & ~3
+            shapes.append((d, circular, n_state, length))
+            offs.append(per_rank[k % world])
+            per_rank[k % world] += length
+        width = max(per_rank)
+        mine = [(k, c) for k, c in enumerate(todo) if k % world == rank]
+        current = torch.cuda.current_stream(dev)
+        gathered = torch.empty(world * width, dtype=torch.float32, device=dev)
+        send = gathered[rank * width:(rank + 1) * width]
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        # circular flags of every clique of the level: one upload
+        circ_all = torch.from_numpy(np.concatenate([np.asarray(sh[1], np.uint8) for sh in shapes])).to(dev, non_blocking=True)
+        circ_off = np.concatenate([[0], np.cumsum([sh[0] for sh in shapes])])
+        t0 = time.time()
+        local = {}
+        used_streams = []
+        for slot, (k, c) in enumerate(mine):
+            sampler, var_order, true_obs = plans[id(c)]
+            d, circular, n_state, length = shapes[k]
+            if reseed:
+                seed = self._seed_for(c, 1)
+                np.random.seed(seed)
+                torch.default_generator.manual_seed(seed)     # the CPU generator only (torch.manual_seed also walks
+                #                                                 every accelerator backend: 0.3 ms per clique)
+            stream = self._stream(slot)
+            stream.wait_stream(current)
+            ms_out = send[offs[k] + n_state: offs[k] + n_state + 2 * d]
+            sim_seed = seed if reseed else int(np.random.randint(0, 2 ** 31 - 1))
+            model = None
+            with torch.cuda.stream(stream):
+                try:
                     # simulator -> normalisation -> training, all on the clique's stream ("next" row N1)
-                    sim_seed = seed if reseed else int(np.random.randint(0, 2 ** 31 - 1))
-                    stream.wait_stream(torch.cuda.current_stream())
-                    try:
-                        with torch.cuda.stream(stream):
-                            model, data = s._prepare_clique_model_device(c, sampler, var_order, sim_seed, counter)
-                    except NotImplementedError:
-                        model = None          # a factor type without a device simulator: host simulation below
+                    model, data = s._prepare_clique_model_device(c, sampler, var_order, sim_seed, counter, ms_out=ms_out)
+                except NotImplementedError:
+                    model = None              # a factor type without a device simulator: host simulation below
                 if model is None:
                     samples, _, _ = sampler.sample(a.local_sample_num)
                     if a.store_clique_samples:
                         s._clique_samples[c] = samples
                     model, data = s._prepare_clique_model(c, samples, var_order)
-                t1 = time.time()
-                sim_time += t1 - t0
-                model.flows[0].fit_launch(data, a.flow_iterations, a.learning_rate, average_window=a.average_window,
-                                          loss_delta_tol=a.loss_delta_tol, stream=stream,
-                                          val=model._validation_data, validation_interval=a.validation_interval,
-                                          slower_stop_rate=a.slower_stop_rate, concurrency=len(mine))
-                launched.append((k, c, model))
-                t0 = time.time()
-            results = {}
+                    ms_out.copy_(torch.cat([torch.as_tensor(model.samples_mean, dtype=torch.float32),
+                                            torch.as_tensor(model.samples_std, dtype=torch.float32)]), non_blocking=True)
             t1 = time.time()
-            for k, c, model in launched:
-                hist, ran = model.flows[0].fit_finish(pull=True)
-                model.pull_normalisation()
+            times[0] += t1 - t0
+            flow = model.flows[0]
+            flow.fit_launch(data, iters, a.learning_rate, average_window=a.average_window, loss_delta_tol=a.loss_delta_tol,
+                            stream=stream, val=model._validation_data, validation_interval=a.validation_interval,
+                            slower_stop_rate=a.slower_stop_rate, concurrency=len(mine))
+            flow.fit_export(send.data_ptr() + 4 * offs[k], iters)
+            local[k] = model
+            used_streams.append(stream)
+            t0 = time.time()
+        t1 = time.time()
+        for stream in used_streams:
+            current.wait_stream(stream)
+        send[0:1].copy_(counter.to(torch.float32))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, send, group=pg)
+        host_t = self._pinned_f32("_pinned", world * width)
+        host_t.copy_(gathered, non_blocking=True)
+        current.synchronize()                                  # the only host wait of the level
+        host = host_t.numpy()
+        times[1] += time.time() - t1
+        if any(host[r * width] != 0.0 for r in range(world)):
+            raise AssertionError("negative discriminant in the inverse spline while sampling a separator factor")
+        out = {}
+        for k, c in enumerate(todo):
+            d, circular, n_state, length = shapes[k]
+            owner = k % world
+            base = owner * width + offs[k]
+            rec = host[base: base + n_state + 2 * d]
+            n_packed = n_state - iters - 4
+            if rec[n_state - 3] != 0.0:
+                raise _lib.NfisamError(_lib.NF_ERR_NAN_LOSS, f"training loss became NaN/inf for clique {_clique_name(c)}")
+            hist = rec[n_packed:n_packed + iters].copy()
+            mean, std = torch.from_numpy(rec[n_state:n_state + d].copy()), torch.from_numpy(rec[n_state + d:n_state + 2 * d].copy())
+            if owner == rank:
+                model = local[k]
+                model.samples_mean, model.samples_std = mean, std
+                model._norm_cache = None
+                model.__dict__.pop("_mean_std_dev", None)
                 model.__dict__.pop("_sim_keep", None)
-                results[k] = (model, hist)
-            if counter is not None and int(counter.item()):
-                raise AssertionError("negative discriminant in the inverse spline while sampling a separator factor")
-            train_time += time.time() - t1
-            if world > 1:
-                results = self._exchange_level(todo, plans, results)
-            for k, c in enumerate(todo):
-                sampler, var_order, true_obs = plans[id(c)]
-                model, hist = results[k]
-                s._clique_true_obs[c] = true_obs
-                s._record_loss(c, hist)
-                s._finish_clique(c, model, true_obs, already_eliminated=True)
-            if clique_dim_timer is not None:
-                for c in level:
-                    clique_dim_timer.append([c.dim, time.time() - t_begin])
-        if timer is not None:
-            timer.append(sim_time)      # same slots as the reference's [sampler_i, train_i] pairs, aggregated per step
-            timer.append(train_time)
+                flow = model.flows[0]
+            else:
+                flow = NSF_AR(dim=d, K=a.num_knots, hidden_dim=a.hidden_dim, device=dev.index, initial_parameters="device")
+                flow.adopt_state(gathered.data_ptr() + 4 * base)
+                sep_dim = d - c.frontal_dim
+                model = NormalizingFlowModelWithSeparator([flow], CustomMultivariateNormal(dim=d),
+                                                          CustomMultivariateNormal(dim=sep_dim) if sep_dim > 0 else None,
+                                                          circular, mean, std)
+            # device views of the normalisation constants (inside the level's buffer, which they keep alive): no upload
+            norm = model._norm()
+            g0 = base + n_state
+            flow.__dict__["_norm_dev"] = {id(norm): (gathered[g0:g0 + d], gathered[g0 + d:g0 + 2 * d],
+                                                     circ_all[circ_off[k]:circ_off[k] + d], norm)}
+            out[k] = (model, hist)
+        return out
 
-    def _exchange_level(self, todo, plans, local):
-        """Every rank ends up with the trained model of every clique of the level: flow parameters, normalisation constants
-        and loss curve of the cliques a rank owns are packed into one float32 vector and ONE all-gather per level moves
-        them (a broadcast per clique was 8 latency-bound collectives + host synchronisations per level)."""
+    def _fit_level_host(self, todo, plans, reseed, times):
+        """One tree level with per-clique host round trips (flow.fit_finish): the path of the CPU-communicator (gloo)
+        tests and of `device_simulation=False`."""
+        s = self.solver
+        a = s._args
+        rank, world = self._world()
+        mine = [(k, c) for k, c in enumerate(todo) if k % world == rank]
+        launched = []
+        t0 = time.time()
+        for slot, (k, c) in enumerate(mine):
+            sampler, var_order, true_obs = plans[id(c)]
+            if reseed:
+                seed = self._seed_for(c, 1)
+                np.random.seed(seed)
+                torch.default_generator.manual_seed(seed)
+            stream = self._stream(slot)
+            samples, _, _ = sampler.sample(a.local_sample_num)
+            if a.store_clique_samples:
+                s._clique_samples[c] = samples
+            model, data = s._prepare_clique_model(c, samples, var_order)
+            t1 = time.time()
+            times[0] += t1 - t0
+            model.flows[0].fit_launch(data, a.flow_iterations, a.learning_rate, average_window=a.average_window,
+                                      loss_delta_tol=a.loss_delta_tol, stream=stream,
+                                      val=model._validation_data, validation_interval=a.validation_interval,
+                                      slower_stop_rate=a.slower_stop_rate, concurrency=len(mine))
+            launched.append((k, c, model))
+            t0 = time.time()
+        results = {}
+        t1 = time.time()
+        for k, c, model in launched:
+            hist, ran = model.flows[0].fit_finish(pull=True)
+            results[k] = (model, hist)
+        times[1] += time.time() - t1
+        if world > 1:
+            results = self._exchange_level_host(todo, plans, results)
+        return results
+
+    def _exchange_level_host(self, todo, plans, local):
+        """Host-staged exchange (CPU communicator): flow parameters, normalisation constants and loss curve of the
+        cliques a rank owns are packed into one float32 vector and ONE all-gather per level moves them."""
         import torch.distributed as dist
 
-        from ..flows import NSF_AR, CustomMultivariateNormal
         from .nfisam import NormalizingFlowModelWithSeparator
 
         s = self.solver
@@ -178,10 +347,7 @@ class CliqueScheduler:
         rank, world = self._world()
         shapes = []                                       # per clique: (d, circular, n_theta, payload length), identical on every rank
         for c in todo:
-            var_order = plans[id(c)][1]
-            circular = []
-            for v in var_order:
-                circular += v.circular_dim_list
+            circular = self._circular(plans[id(c)][1])
             d = len(circular)
             n_theta = NSF_AR.num_parameters(d, a.num_knots, a.hidden_dim)
             shapes.append((d, circular, n_theta, n_theta + 2 * d + a.flow_iterations))
@@ -200,7 +366,7 @@ class CliqueScheduler:
         dev = self._comm_device()
         send = torch.from_numpy(mine).to(dev)
         gathered = [torch.empty(width, dtype=torch.float32, device=dev) for _ in range(world)]
-        dist.all_gather(gathered, send)
+        dist.all_gather(gathered, send, group=self._group())
         rows = [g.cpu().numpy() for g in gathered]
         out = dict(local)
         offs = [0] * world
@@ -224,17 +390,17 @@ class CliqueScheduler:
         """Root -> leaves like FactorGraphSolver.sample_posterior (src/slam/FactorGraphSolver.py:497-550): same
         clique order, but the separator samples never leave the GPU: latent draws from the device generator (or, with
         `device_latents=False`, torch's CPU generator clique by clique like the reference, one upload), ONE call
-        (nfisam_posterior_pass) that enqueues one inverse kernel per clique reading / writing a device sample matrix,
-        one D2H copy of all variables, one discriminant check for the pass.  The per-clique index lists are cached
-        across incremental steps (variables keep their columns).  Under torch.distributed (NCCL) whole subtrees are
-        sampled by their owner rank and one all-reduce assembles the matrix."""
+        (nfisam_posterior_pass) that walks every clique reading / writing a device sample matrix, one D2H copy of all
+        variables (through a pinned staging buffer), one discriminant check for the pass.  The per-clique index lists are
+        cached across incremental steps (variables keep their columns).  With a process group (NCCL) whole subtrees are
+        sampled by their owner rank and ONE all-reduce assembles the matrix and the discriminant counter."""
         import torch.distributed as dist
 
         s = self.solver
         n = s._args.posterior_sample_num
         rank, world = self._world()
         start = time.time()
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = self._device()
         order = []
         stack = [s._physical_bayes_tree.root]
         while stack:
@@ -260,8 +426,9 @@ class CliqueScheduler:
         for clique in order:
             spans.append((width, clique.frontal_dim))
             width += clique.frontal_dim
-        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        dev_index = dev.index
+        current = torch.cuda.current_stream(dev)
+        stream = ctypes.c_void_p(current.cuda_stream)
         lib = _lib.load()
         if seeded or getattr(s._args, "device_latents", False):
             # latent draws from the device generator (Philox keyed by a seed; slot = latent column pair): one launch, no
@@ -290,7 +457,8 @@ class CliqueScheduler:
                     col_of[v] = self.__dict__.get("_posterior_total", 0)
                     self._posterior_total = col_of[v] + v.dim
         total = self.__dict__.get("_posterior_total", 0)
-        S = torch.zeros((n, max(total, 1)), dtype=torch.float32, device=dev)
+        ld_s = total + 1                                  # spare last column: [0, total] carries the discriminant counter
+        S = torch.zeros((n, ld_s), dtype=torch.float32, device=dev)
         old_cache = self.__dict__.get("_gather_cache", {})
         cache = {}
         mine = [k for k, owner in enumerate(owners) if owner == rank or owner < 0]
@@ -322,16 +490,19 @@ class CliqueScheduler:
             it.out_cols_host = ctypes.addressof(entry[3])
             it.norm = entry[6]
         self._gather_cache = cache
-        _lib.check(lib.nfisam_posterior_pass(items, len(mine), zdev.data_ptr(), int(zdev.shape[1]), S.data_ptr(), int(S.shape[1]), n,
+        _lib.check(lib.nfisam_posterior_pass(items, len(mine), zdev.data_ptr(), int(zdev.shape[1]), S.data_ptr(), ld_s, n,
                                              counter.data_ptr(), stream))
+        if world > 1 and rank != 0:     # the redundantly sampled root block is contributed by rank 0 only
+            root_cols = [col_of[v] + j for v in s._physical_bayes_tree.root.frontal for j in range(v.dim)]
+            S[:, root_cols] = 0.0
+        S[0, total:total + 1] = counter.to(torch.float32)
         if world > 1:
-            if rank != 0:     # the redundantly sampled root block is contributed by rank 0 only
-                root_cols = [col_of[v] + j for v in s._physical_bayes_tree.root.frontal for j in range(v.dim)]
-                S[:, root_cols] = 0.0
-            dist.all_reduce(S, op=dist.ReduceOp.SUM)       # x + 0 + ... + 0 is exact: identical on every rank
-            dist.all_reduce(counter, op=dist.ReduceOp.SUM)
-        host = S.cpu().numpy()
-        bad = int(counter.item())
+            dist.all_reduce(S, op=dist.ReduceOp.SUM, group=self._group())       # x + 0 + ... + 0 is exact: identical on every rank
+        stage = self._pinned_f32("_pinned_s", n * ld_s).view(n, ld_s)
+        stage.copy_(S, non_blocking=True)
+        current.synchronize()
+        host = stage.numpy().copy()                      # the staging buffer is reused by the next step
+        bad = int(host[0, total])
         if bad:
             raise AssertionError(f"negative discriminant in the inverse spline for {bad} samples")   # src/flows/utils.py:133
         samples = {v: host[:, col_of[v]:col_of[v] + v.dim] for frontal in frontals for v in frontal}
@@ -341,10 +512,10 @@ class CliqueScheduler:
 
     # -- down-pass, host path (CPU communicator: gloo tests) -------------------------------------------
     def sample_posterior(self, timer: List[float] = None):
-        """Root -> leaves with per-clique seeded latent draws; under torch.distributed the owner of a clique
+        """Root -> leaves with per-clique seeded latent draws; with a process group the owner of a clique
         draws and broadcasts its frontal samples (the separator samples of its children).  Uses the
         device-resident pass whenever the communicator lives on the GPU."""
-        if torch.cuda.is_available() and self._comm_device().type == "cuda" or (torch.cuda.is_available() and not self.distributed):
+        if torch.cuda.is_available() and self._comm_on_cuda():
             return self.sample_posterior_device(timer=timer, seeded=True)
         s = self.solver
         a = s._args

@@ -205,11 +205,17 @@ class SimulationBasedSampler:
         training columns [observations | separator | frontal] in order.  Raises NotImplementedError when a factor has
         no device simulator (the caller then uses `sample`).  Draws the mixtures' multinomial splits from np.random."""
         steps, var_ordering, _ = self.plan()
-        col_of, off = {}, 0
-        for v in var_ordering:
-            col_of[v] = off
+        # Observation columns are assigned by POSITION: two binary factors on the same variable pair produce observation
+        # variables of the same name ('O<var1><var2>', equality is by name), which a dict keyed by Variable would collapse
+        # into one column block (the host `sample` path hstacks and is unaffected).
+        n_obs = len(var_ordering) - len(self.vars)
+        col_of, obs_cols, off = {}, [], 0
+        for k, v in enumerate(var_ordering):
+            if k < n_obs:
+                obs_cols.append(off)
+            else:
+                col_of[v] = off
             off += v.dim
-        obs_cols = [col_of[v] for v in var_ordering[:len(var_ordering) - len(self.vars)]]
         prog = SimProgram(num_samples, col_of, off, counter, seed)
         k_obs = 0
         for st in steps:

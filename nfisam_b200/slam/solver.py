@@ -65,6 +65,7 @@ class FactorGraphSolver:
         self._elimination_ordering = []
         self._reverse_ordering_map = {}
         self._temp_training_loss = {}
+        self._frontal_owner = {}           # variable -> clique of the physical tree that holds it as a frontal variable
 
     # -- accessors (reference names) ---------------------------------------------------------------
     elimination_method = property(lambda self: self._args.elimination_method)
@@ -109,10 +110,13 @@ class FactorGraphSolver:
         tree, and recycle the old root's density model when it became a leaf with unchanged variable
         order (FactorGraphSolver.py:256-358)."""
         start = time.time()
-        old_nodes = set(self.physical_vars)
-        touched = set().union(*[set(f.vars) for f in self._new_factors]) & old_nodes
+        known = self._physical_graph._var_set
+        touched = {v for f in self._new_factors for v in f.vars if v in known}
+        removed = []
         if self._physical_bayes_tree is not None:
-            affected, sub_trees = self._physical_bayes_tree.get_affected_vars_and_partial_bayes_trees(vars=touched)
+            # the previous tree is consumed: its untouched subtrees move into the new tree as they are (shallow, like the
+            # reference), so a step costs O(affected cliques), not O(trajectory length)
+            affected, sub_trees, removed = self._physical_bayes_tree.split_affected(vars=touched, owner=self._frontal_owner)
             self._working_graph = self._physical_graph.get_sub_factor_graph_with_prior(
                 variables=affected, sub_trees=sub_trees, clique_prior_dict=self._implicit_factors)
         else:
@@ -122,9 +126,10 @@ class FactorGraphSolver:
         for factor in self._new_factors:
             self._working_graph.add_factor(factor)
 
-        old_ordering = self._elimination_ordering
+        old_rmap = self._reverse_ordering_map
         self.generate_ordering()
-        working = set(self.working_vars)
+        new_rmap = self._reverse_ordering_map
+        working = self._working_graph._var_set
         self._working_bayes_tree = self._working_graph.get_bayes_tree(
             ordering=[v for v in self._elimination_ordering if v in working])
 
@@ -133,16 +138,20 @@ class FactorGraphSolver:
         for factor in self._new_factors:
             self._physical_graph.add_factor(factor)
         self._physical_bayes_tree = self._working_bayes_tree.__copy__()
-        self._physical_bayes_tree.append_child_bayes_trees(sub_trees)
+        for c in self._physical_bayes_tree._walk():
+            for v in c.frontal:
+                self._frontal_owner[v] = c
+        self._physical_bayes_tree.append_child_bayes_trees(sub_trees, among_current=True)
 
-        physical_cliques = self._physical_bayes_tree.clique_nodes
-        stale = [c for c in list(self._clique_density_model.keys()) if c not in physical_cliques]
-        working_cliques = [(c, c.vars) for c in self._working_bayes_tree.clique_ordering()] if stale else []
+        working_list = self._working_bayes_tree.clique_ordering()
+        working_set = set(working_list)
+        stale = [c for c in removed if c in self._clique_density_model and c not in working_set]
+        working_cliques = [(c, c.vars) for c in working_list] if stale else []
         for old_clique in stale:
             old_vars = old_clique.vars
             for new_clique, new_vars in working_cliques:
-                if old_vars == new_vars and [v for v in old_ordering if v in old_vars] == \
-                        [v for v in self._elimination_ordering if v in new_vars]:
+                # same variables in the same relative elimination order
+                if old_vars == new_vars and sorted(old_vars, key=old_rmap.__getitem__) == sorted(new_vars, key=new_rmap.__getitem__):
                     self._clique_true_obs[new_clique] = self._clique_true_obs[old_clique]
                     if old_clique in self._clique_variable_pattern:
                         self._clique_variable_pattern[new_clique] = self._clique_variable_pattern[old_clique]
@@ -158,7 +167,8 @@ class FactorGraphSolver:
                     self._working_graph = self._working_graph.eliminate_clique_variables(clique=new_clique, new_factor=new_factor)
                     break
         for old_clique in stale:
-            for table in (self._clique_density_model, self._clique_true_obs, self._clique_variable_pattern, self._clique_samples):
+            for table in (self._clique_density_model, self._clique_true_obs, self._clique_variable_pattern, self._clique_samples,
+                          self._implicit_factors):
                 table.pop(old_clique, None)
         self._new_nodes, self._new_factors = [], []
         if timer is not None:

@@ -18,3 +18,15 @@
 #include "nsf_oracle_impl.h"
 #undef REAL
 #undef SUFFIX
+
+/* Thread count of the OpenMP loops (bench.py sets it explicitly: torchrun exports OMP_NUM_THREADS=1).  Returns the
+ * count in effect. */
+#ifdef _OPENMP
+#include <omp.h>
+int nsf_set_num_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+int nsf_set_num_threads(int n) { (void)n; return 1; }
+#endif

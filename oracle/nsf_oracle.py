@@ -50,6 +50,11 @@ def _sfx(dtype):
     raise TypeError(dtype)
 
 
+def set_num_threads(n):
+    """Sets the OpenMP thread count of the C loops; returns the count in effect."""
+    return int(lib().nsf_set_num_threads(int(n)))
+
+
 def num_params(d, K, H):
     return int(lib().nsf_num_params_f32(int(d), int(K), int(H)))
 

@@ -26,6 +26,11 @@ from slam.RunBatch import graph_file_parser, group_nodes_factors_incrementally  
 from factors.Factors import BinaryFactorMixture  # noqa: E402
 
 ITERS = int(os.environ.get("GOLDEN_ITERS", "600"))
+# settings of example/slam/manhattan_world_with_range/manhattan_plaza/run_nfisam.py:5-10, 42-46 (lr .01, 500 iterations,
+# loss_delta_tol 1e-9 = no early stop) for the reference's own 136-pose ambiguous-association graph
+PLAZA = dict(num_knots=9, flow_iterations=500, local_sample_num=2000, learning_rate=.01, hidden_dim=8, cuda_training=False,
+             elimination_method="pose_first", data_parallel=False, training_set_frac=1.0, loss_delta_tol=1e-9, average_window=50,
+             posterior_sample_num=500)
 
 
 def run(case, seed=0):
@@ -34,9 +39,12 @@ def run(case, seed=0):
     torch.manual_seed(seed)
     nodes, truth, factors = graph_file_parser(os.path.join(HERE, "..", "data", case + ".fg"), "fg", 0.1)
     steps = group_nodes_factors_incrementally(nodes=nodes, factors=factors, incremental_step=1)
-    args = NFiSAMArgs(num_knots=9, flow_iterations=ITERS, local_sample_num=2000, learning_rate=.025, hidden_dim=8,
-                      cuda_training=False, elimination_method="pose_first", training_set_frac=1.0, loss_delta_tol=.01,
-                      posterior_sample_num=1000)
+    if case.startswith("manhattan_plaza"):
+        args = NFiSAMArgs(**PLAZA)
+    else:
+        args = NFiSAMArgs(num_knots=9, flow_iterations=ITERS, local_sample_num=2000, learning_rate=.025, hidden_dim=8,
+                          cuda_training=False, elimination_method="pose_first", training_set_frac=1.0, loss_delta_tol=.01,
+                          posterior_sample_num=1000)
     solver = NFiSAM(args)
     out = {"truth": np.concatenate([truth[v] for v in nodes]), "names": np.array([v.name for v in nodes])}
     mixtures = []

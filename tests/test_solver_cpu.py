@@ -147,7 +147,8 @@ nodes, truth, factors = make_manhattan_range_graph(robots=2, poses=3, landmarks=
 steps = group_nodes_factors_incrementally(nodes, factors, incremental_step=1)
 with oracle_backend():
     solver = NFiSAM(NFiSAMArgs(num_knots=5, flow_iterations=12, local_sample_num=200, posterior_sample_num=64,
-                               deterministic_cliques=True, seed=5))
+                               deterministic_cliques=True, seed=5, process_group="world" if world > 1 else None))
+    assert solver._scheduler.distributed == (world > 1)
     for sn, sf in steps:
         for v in sn: solver.add_node(v)
         for f in sf: solver.add_factor(f)
@@ -160,6 +161,26 @@ np.save({out!r} + f"_w{{world}}_r{{rank}}.npy", x)
 if world > 1:
     dist.destroy_process_group()
 """
+
+
+def test_scheduler_ignores_a_foreign_default_process_group():
+    """The solver only runs distributed on a process group it was handed (NFiSAMArgs.process_group): a default group the
+    application initialised for something else (round 1: bench.py's) must not pull collectives into a solve."""
+    import torch.distributed as dist
+
+    from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29741", rank=0, world_size=1)
+    try:
+        solver = NFiSAM(NFiSAMArgs())
+        assert not solver._scheduler.distributed and solver._scheduler._world() == (0, 1)
+        assert NFiSAM(NFiSAMArgs(process_group="world"))._scheduler._world() == (0, 1)
+        with pytest.raises(ValueError):
+            NFiSAM(NFiSAMArgs(process_group="default"))._scheduler._group()
+    finally:
+        dist.destroy_process_group()
+    with pytest.raises(RuntimeError):
+        NFiSAM(NFiSAMArgs(process_group="world"))._scheduler._group()
 
 
 def test_two_rank_gloo_schedule_matches_single_process(tmp_path):
@@ -177,3 +198,51 @@ def test_two_rank_gloo_schedule_matches_single_process(tmp_path):
     assert np.array_equal(r0, r1)
     assert r0.shape == single.shape
     assert np.allclose(r0, single, rtol=0, atol=1e-5)
+
+
+def test_duplicate_pair_observations_get_distinct_columns():
+    """Two binary factors on the same variable pair yield observation variables of the same name; the device op list must
+    still give every simulated observation its own column block, in the order `sample()` stacks them (round-1 advisor
+    finding: both landed on one block and overwrote a variable's columns)."""
+    from nfisam_b200 import _lib
+    from nfisam_b200.factors import SE2RelativeGaussianLikelihoodFactor as Odo
+    from nfisam_b200.factors import UnarySE2ApproximateGaussianPriorFactor as Prior
+    from nfisam_b200.factors.geometry import SE2Pose
+    from nfisam_b200.slam.simulation_sampler import SimulationBasedSampler
+
+    v = _vars(["X0", "X1"])
+    cov = np.diag([.04, .04, .001])
+    factors = [Prior(v["X0"], SE2Pose(0.0, 0.0, 0.0), cov)] + [Odo(v["X0"], v["X1"], SE2Pose(1.0 + k, 0.0, 0.1 * k), cov) for k in range(3)]
+    sampler = SimulationBasedSampler(factors=factors, vars=[v["X0"], v["X1"]])
+    steps, var_order, obs = sampler.plan()
+    assert [st[0] for st in steps] == ["prior", "gen", "obs", "obs"] and len(obs) == 6
+    prog = sampler.program(16, None, seed=1)
+    outs = [(op.type, op.out) for op in prog.ops]
+    assert outs == [(_lib.NF_SIM_SE2_PRIOR, 6), (_lib.NF_SIM_SE2_GEN_FWD, 9), (_lib.NF_SIM_SE2_OBS, 0), (_lib.NF_SIM_SE2_OBS, 3)]
+    assert prog.ld == 12
+    np.random.seed(0)
+    samples, order2, _ = sampler.sample(16)
+    assert samples.shape == (16, 12) and [x.name for x in order2[2:]] == ["X0", "X1"]
+
+
+def test_deep_chain_tree_needs_no_recursion():
+    """Chain-shaped Bayes trees are as deep as the trajectory is long: levels(), __copy__ and the subtree hand-over of the
+    incremental update must not recurse (round-1 advisor finding: RecursionError at ~1000 cliques)."""
+    from nfisam_b200.slam.bayes_tree import BayesTree, BayesTreeNode
+
+    n = 3000
+    v = _vars([f"X{k}" for k in range(n)])
+    root = BayesTreeNode(frontal={v[f"X{n - 1}"]})
+    node = root
+    for k in range(n - 2, -1, -1):
+        node = node.create_child(v[f"X{k}"], {v[f"X{k + 1}"]})
+    tree = BayesTree(root_clique=root)
+    levels = tree.levels()
+    assert len(levels) == n and all(len(lv) == 1 for lv in levels) and levels[0][0] is node
+    copy = tree.__copy__()
+    assert len(copy._walk()) == n and copy.root is not root
+    owner = tree.frontal_owner_map()
+    affected, subs, removed = tree.split_affected({v[f"X{n - 2}"]}, owner=owner)
+    assert {x.name for x in affected} == {f"X{n - 1}", f"X{n - 2}"} and len(removed) == 2
+    assert len(subs) == 1 and subs[0].root.parent is None and v[f"X{n - 3}"] in subs[0].root.frontal    # handed over, not copied
+    assert subs[0].root is owner[v[f"X{n - 3}"]]
