@@ -75,6 +75,10 @@ int nfisam_flow_num_params(const nf_flow_t* f, int64_t* n);
 /* Host vectors in state_dict order; synchronous. Setting parameters resets the Adam state. */
 int nfisam_flow_set_params(nf_flow_t* f, const float* theta_host, int64_t n);
 int nfisam_flow_get_params(const nf_flow_t* f, float* theta_host, int64_t n);
+/* Asynchronous set_params: theta_host is consumed before the call returns (repacked into pinned staging memory), the
+ * upload is enqueued on `stream` and nothing synchronises -- a scheduler creating one flow per clique does not wait for
+ * the device.  Later work on other streams must be ordered after `stream` by the caller. */
+int nfisam_flow_set_params_async(nf_flow_t* f, const float* theta_host, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Forward / log-prob / inverse
@@ -129,7 +133,9 @@ int nfisam_flow_set_bad_counter(nf_flow_t* f, unsigned long long* counter_dev);
  *   given column j (j < sep_dim)  = S[:, sep_cols[j]]  if sep_cols[j] >= 0, else the constant sep_const[j]
  *                                   (the clique's observation vector, which the reference tiles, :518-526);
  *   generated column c (c < out_dim) is written to S[:, out_cols[c]];
- *   latent draws are z_dev[:, z_col0 .. z_col0 + out_dim) of a (n, ld_z) matrix.
+ *   latent draws are z_dev[:, z_col0 .. z_col0 + out_dim) of a (n, ld_z) matrix; z_col0 = -1: the latent matrix has the
+ *   column layout of S, the draw of generated column c is z_dev[:, out_cols[c]] (lets a scheduler keep per-clique items
+ *   unchanged across incremental steps).
  * The index lists are host arrays (they travel as kernel parameters).  Asynchronous on `stream`. */
 int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z_col0, float* s_dev, int ld_s,
                                const int32_t* sep_cols_host, const float* sep_const_host, int sep_dim,

@@ -113,6 +113,7 @@ SYMBOLS = {
     "nfisam_flow_num_params": (_INT, [_P, ctypes.POINTER(_I64)]),
     "nfisam_flow_set_params": (_INT, [_P, _P, _I64]),
     "nfisam_flow_get_params": (_INT, [_P, _P, _I64]),
+    "nfisam_flow_set_params_async": (_INT, [_P, _P, _I64, _P]),
     "nfisam_flow_forward": (_INT, [_P, _P, _I64, _INT, _P, _P, _INT, _P, _P]),
     "nfisam_flow_log_prob": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "nfisam_flow_inverse": (_INT, [_P, _P, _P, _I64, _INT, _INT, _P, _P, ctypes.POINTER(nf_affine), _P]),

@@ -79,7 +79,16 @@ struct nf_flow {
     float* d_grad = nullptr;
     int adam_steps = 0;
     unsigned long long* d_bad = nullptr;
+    bool bad_ready = false;                    // d_bad is zeroed on the stream of its first use (create does not touch the device)
     unsigned long long* d_bad_ext = nullptr;   // caller-owned counter (nfisam_flow_set_bad_counter)
+    unsigned long long* bad_counter(cudaStream_t st) {
+        if (d_bad_ext) return d_bad_ext;
+        if (!bad_ready) {
+            cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st);
+            bad_ready = true;
+        }
+        return d_bad;
+    }
     // training scratch
     float* d_loss_part = nullptr;
     size_t loss_part_cap = 0;
@@ -287,13 +296,10 @@ int nfisam_flow_create(int dim, int K, int hidden, float tail_bound, int device,
     f->d_ctrl = reinterpret_cast<NfTrainCtrl*>(q); q += up(2 * sizeof(NfTrainCtrl));
     f->d_norm = reinterpret_cast<float*>(q); q += up(2 * sizeof(float) * dim);
     f->d_circ = q;
-    cudaError_t e = cudaMemsetAsync(base, 0, total, cudaStreamLegacy);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);     // zeros are in place before any stream uses the handle
-    if (e != cudaSuccess) {
-        int rc = nf_cuda_fail(e, "flow_create initialisation");
-        nfisam_flow_destroy(f);
-        return rc;
-    }
+    // No device work here: the parameters arrive through set_params / import_state, the Adam state and the control record
+    // are zeroed by every training launch, the discriminant counter on the stream of its first use.  (A memset +
+    // synchronisation on the legacy stream at this point stalled the host for milliseconds per clique whenever other
+    // cliques' training kernels filled the SMs.)
     *out = f;
     return NF_OK;
 }
@@ -319,18 +325,33 @@ int nfisam_flow_num_params(const nf_flow_t* f, int64_t* n) {
     return NF_OK;
 }
 
-int nfisam_flow_set_params(nf_flow_t* f, const float* theta_host, int64_t n) {
+int nfisam_flow_set_params_async(nf_flow_t* f, const float* theta_host, int64_t n, void* stream) {
     if (!f || !theta_host) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
     if (n != f->n_theta) return nf_set_error(NF_ERR_BAD_ARG, "expected %lld parameters, got %lld", (long long)f->n_theta, (long long)n);
-    std::vector<float> pk((size_t)f->n_packed, 0.0f);
-    for (int64_t p = 0; p < f->n_packed; ++p)
-        if (f->pk2th[p] >= 0) pk[p] = theta_host[f->pk2th[p]];
+    if (f->pending_launches) return nf_set_error(NF_ERR_BAD_ARG, "a training run is pending on this handle");
     DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
     const size_t bytes = sizeof(float) * (size_t)f->n_packed;
-    NF_CUDA(cudaMemcpy(f->d_pk, pk.data(), bytes, cudaMemcpyHostToDevice));
-    NF_CUDA(cudaMemset(f->d_m, 0, bytes));
-    NF_CUDA(cudaMemset(f->d_v, 0, bytes));
+    // repacked into a pinned staging block: the copy is a real asynchronous DMA and theta_host is consumed on return
+    float* pk = static_cast<float*>(nf_pinned_alloc(f->device, bytes));
+    if (!pk) return nf_set_error(NF_ERR_OOM, "pinned host allocation of %zu bytes failed", bytes);
+    for (int64_t p = 0; p < f->n_packed; ++p) pk[p] = f->pk2th[p] >= 0 ? theta_host[f->pk2th[p]] : 0.0f;
+    cudaError_t e = cudaMemcpyAsync(f->d_pk, pk, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->d_m, 0, bytes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->d_v, 0, bytes, st);
+    f->touch(st);
+    nf_pinned_free(f->device, pk, f->last_op);
+    if (e != cudaSuccess) return nf_cuda_fail(e, "nfisam_flow_set_params_async");
     f->adam_steps = 0;
+    f->exported_launches = -1;
+    return NF_OK;
+}
+
+int nfisam_flow_set_params(nf_flow_t* f, const float* theta_host, int64_t n) {
+    const int rc = nfisam_flow_set_params_async(f, theta_host, n, cudaStreamLegacy);
+    if (rc != NF_OK) return rc;
+    DeviceGuard g(f->device);
+    NF_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     return NF_OK;
 }
 
@@ -385,7 +406,7 @@ int nfisam_flow_inverse(nf_flow_t* f, const float* z_dev, const float* x_sep_dev
     }
     DeviceGuard g(f->device);
     const int rc = nf_launch_inverse(f->fd, f->d_pk, z_dev, x_sep_dev, n, sep_dim, out_dim, x_out_dev, logdet_dev, mean, stdv, circ,
-                                     f->d_bad_ext ? f->d_bad_ext : f->d_bad, f->device, (cudaStream_t)stream);
+                                     f->bad_counter((cudaStream_t)stream), f->device, (cudaStream_t)stream);
     f->touch((cudaStream_t)stream);
     return rc;
 }
@@ -402,7 +423,10 @@ int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z
             return nf_set_error(NF_ERR_BAD_ARG, "given column %d out of range / constant missing", j);
     for (int c = 0; c < out_dim; ++c)
         if (out_cols_host[c] < 0 || out_cols_host[c] >= ld_s) return nf_set_error(NF_ERR_BAD_ARG, "output column %d out of range", c);
-    if (z_col0 < 0 || z_col0 + out_dim > ld_z) return nf_set_error(NF_ERR_BAD_ARG, "latent columns out of range");
+    if (z_col0 < -1 || z_col0 + out_dim > ld_z) return nf_set_error(NF_ERR_BAD_ARG, "latent columns out of range");
+    if (z_col0 == -1)
+        for (int c = 0; c < out_dim; ++c)
+            if (out_cols_host[c] >= ld_z) return nf_set_error(NF_ERR_BAD_ARG, "z_col0 = -1: output column %d outside the latent matrix", c);
     const float* mean = nullptr; const float* stdv = nullptr; const uint8_t* circ = nullptr;
     if (norm) {
         if (!norm->mean_dev || !norm->std_dev || !norm->circular_dev) return nf_set_error(NF_ERR_BAD_ARG, "incomplete nf_affine");
@@ -410,7 +434,7 @@ int nfisam_flow_inverse_gather(nf_flow_t* f, const float* z_dev, int ld_z, int z
     }
     DeviceGuard g(f->device);
     const int rc = nf_launch_inverse_gather(f->fd, f->d_pk, z_dev, ld_z, z_col0, s_dev, ld_s, sep_cols_host, sep_const_host, sep_dim,
-                                            out_cols_host, out_dim, n, mean, stdv, circ, f->d_bad_ext ? f->d_bad_ext : f->d_bad,
+                                            out_cols_host, out_dim, n, mean, stdv, circ, f->bad_counter((cudaStream_t)stream),
                                             f->device, (cudaStream_t)stream);
     f->touch((cudaStream_t)stream);
     return rc;
@@ -432,7 +456,10 @@ int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float*
         if (it.sep_dim < 0 || it.out_dim < 1 || it.sep_dim + it.out_dim > f->fd.d)
             return nf_set_error(NF_ERR_BAD_ARG, "item %d: bad sep_dim / out_dim", k);
         if (it.sep_dim > 0 && !it.sep_cols_host) return nf_set_error(NF_ERR_BAD_ARG, "item %d: sep_cols_host is NULL", k);
-        if (it.z_col0 < 0 || it.z_col0 + it.out_dim > ld_z) return nf_set_error(NF_ERR_BAD_ARG, "item %d: latent columns out of range", k);
+        if (it.z_col0 < -1 || it.z_col0 + it.out_dim > ld_z) return nf_set_error(NF_ERR_BAD_ARG, "item %d: latent columns out of range", k);
+        if (it.z_col0 == -1)
+            for (int c = 0; c < it.out_dim; ++c)
+                if (it.out_cols_host[c] >= ld_z) return nf_set_error(NF_ERR_BAD_ARG, "item %d: z_col0 = -1 but output column %d is outside the latent matrix", k, c);
         const bool any = it.norm.mean_dev || it.norm.std_dev || it.norm.circular_dev;
         if (any && !(it.norm.mean_dev && it.norm.std_dev && it.norm.circular_dev))
             return nf_set_error(NF_ERR_BAD_ARG, "item %d: incomplete nf_affine", k);
@@ -566,6 +593,11 @@ int nfisam_flow_pop_bad_count(nf_flow_t* f, void* stream, int64_t* count) {
     if (!f || !count) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
     DeviceGuard g(f->device);
     unsigned long long h = 0;
+    if (!f->bad_ready) {                     // the internal counter was never used
+        NF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        *count = 0;
+        return NF_OK;
+    }
     NF_CUDA(cudaMemcpyAsync(&h, f->d_bad, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     NF_CUDA(cudaMemsetAsync(f->d_bad, 0, sizeof(h), (cudaStream_t)stream));
     NF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -638,6 +670,10 @@ int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_s
         NF_CUDA(cudaMemcpyAsync(f->d_circ, circular_host, d, cudaMemcpyHostToDevice, f->streams[0]));
         NF_CUDA(cudaStreamSynchronize(f->streams[0]));
     }
+    if (!f->d_bad_ext && !f->bad_ready) {          // both pipeline streams add to the counter: zero it before either runs
+        f->bad_counter(f->streams[0]);
+        NF_CUDA(cudaStreamSynchronize(f->streams[0]));
+    }
     const int64_t chunk = n < (1 << 20) ? (n + 1) / 2 > 0 ? (n + 1) / 2 : 1 : (1 << 20);
     if ((rc = ensure_cap(f, f->d_stage_in, &f->stage_in_cap, (size_t)chunk * d)) != NF_OK) return rc;
     if ((rc = ensure_cap(f, f->d_stage_aux, &f->stage_aux_cap, (size_t)chunk * d)) != NF_OK) return rc;
@@ -652,14 +688,14 @@ int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_s
                                     cudaMemcpyHostToDevice, st));
         rc = nf_launch_inverse(f->fd, f->d_pk, f->d_stage_in[s], sep_dim > 0 ? f->d_stage_aux[s] : nullptr, m, sep_dim,
                                out_dim, f->d_stage_out[s], nullptr, has_norm ? f->d_norm : nullptr, has_norm ? f->d_norm + d : nullptr,
-                               has_norm ? f->d_circ : nullptr, f->d_bad, f->device, st);
+                               has_norm ? f->d_circ : nullptr, f->bad_counter(st), f->device, st);
         if (rc != NF_OK) return rc;
         NF_CUDA(cudaMemcpyAsync(x_out_host + o * fr, f->d_stage_out[s], sizeof(float) * (size_t)m * fr, cudaMemcpyDeviceToHost, st));
     }
     NF_CUDA(cudaStreamSynchronize(f->streams[0]));
     NF_CUDA(cudaStreamSynchronize(f->streams[1]));
     unsigned long long h = 0;
-    NF_CUDA(cudaMemcpy(&h, f->d_bad, sizeof(h), cudaMemcpyDeviceToHost));
+    if (f->bad_ready && !f->d_bad_ext) NF_CUDA(cudaMemcpy(&h, f->d_bad, sizeof(h), cudaMemcpyDeviceToHost));
     if (h) {
         cudaMemset(f->d_bad, 0, sizeof(h));
         return nf_set_error(NF_ERR_NEG_DISCRIMINANT, "%llu samples hit a negative discriminant in the inverse spline", h);

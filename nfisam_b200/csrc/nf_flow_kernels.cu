@@ -196,7 +196,7 @@ nf_inverse_kernel(const float* __restrict__ pk, int w_first, int wcount, int d, 
         }
         for (int t = threadIdx.x; t < cnt * f; t += TPB) {
             const int r = t / f, c = t - r * f;
-            zs[r * dp + c] = GATHER ? zin[(s0 + r) * ga.ld_z + ga.z_col0 + c] : zin[s0 * f + t];
+            zs[r * dp + c] = GATHER ? zin[(s0 + r) * ga.ld_z + (ga.z_col0 >= 0 ? ga.z_col0 + c : ga.out_cols[c])] : zin[s0 * f + t];
         }
         __syncthreads();
         if (threadIdx.x < cnt) {
@@ -320,11 +320,11 @@ nf_posterior_pass_kernel(const NfPassItem* __restrict__ items, const int2* __res
                 for (int u = 0; u < 8; ++u)
                     if (c0 + u < sep) xrow[c0 + u] = v[u];
             }
-            const float* zr = zin + row * ld_z + z0;
+            const float* zr = zin + row * ld_z;            // z_col0 < 0: the latent matrix shares the sample matrix's column layout
             for (int c0 = 0; c0 < f; c0 += 8) {
                 float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = c0 + u < f ? __ldg(zr + c0 + u) : 0.0f;
+                for (int u = 0; u < 8; ++u) v[u] = c0 + u < f ? __ldg(zr + (z0 >= 0 ? z0 + c0 + u : it.out_cols[c0 + u])) : 0.0f;
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
                     if (c0 + u < f) zrow[c0 + u] = v[u];

@@ -132,4 +132,6 @@ typedef std::shared_ptr<NfEvent> NfEventRef;
 NfEventRef nf_event_record(int device, cudaStream_t st);          // nullptr when the event could not be recorded
 void* nf_pool_alloc(int device, size_t bytes);                    // current device must be `device`; nullptr = out of memory
 void nf_pool_free(int device, void* p, NfEventRef after);         // reusable once `after` has completed (nullptr: at once)
+void* nf_pinned_alloc(int device, size_t bytes);                  // pinned host staging blocks, same reuse rule
+void nf_pinned_free(int device, void* p, NfEventRef after);
 

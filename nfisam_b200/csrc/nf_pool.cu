@@ -35,6 +35,7 @@ struct DevPool {
     size_t idle_bytes = 0;
 };
 DevPool g_pools[MAX_DEV];
+DevPool g_pinned[MAX_DEV];                           // pinned host staging blocks (cudaMallocHost), same reuse rule
 
 void drain_retired(DevPool& pool) {
     for (size_t k = 0; k < pool.retired.size();) {
@@ -85,10 +86,28 @@ NfEventRef nf_event_record(int device, cudaStream_t st) {
     return ref;
 }
 
+static void* pool_alloc(DevPool& pool, size_t bytes, bool pinned);
+static void pool_free(DevPool& pool, void* p, NfEventRef after, bool pinned);
+
 void* nf_pool_alloc(int device, size_t bytes) {
     if (device < 0 || device >= MAX_DEV) return nullptr;
+    return pool_alloc(g_pools[device], bytes, false);
+}
+void nf_pool_free(int device, void* p, NfEventRef after) {
+    if (!p || device < 0 || device >= MAX_DEV) return;
+    pool_free(g_pools[device], p, std::move(after), false);
+}
+void* nf_pinned_alloc(int device, size_t bytes) {
+    if (device < 0 || device >= MAX_DEV) return nullptr;
+    return pool_alloc(g_pinned[device], bytes, true);
+}
+void nf_pinned_free(int device, void* p, NfEventRef after) {
+    if (!p || device < 0 || device >= MAX_DEV) return;
+    pool_free(g_pinned[device], p, std::move(after), true);
+}
+
+static void* pool_alloc(DevPool& pool, size_t bytes, bool pinned) {
     const size_t cap = ((bytes ? bytes : 1) + GRAIN - 1) / GRAIN * GRAIN;
-    DevPool& pool = g_pools[device];
     std::lock_guard<std::mutex> lk(pool.mu);
     drain_retired(pool);
     auto it = pool.ready.lower_bound(cap);
@@ -100,14 +119,15 @@ void* nf_pool_alloc(int device, size_t bytes) {
         return p;
     }
     void* p = nullptr;
-    if (cudaMalloc(&p, cap) != cudaSuccess) {
+    auto raw_alloc = [&](void** q) { return pinned ? cudaMallocHost(q, cap) : cudaMalloc(q, cap); };
+    if (raw_alloc(&p) != cudaSuccess) {
         cudaGetLastError();
         // give cached blocks back to the driver and retry once
-        for (auto& kv : pool.ready) cudaFree(kv.second);
+        for (auto& kv : pool.ready) { if (pinned) cudaFreeHost(kv.second); else cudaFree(kv.second); }
         pool.ready.clear();
         pool.idle_bytes = 0;
         for (const Retired& r : pool.retired) pool.idle_bytes += r.cap;
-        if (cudaMalloc(&p, cap) != cudaSuccess) {
+        if (raw_alloc(&p) != cudaSuccess) {
             cudaGetLastError();
             return nullptr;
         }
@@ -116,16 +136,19 @@ void* nf_pool_alloc(int device, size_t bytes) {
     return p;
 }
 
-void nf_pool_free(int device, void* p, NfEventRef after) {
-    if (!p || device < 0 || device >= MAX_DEV) return;
-    DevPool& pool = g_pools[device];
+static void pool_free(DevPool& pool, void* p, NfEventRef after, bool pinned) {
     std::lock_guard<std::mutex> lk(pool.mu);
     auto it = pool.live.find(p);
     if (it == pool.live.end()) return;               // not ours
     const size_t cap = it->second;
     pool.live.erase(it);
     if (pool.idle_bytes + cap > POOL_LIMIT) {
-        cudaFree(p);                                 // synchronises the device: safe whatever is still in flight
+        if (pinned) {
+            if (after) cudaEventSynchronize(after->ev);
+            cudaFreeHost(p);
+        } else {
+            cudaFree(p);                             // synchronises the device: safe whatever is still in flight
+        }
         cudaGetLastError();
         return;
     }

@@ -243,7 +243,8 @@ class NSF_AR(nn.Module):
         ver = self._param_version()
         if ver != self._synced and not self._device_newer:
             theta = self.flat_parameters()
-            _lib.check(lib.nfisam_flow_set_params(self._h, theta.ctypes.data_as(ctypes.c_void_p), theta.size))
+            # asynchronous on the device's current stream (the stream every other entry point of this class uses)
+            _lib.check(lib.nfisam_flow_set_params_async(self._h, theta.ctypes.data_as(ctypes.c_void_p), theta.size, self._stream()))
             self._synced = ver
         return self._h
 

@@ -386,14 +386,56 @@ class CliqueScheduler:
         return out
 
     # -- down-pass: device-resident -------------------------------------------------------------------
+    def _pass_entry(self, clique, col_of, share_z):
+        """Descriptor of one clique of the down-pass, built once per clique node and kept until the node leaves the tree:
+        the columns of a variable and (when the latent matrix shares the sample matrix's layout) of its latent draws are
+        fixed for the life of the solver, so a clique that an incremental step did not touch keeps its descriptor."""
+        s = self.solver
+        rmap = s._reverse_ordering_map
+        model = s._clique_density_model[clique]
+        frontal = sorted(clique.frontal, key=rmap.__getitem__)
+        separator = sorted(clique.separator, key=rmap.__getitem__)
+        for v in frontal:
+            if v not in col_of:
+                col_of[v] = self._posterior_total
+                self._posterior_total += v.dim
+        obs = [float(o) for o in s._clique_true_obs[clique]]
+        sep_cols = [-1] * len(obs) + [col_of[v] + j for v in separator for j in range(v.dim)]
+        out_cols = [col_of[v] + j for v in frontal for j in range(v.dim)]
+        sc = (ctypes.c_int32 * max(len(sep_cols), 1))(*sep_cols)
+        sk = (ctypes.c_float * max(len(sep_cols), 1))(*(obs + [0.0] * (len(sep_cols) - len(obs))))
+        oc = (ctypes.c_int32 * len(out_cols))(*out_cols)
+        flow = model.flows[0]
+        norm = model._norm()
+        aff = flow._affine(norm)
+        keep = flow.__dict__["_norm_dev"][id(norm)]       # device copies of mean / std / circular: kept alive here
+        if self._pass_free:
+            slot = self._pass_free.pop()
+        else:
+            slot = self._pass_used
+            self._pass_used += 1
+            if slot >= len(self._pass_items):
+                grown = (_lib.nf_gather_item * max(256, 2 * len(self._pass_items)))()
+                ctypes.memmove(grown, self._pass_items, ctypes.sizeof(self._pass_items))
+                self._pass_items = grown
+        it = self._pass_items[slot]
+        it.flow = flow.handle()
+        it.z_col0, it.sep_dim, it.out_dim = -1 if share_z else 0, len(sep_cols), len(out_cols)
+        it.sep_cols_host = ctypes.addressof(sc)
+        it.sep_const_host = ctypes.addressof(sk)
+        it.out_cols_host = ctypes.addressof(oc)
+        it.norm = aff
+        return (slot, clique, model, sc, sk, oc, keep, share_z, clique.frontal_dim, len(obs) + clique.separator_dim)
+
     def sample_posterior_device(self, timer: List[float] = None, seeded: bool = False):
         """Root -> leaves like FactorGraphSolver.sample_posterior (src/slam/FactorGraphSolver.py:497-550): same
         clique order, but the separator samples never leave the GPU: latent draws from the device generator (or, with
         `device_latents=False`, torch's CPU generator clique by clique like the reference, one upload), ONE call
         (nfisam_posterior_pass) that walks every clique reading / writing a device sample matrix, one D2H copy of all
-        variables (through a pinned staging buffer), one discriminant check for the pass.  The per-clique index lists are
-        cached across incremental steps (variables keep their columns).  With a process group (NCCL) whole subtrees are
-        sampled by their owner rank and ONE all-reduce assembles the matrix and the discriminant counter."""
+        variables (through a pinned staging buffer), one discriminant check for the pass.  Per step the host only walks
+        the tree and gathers the cached descriptors of its cliques (`_pass_entry`): new descriptors are built for the
+        cliques the step re-trained, nothing else.  With a process group (NCCL) whole subtrees are sampled by their owner
+        rank and ONE all-reduce assembles the matrix and the discriminant counter."""
         import torch.distributed as dist
 
         s = self.solver
@@ -401,99 +443,89 @@ class CliqueScheduler:
         rank, world = self._world()
         start = time.time()
         dev = self._device()
-        order = []
-        stack = [s._physical_bayes_tree.root]
-        while stack:
-            clique = stack.pop()
-            order.append(clique)
-            stack.extend(clique.children)
+        share_z = bool(seeded or getattr(s._args, "device_latents", False))
+        if "_pass_entries" not in self.__dict__:
+            self._pass_entries, self._pass_free, self._pass_used = {}, [], 0
+            self._pass_items = (_lib.nf_gather_item * 256)()
+            self._posterior_cols, self._posterior_total = {}, 0
+        entries, col_of = self._pass_entries, self._posterior_cols
         # Ownership by top-level subtree: the root clique is sampled redundantly by every rank (replicated model,
         # deterministic kernel => identical separator samples everywhere, no broadcast needed), each child subtree
         # of the root is sampled entirely by one rank, and ONE all-reduce assembles the sample matrix at the end.
         # (Broadcasting every clique's frontal block was measured at 25 ms/step on 8 GPUs for a 512-pose graph
         # against 12 ms for the whole pass on one GPU: per-clique collectives are latency-bound.)
-        owner_of = {id(s._physical_bayes_tree.root): -1}
-        for k, child in enumerate(s._physical_bayes_tree.root.children):
-            stack2 = [child]
-            while stack2:
-                c = stack2.pop()
-                owner_of[id(c)] = k % world
-                stack2.extend(c.children)
-        owners = [owner_of[id(c)] for c in order]
-        rmap = s._reverse_ordering_map
-        frontals = [sorted(c.frontal, key=rmap.__getitem__) for c in order]
-        spans, width = [], 0
-        for clique in order:
-            spans.append((width, clique.frontal_dim))
-            width += clique.frontal_dim
-        dev_index = dev.index
+        root = s._physical_bayes_tree.root
+        order = [root]
+        mine_from = [0]                       # [begin, end) ranges of `order` this rank samples
+        for k, child in enumerate(root.children):
+            begin = len(order)
+            stack = [child]
+            while stack:
+                c = stack.pop()
+                order.append(c)
+                if c.children:
+                    stack.extend(c.children)
+            if k % world == rank:
+                mine_from += [begin, len(order)]
+        if len(mine_from) == 1:
+            mine_from.append(1)
+        else:
+            mine_from[1:1] = [1]
+        slots = []
+        live = set()
+        for c in order:
+            key = id(c)
+            ent = entries.get(key)
+            if ent is None or ent[7] != share_z:        # a node that stays in the tree keeps its model (the update replaces nodes)
+                if ent is not None:
+                    self._pass_free.append(ent[0])
+                ent = entries[key] = self._pass_entry(c, col_of, share_z)
+            live.add(key)
+            slots.append(ent[0])
+        for key in entries.keys() - live:          # cliques that left the tree: descriptor slots (and the device buffers they pin) go
+            self._pass_free.append(entries.pop(key)[0])
+        total = self._posterior_total
+        ld_s = total + 1                           # spare last column: [0, total] carries the discriminant counter
         current = torch.cuda.current_stream(dev)
         stream = ctypes.c_void_p(current.cuda_stream)
         lib = _lib.load()
-        if seeded or getattr(s._args, "device_latents", False):
+        if world > 1:
+            mine = [i for b in range(0, len(mine_from), 2) for i in range(mine_from[b], mine_from[b + 1])]
+        else:
+            mine = range(len(order))
+        item_size = ctypes.sizeof(_lib.nf_gather_item)
+        items_np = np.frombuffer(self._pass_items, dtype=np.dtype((np.void, item_size)))
+        compact = items_np[np.fromiter((slots[i] for i in mine), dtype=np.int64, count=len(mine))]
+        if share_z:
             # latent draws from the device generator (Philox keyed by a seed; slot = latent column pair): one launch, no
-            # upload.  Seeded: one seed per step, every rank generates the same (n, total) matrix and a clique uses its
-            # own columns, so the draws do not depend on which rank owns the clique (nor on the number of ranks).
+            # upload.  The latent matrix has the column layout of the sample matrix: a clique's draws only depend on the
+            # seed and its variables' columns, not on which rank owns the clique nor on the number of ranks.
             if seeded:
                 z_seed = (7919 * s._step_counter + 104729 * 2 + int(s._args.seed)) % (2 ** 31 - 1)
             else:
                 z_seed = int(np.random.randint(0, 2 ** 31 - 1))
-            zdev = torch.empty((n, max(width, 1)), dtype=torch.float32, device=dev)
-            _lib.check(lib.nfisam_randn_f32(ctypes.c_uint64(z_seed), 0, zdev.data_ptr(), n, width, max(width, 1), dev_index, stream))
+            zdev = torch.empty((n, max(total, 1)), dtype=torch.float32, device=dev)
+            _lib.check(lib.nfisam_randn_f32(ctypes.c_uint64(z_seed), 0, zdev.data_ptr(), n, total, max(total, 1), dev.index, stream))
         else:
             # latent draws on the host, in clique order (the reference's RNG consumption, clique by clique), one upload
+            width = sum(entries[id(c)][8] for c in order)
             zall = torch.empty((n, max(width, 1)), dtype=torch.float32).pin_memory()
-            for clique, (off, w) in zip(order, spans):
-                obs_dim = len(s._clique_true_obs[clique]) + clique.separator_dim
-                zall[:, off:off + w] = s._clique_density_model[clique].draw_latent(n, obs_dim, w)
+            off = 0
+            items_view = ctypes.cast(compact.ctypes.data, ctypes.POINTER(_lib.nf_gather_item))
+            pos = {i: j for j, i in enumerate(mine)}
+            for i, c in enumerate(order):
+                ent = entries[id(c)]
+                zall[:, off:off + ent[8]] = ent[2].draw_latent(n, ent[9], ent[8])
+                if i in pos:
+                    items_view[pos[i]].z_col0 = off
+                off += ent[8]
             zdev = zall.to(dev, non_blocking=True)
         counter = torch.zeros(1, dtype=torch.int64, device=dev)
-        # one device matrix holds every variable.  A variable keeps its columns for the life of the solver, so the
-        # per-clique index lists below can be cached across incremental steps.
-        col_of = self.__dict__.setdefault("_posterior_cols", {})
-        for frontal in frontals:
-            for v in frontal:
-                if v not in col_of:
-                    col_of[v] = self.__dict__.get("_posterior_total", 0)
-                    self._posterior_total = col_of[v] + v.dim
-        total = self.__dict__.get("_posterior_total", 0)
-        ld_s = total + 1                                  # spare last column: [0, total] carries the discriminant counter
         S = torch.zeros((n, ld_s), dtype=torch.float32, device=dev)
-        old_cache = self.__dict__.get("_gather_cache", {})
-        cache = {}
-        mine = [k for k, owner in enumerate(owners) if owner == rank or owner < 0]
-        items = (_lib.nf_gather_item * max(len(mine), 1))()
-        for slot, k in enumerate(mine):
-            clique, frontal = order[k], frontals[k]
-            model = s._clique_density_model[clique]
-            separator = sorted(clique.separator, key=rmap.__getitem__)
-            key = (id(model), tuple(map(id, frontal)), tuple(map(id, separator)))
-            entry = old_cache.get(id(model))
-            if entry is None or entry[0] != key:
-                obs = [float(o) for o in s._clique_true_obs[clique]]
-                sep_cols = [-1] * len(obs) + [col_of[v] + j for v in separator for j in range(v.dim)]
-                out_cols = [col_of[v] + j for v in frontal for j in range(v.dim)]
-                sc = (ctypes.c_int32 * max(len(sep_cols), 1))(*sep_cols)
-                sk = (ctypes.c_float * max(len(sep_cols), 1))(*(obs + [0.0] * (len(sep_cols) - len(obs))))
-                oc = (ctypes.c_int32 * len(out_cols))(*out_cols)
-                flow = model.flows[0]
-                norm = model._norm()
-                aff = flow._affine(norm)
-                keep = flow.__dict__["_norm_dev"][id(norm)]       # device copies of mean / std / circular: kept alive here
-                entry = (key, sc, sk, oc, len(sep_cols), len(out_cols), aff, keep, flow.handle(), model)
-            cache[id(model)] = entry
-            it = items[slot]
-            it.flow = entry[8]
-            it.z_col0, it.sep_dim, it.out_dim = spans[k][0], entry[4], entry[5]
-            it.sep_cols_host = ctypes.addressof(entry[1])
-            it.sep_const_host = ctypes.addressof(entry[2])
-            it.out_cols_host = ctypes.addressof(entry[3])
-            it.norm = entry[6]
-        self._gather_cache = cache
-        _lib.check(lib.nfisam_posterior_pass(items, len(mine), zdev.data_ptr(), int(zdev.shape[1]), S.data_ptr(), ld_s, n,
-                                             counter.data_ptr(), stream))
+        _lib.check(lib.nfisam_posterior_pass(ctypes.cast(compact.ctypes.data, ctypes.POINTER(_lib.nf_gather_item)), len(mine),
+                                             zdev.data_ptr(), int(zdev.shape[1]), S.data_ptr(), ld_s, n, counter.data_ptr(), stream))
         if world > 1 and rank != 0:     # the redundantly sampled root block is contributed by rank 0 only
-            root_cols = [col_of[v] + j for v in s._physical_bayes_tree.root.frontal for j in range(v.dim)]
+            root_cols = [col_of[v] + j for v in root.frontal for j in range(v.dim)]
             S[:, root_cols] = 0.0
         S[0, total:total + 1] = counter.to(torch.float32)
         if world > 1:
@@ -505,7 +537,7 @@ class CliqueScheduler:
         bad = int(host[0, total])
         if bad:
             raise AssertionError(f"negative discriminant in the inverse spline for {bad} samples")   # src/flows/utils.py:133
-        samples = {v: host[:, col_of[v]:col_of[v] + v.dim] for frontal in frontals for v in frontal}
+        samples = {v: host[:, c0:c0 + v.dim] for v, c0 in col_of.items()}
         if timer is not None:
             timer.append(time.time() - start)
         return samples
