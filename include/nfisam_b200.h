@@ -230,7 +230,9 @@ typedef enum nf_factor_type {
     NF_FACTOR_SE2_PRIOR = 1,     /* UnarySE2ApproximateGaussianPriorFactor.log_pdf, Factors.py:823-827 */
     NF_FACTOR_SE2_BETWEEN = 2,   /* SE2RelativeGaussianLikelihoodFactor.log_pdf,   Factors.py:1443-1448 */
     NF_FACTOR_RANGE = 3,         /* SE2R2Range / R2Range GaussianLikelihoodFactor.log_pdf, Factors.py:2724-2730, 2195-2201 */
-    NF_FACTOR_GAUSS_PRIOR = 4    /* ExplicitPriorFactor over a Gaussian (R2 landmark priors), Factors.py:328-360 */
+    NF_FACTOR_GAUSS_PRIOR = 4,   /* ExplicitPriorFactor over a Gaussian (R2 landmark priors), Factors.py:328-360 */
+    NF_FACTOR_R2_BETWEEN = 5,    /* R2RelativeGaussianLikelihoodFactor: Gaussian on x2 - x1 - obs, Factors.py:912-1092 */
+    NF_FACTOR_RANGE_PRIOR = 6    /* UnaryR2RangeGaussianPriorFactor: N(|x - centre| - mu; 0, sigma^2), Factors.py:2226-2298 */
 } nf_factor_type;
 
 #define NF_FACTOR_MAX_COLS 6
@@ -244,13 +246,15 @@ typedef struct nf_factor_desc {
     int32_t n_comp;                     /* on the first descriptor of a group: group size; else 0 */
     int32_t cols[NF_FACTOR_MAX_COLS];   /* column indices into the sample row; unused = -1.
                                            SE2: (x, y, th) [+ (x2, y2, th2)]; RANGE: (x1, y1, x2, y2);
-                                           GAUSS_PRIOR: up to 3 columns */
+                                           GAUSS_PRIOR: up to 3 columns; R2_BETWEEN: (x1, y1, x2, y2);
+                                           RANGE_PRIOR: (x, y) */
     int32_t n_cols;
     int32_t pad_;
     double weight;                      /* mixture weight (normalised); 1 for plain factors */
-    double obs[3];                      /* SE2: observation / prior pose (x, y, th); RANGE: obs[0] = range; GAUSS: mean */
+    double obs[3];                      /* SE2: observation / prior pose (x, y, th); RANGE: obs[0] = range; GAUSS: mean;
+                                           R2_BETWEEN: displacement (dx, dy); RANGE_PRIOR: (centre x, centre y, mu) */
     double info[9];                     /* SE2 / GAUSS: precision matrix row-major (3x3 or top-left n x n);
-                                           RANGE: info[0] = 1 / sigma^2 */
+                                           R2_BETWEEN: 2 x 2 precision in info[0..3]; RANGE / RANGE_PRIOR: info[0] = 1 / sigma^2 */
     double lnorm;                       /* log normalisation constant: -0.5*(dim*ln(2pi) + ln det Sigma) */
     double obs_cs[2];                   /* SE2 types: cos and sin of the (wrapped) observation / prior angle obs[2] */
 } nf_factor_desc;
@@ -291,8 +295,13 @@ typedef enum nf_sim_type {
     NF_SIM_SE2_OBS = 4,     /* out(3) = (a^-1 * b) * Exp(L eps)      (both given)        Factors.py:1286-1300 */
     NF_SIM_RANGE_GEN = 5,   /* out(2) = a[:2] + (obs0 + sigma eps) (cos u, sin u), u ~ U(-pi, pi)   Factors.py:2575-2603 */
     NF_SIM_RANGE_OBS = 6,   /* out(1) = |b[:2] - a[:2]| + sigma eps                      Factors.py:2605-2621 */
-    NF_SIM_COPY_F32 = 7     /* out(n_out) = src[row, 0..n_out) (float32 samples of a flow-backed separator factor,
+    NF_SIM_COPY_F32 = 7,    /* out(n_out) = src[row, 0..n_out) (float32 samples of a flow-backed separator factor,
                                src/slam/NFiSAM.py:283-291, produced by nfisam_flow_inverse_gather) */
+    NF_SIM_R2_GEN_FWD = 8,  /* out(2) = a + L eps + obs              (var1 given)        Factors.py:1024-1030 */
+    NF_SIM_R2_GEN_BWD = 9,  /* out(2) = a - L eps - obs              (var2 given)        Factors.py:1013-1023 */
+    NF_SIM_R2_OBS = 10,     /* out(2) = b - a + L eps                (both given)        Factors.py:1031-1036 */
+    NF_SIM_RANGE_PRIOR = 11 /* out(2) = obs[0:2] + (obs[2] + sigma eps) (cos u, sin u), u ~ U(-pi, pi): range ring around a
+                               fixed centre, src/stats/Distributions.py:125-130 (UnaryR2RangeGaussianPriorFactor) */
 } nf_sim_type;
 
 typedef struct nf_sim_op {

@@ -9,12 +9,13 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnfisam_b200.so")
+# NFISAM_B200_LIB points at an alternative build of the same library (A/B and profiling builds under scratch/)
+LIB_PATH = os.environ.get("NFISAM_B200_LIB") or os.path.join(_HERE, "libnfisam_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 NF_OK = 0
 NF_ERR_BAD_ARG, NF_ERR_CUDA, NF_ERR_NAN_LOSS, NF_ERR_NEG_DISCRIMINANT, NF_ERR_OOM, NF_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
-NF_FACTOR_SE2_PRIOR, NF_FACTOR_SE2_BETWEEN, NF_FACTOR_RANGE, NF_FACTOR_GAUSS_PRIOR = 1, 2, 3, 4
+NF_FACTOR_SE2_PRIOR, NF_FACTOR_SE2_BETWEEN, NF_FACTOR_RANGE, NF_FACTOR_GAUSS_PRIOR, NF_FACTOR_R2_BETWEEN, NF_FACTOR_RANGE_PRIOR = 1, 2, 3, 4, 5, 6
 NF_FACTOR_MAX_COLS = 6
 NFISAM_MAX_DIM = 32      # include/nfisam_b200.h
 
@@ -63,7 +64,7 @@ class nf_factor_desc(ctypes.Structure):
 
 
 NF_SIM_SE2_PRIOR, NF_SIM_GAUSS_PRIOR, NF_SIM_SE2_GEN_FWD, NF_SIM_SE2_GEN_BWD, NF_SIM_SE2_OBS, NF_SIM_RANGE_GEN, \
-    NF_SIM_RANGE_OBS, NF_SIM_COPY_F32 = range(8)
+    NF_SIM_RANGE_OBS, NF_SIM_COPY_F32, NF_SIM_R2_GEN_FWD, NF_SIM_R2_GEN_BWD, NF_SIM_R2_OBS, NF_SIM_RANGE_PRIOR = range(12)
 
 
 class nf_sim_op(ctypes.Structure):

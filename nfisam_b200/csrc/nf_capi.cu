@@ -942,6 +942,8 @@ static int validate_descs(const nf_factor_desc* d, int n_desc, int D, int* n_gro
                 case NF_FACTOR_SE2_BETWEEN: need = 6; break;
                 case NF_FACTOR_RANGE: need = 4; break;
                 case NF_FACTOR_GAUSS_PRIOR: need = f.n_cols; if (need < 1 || need > 3) need = -1; break;
+                case NF_FACTOR_R2_BETWEEN: need = 4; break;
+                case NF_FACTOR_RANGE_PRIOR: need = 2; break;
                 default: need = -1;
             }
             if (need < 0 || f.n_cols != need) return nf_set_error(NF_ERR_BAD_ARG, "descriptor %d: bad type / n_cols", i + c);
@@ -1030,6 +1032,10 @@ int nfisam_simulate(const nf_sim_op* ops_host, int n_ops, uint64_t seed, double*
             case NF_SIM_SE2_OBS: need_a = 3; need_b = 3; break;
             case NF_SIM_RANGE_GEN: width = 2; need_a = 2; break;
             case NF_SIM_RANGE_OBS: width = 1; need_a = 2; need_b = 2; break;
+            case NF_SIM_R2_GEN_FWD:
+            case NF_SIM_R2_GEN_BWD: width = 2; need_a = 2; break;
+            case NF_SIM_R2_OBS: width = 2; need_a = 2; need_b = 2; break;
+            case NF_SIM_RANGE_PRIOR: width = 2; break;
             case NF_SIM_COPY_F32:
                 width = op.n_out;
                 if (!op.src_dev || op.src_ld < op.n_out) return nf_set_error(NF_ERR_BAD_ARG, "op %d: bad source matrix", k);

@@ -6,6 +6,8 @@
 //   SE2 prior log_pdf                      src/factors/Factors.py:823-827
 //   SE2 relative log_pdf                   src/factors/Factors.py:1443-1448
 //   range log_pdf                          src/factors/Factors.py:2195-2201, 2724-2730
+//   R2 relative (displacement) log_pdf     src/factors/Factors.py:912-1092 (evaluate_loglike 1070-1074)
+//   R2 range prior                         src/factors/Factors.py:2226-2298
 //   mixture pdf / log_pdf                  src/factors/Factors.py:3126-3133
 //   mixture posterior_weights              src/factors/Factors.py:3159-3180
 //   joint log_pdf                          src/sampler/sampler_utils.py:86-99
@@ -95,6 +97,19 @@ __device__ __forceinline__ double component_logpdf(const nf_factor_desc& f, cons
                 q += v[a] * row;
             }
             return -0.5 * q + f.lnorm;
+        }
+        case NF_FACTOR_R2_BETWEEN: {
+            // delta = x2 - x1 - obs, Gaussian with a 2 x 2 precision (Factors.py:1070-1074)
+            const double dx = xr[f.cols[2] * xstride] - xr[f.cols[0] * xstride] - f.obs[0];
+            const double dy = xr[f.cols[3] * xstride] - xr[f.cols[1] * xstride] - f.obs[1];
+            const double q = dx * (f.info[0] * dx + f.info[1] * dy) + dy * (f.info[2] * dx + f.info[3] * dy);
+            return -0.5 * q + f.lnorm;
+        }
+        case NF_FACTOR_RANGE_PRIOR: {
+            // range to a fixed centre: N(|x - c| - mu; 0, sigma^2)  (Factors.py:2226-2298)
+            const double dx = xr[f.cols[0] * xstride] - f.obs[0], dy = xr[f.cols[1] * xstride] - f.obs[1];
+            const double delta = sqrt(dx * dx + dy * dy) - f.obs[2];
+            return -0.5 * (delta * f.info[0] * delta) + f.lnorm;
         }
         default:
             return 0.0;

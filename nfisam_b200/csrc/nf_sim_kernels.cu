@@ -5,6 +5,8 @@
 //   UnarySE2ApproximateGaussianPriorFactor.sample         src/factors/Factors.py:725-731
 //   SE2RelativeGaussianLikelihoodFactor.sample            src/factors/Factors.py:1196-1317 (correlated R,t branch)
 //   SE2R2RangeGaussianLikelihoodFactor.sample_*           src/factors/Factors.py:2575-2621
+//   R2RelativeGaussianLikelihoodFactor.sample             src/factors/Factors.py:995-1036
+//   UnaryR2RangeGaussianPriorFactor (GaussianRangeDistribution.rvs)   src/stats/Distributions.py:125-130
 //   mixture row ranges                                    src/factors/Factors.py:3146-3157, 3260-3276, 3339-3374
 //   SE2Pose exp map / compose / inverse                   src/geometry/TwoDimension.py:337-354, 475-477, 494-498
 //   NFiSAM.normalize_training_samples                     src/slam/NFiSAM.py:515-548
@@ -203,6 +205,36 @@ nf_simulate_kernel(const __grid_constant__ SimPack pack, int n_ops, uint64_t see
                 normal2(seed, (uint64_t)row, (uint32_t)op.slot, e0, unused);
                 const double dx = srow[op.in_b] - srow[op.in_a], dy = srow[op.in_b + 1] - srow[op.in_a + 1];
                 srow[op.out] = sqrt(dx * dx + dy * dy) + op.chol[0] * e0;
+                break;
+            }
+            case NF_SIM_R2_GEN_FWD:
+            case NF_SIM_R2_GEN_BWD:
+            case NF_SIM_R2_OBS: {
+                double e0, e1;
+                normal2(seed, (uint64_t)row, (uint32_t)op.slot, e0, e1);
+                const double n0 = op.chol[0] * e0, n1 = op.chol[1] * e0 + op.chol[2] * e1;
+                const double ax = srow[op.in_a], ay = srow[op.in_a + 1];
+                if (op.type == NF_SIM_R2_GEN_FWD) {            // var2 = var1 + noise + obs
+                    srow[op.out] = ax + n0 + op.obs[0];
+                    srow[op.out + 1] = ay + n1 + op.obs[1];
+                } else if (op.type == NF_SIM_R2_GEN_BWD) {     // var1 = var2 - noise - obs
+                    srow[op.out] = ax - n0 - op.obs[0];
+                    srow[op.out + 1] = ay - n1 - op.obs[1];
+                } else {                                        // observation = var2 - var1 + noise
+                    srow[op.out] = srow[op.in_b] - ax + n0;
+                    srow[op.out + 1] = srow[op.in_b + 1] - ay + n1;
+                }
+                break;
+            }
+            case NF_SIM_RANGE_PRIOR: {
+                double e0, unused, u0, unused2;
+                normal2(seed, (uint64_t)row, (uint32_t)op.slot, e0, unused);
+                uniform2(seed, (uint64_t)row, (uint32_t)op.slot + 1u, u0, unused2);
+                const double dist = op.obs[2] + op.chol[0] * e0;
+                double s, c;
+                sincos(-PI + TWO_PI * u0, &s, &c);
+                srow[op.out] = op.obs[0] + dist * c;
+                srow[op.out + 1] = op.obs[1] + dist * s;
                 break;
             }
             case NF_SIM_COPY_F32: {

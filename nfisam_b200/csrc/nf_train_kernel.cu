@@ -19,6 +19,7 @@
 //     the loop needs neither a cooperative launch nor a host synchronisation.
 // All reductions run in a fixed order: results are bitwise reproducible run to run.
 #include <cooperative_groups.h>
+#include <cstdio>
 
 #include "nf_internal.h"
 
@@ -27,6 +28,14 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr float HALF_LOG_2PI = 0.91893853320467274178f;
+
+// -DNF_TRAIN_TIMING: block (0, d-1) thread 0 accumulates clock64() differences per phase of the iteration and prints them at
+// the end of the launch (profiling builds only: scratch/, never the shipped library)
+#ifdef NF_TRAIN_TIMING
+#define NF_T(k) do { if (tm_on) { const long long now_ = clock64(); tm_acc[k] += now_ - tm_last; tm_last = now_; } } while (0)
+#else
+#define NF_T(k) do { } while (0)
+#endif
 
 // d f / d out for one (sample, dim), f = -z^2/2 + logdet.  `o2` holds the conditioner outputs (interleaved
 // layout of nf_common.cuh) on entry and gscale * df/dout, same layout, on exit.  Returns f.
@@ -108,6 +117,192 @@ __device__ __forceinline__ float nf_rqs_grad(float2 (&o2)[NP], float B, float xi
     }
     return f;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Parameter-gradient outer products of one 32-sample tile on the tensor cores.
+//   dW3[p][k] = sum_s gout[s][p] h2[s][k],   dW2[j][k] = sum_s g2[s][j] h1[s][k],   dW1[j][k] = sum_s g1[s][j] x[s][k]
+// are small GEMMs whose contraction runs over the 32 samples of the tile: M = outputs (28 / 8 / 8 at K = 9, H = 8), N = inputs
+// (8 / 8 / i), K = 32.  The lane-owned FFMA form of round 1 (every lane walks the 32 staged samples: ~30 instructions per sample,
+// a third of all instructions of an iteration and 4.6 of its 14.7 k cycles at n = 2000) is replaced by mma.sync.m16n8k8 TF32
+// with the 3xTF32 split (hi * hi + hi * lo + lo * hi: the products carry ~21 mantissa bits, fp32 accumulation), which keeps the
+// gradient inside the 2e-4 parity bound against autograd with room to spare.  Bias gradients (column sums) ride on the same A
+// fragments against a B of ones (exact in TF32).  Accumulator fragments stay in registers across the tiles of an iteration;
+// every reduction order is fixed, so training remains bitwise reproducible.
+// Fragment layout of mma.m16n8k8 (g = lane / 4, t = lane % 4): A (row, col) a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
+// B (k, n) b0 (t, g) b1 (t+4, g); C c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+// ---------------------------------------------------------------------------------------------------------------------
+// x = hi + lo with hi the upper 19 bits of x (a valid TF32 number) and lo = x - hi (exact).  The tensor core ignores the
+// low 13 mantissa bits of a TF32 operand, so lo is passed as it is: |lo - tf32(lo)| <= 2^-10 |lo| <= 2^-20 |x|.
+// (cvt.rna.tf32.f32 is not a single instruction on sm_100a: ptxas expands it to FSETP + IADD + SEL + LOP3, which made the
+// rounding split 9 instructions per element.)
+__device__ __forceinline__ void nf_split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void nf_mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+struct NfFragA {
+    uint32_t hi[4], lo[4];
+};
+__device__ __forceinline__ void nf_load_a(NfFragA& f, float a0, float a1, float a2, float a3) {
+    nf_split_tf32(a0, f.hi[0], f.lo[0]);
+    nf_split_tf32(a1, f.hi[1], f.lo[1]);
+    nf_split_tf32(a2, f.hi[2], f.lo[2]);
+    nf_split_tf32(a3, f.hi[3], f.lo[3]);
+}
+// c += A B at fp32-level accuracy; the small cross terms are added first
+__device__ __forceinline__ void nf_mma_3x(float (&c)[4], const NfFragA& a, float b0, float b1) {
+    uint32_t bh0, bl0, bh1, bl1;
+    nf_split_tf32(b0, bh0, bl0);
+    nf_split_tf32(b1, bh1, bl1);
+    nf_mma_tf32(c, a.lo, bh0, bh1);
+    nf_mma_tf32(c, a.hi, bl0, bl1);
+    nf_mma_tf32(c, a.hi, bh0, bh1);
+}
+// Accumulator fragments of one warp for conditioner i (see the layout comment above):
+//   c3[m][n]  dW3:   A = gout^T (rows p = 16 m + g, + 8),  B = h2  -> (p, k = 8 n + 2 t, + 1)
+//   c2[n]     dW2:   A = g2^T   (rows j; H = 8: the lower half of the tile is zero),  B = h1  -> (j, k)
+//   cx[m][n]  dW1^T: A = x^T    (rows k = 16 m + g, + 8: the conditioner's input columns),  B = g1  -> (k, j = 8 n + 2 t, + 1)
+// Putting the input columns of layer 1 on the M side keeps i <= 16 inside ONE tile: 48 MMAs per 32-sample tile at K = 9, H = 8
+// (24 + 12 + 12).  mma.sync issues every 8 cycles per SM sub-partition on B200 (measured, any operand type), so the count is
+// what matters.  Bias gradients are plain column sums by lanes that own a column (accb3 / accb21).
+template <int H, int PP>
+struct NfGradAcc {
+    static constexpr int MT3 = (PP + 15) / 16, NT = H / 8, MTX = NF_MAX_DIM / 16;
+    float c3[MT3][NT][4], c2[NT][4], cx[MTX][NT][4];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int m = 0; m < MT3; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c3[m][n][e] = 0.0f;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c2[n][e] = 0.0f;
+#pragma unroll
+        for (int m = 0; m < MTX; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cx[m][n][e] = 0.0f;
+    }
+};
+
+struct NfFragB {
+    uint32_t hi[2], lo[2];
+};
+__device__ __forceinline__ void nf_load_b(NfFragB& f, float b0, float b1) {
+    nf_split_tf32(b0, f.hi[0], f.lo[0]);
+    nf_split_tf32(b1, f.hi[1], f.lo[1]);
+}
+
+// stage: the warp's 32 staging rows (gout | h2 | g2 | h1 | g1, stride STG), slot: its 32 data rows (stride dp).
+// MTXV = ceil(i / 16): the tiles of input columns conditioner i needs.  Per 8-sample step all fragments are loaded and split
+// first, then the three 3xTF32 passes (lo * hi, hi * lo, hi * hi) run over ALL accumulators in turn, so that consecutive MMAs
+// never wait on the same accumulator.
+template <int H, int PP, int MTXV>
+__device__ __forceinline__ void nf_reduce_tile_mma(const float* __restrict__ stage, const float* __restrict__ slot, int stg, int dp,
+                                                   int i, int lane, NfGradAcc<H, PP>& acc) {
+    constexpr int MT3 = NfGradAcc<H, PP>::MT3, NT = H / 8;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const float* r0 = stage + (8 * ks + t) * stg;
+        const float* r1 = r0 + 4 * stg;
+        const float* x0 = slot + (8 * ks + t) * dp;
+        const float* x1 = x0 + 4 * dp;
+        NfFragA a3[MT3], a2, ax[MTXV];
+        NfFragB bh2[NT], bh1[NT], bg1[NT];
+        // rows past PP (last gout tile) read the h2 / g2 columns that follow: finite values, their accumulator rows are never stored
+#pragma unroll
+        for (int m = 0; m < MT3; ++m) nf_load_a(a3[m], r0[16 * m + g], r0[16 * m + g + 8], r1[16 * m + g], r1[16 * m + g + 8]);
+        if (H == 8) nf_load_a(a2, r0[PP + H + g], 0.0f, r1[PP + H + g], 0.0f);
+        else nf_load_a(a2, r0[PP + H + g], r0[PP + H + g + 8], r1[PP + H + g], r1[PP + H + g + 8]);
+#pragma unroll
+        for (int m = 0; m < MTXV; ++m) {
+            const int k0 = 16 * m + g, k1 = k0 + 8;
+            nf_load_a(ax[m], k0 < i ? x0[k0] : 0.0f, k1 < i ? x0[k1] : 0.0f, k0 < i ? x1[k0] : 0.0f, k1 < i ? x1[k1] : 0.0f);
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            nf_load_b(bh2[n], r0[PP + 8 * n + g], r1[PP + 8 * n + g]);
+            nf_load_b(bh1[n], r0[PP + 2 * H + 8 * n + g], r1[PP + 2 * H + 8 * n + g]);
+            nf_load_b(bg1[n], r0[PP + 3 * H + 8 * n + g], r1[PP + 3 * H + 8 * n + g]);
+        }
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {           // small cross terms first
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+#pragma unroll
+                for (int m = 0; m < MT3; ++m)
+                    nf_mma_tf32(acc.c3[m][n], pass == 0 ? a3[m].lo : a3[m].hi, pass == 1 ? bh2[n].lo[0] : bh2[n].hi[0],
+                                pass == 1 ? bh2[n].lo[1] : bh2[n].hi[1]);
+                nf_mma_tf32(acc.c2[n], pass == 0 ? a2.lo : a2.hi, pass == 1 ? bh1[n].lo[0] : bh1[n].hi[0],
+                            pass == 1 ? bh1[n].lo[1] : bh1[n].hi[1]);
+#pragma unroll
+                for (int m = 0; m < MTXV; ++m)
+                    nf_mma_tf32(acc.cx[m][n], pass == 0 ? ax[m].lo : ax[m].hi, pass == 1 ? bg1[n].lo[0] : bg1[n].hi[0],
+                                pass == 1 ? bg1[n].lo[1] : bg1[n].hi[1]);
+            }
+        }
+    }
+}
+
+// Bias gradients of the tile: lane p (+ 32 c) sums column p of gout; lanes 0..H-1 sum g2, lanes H..2H-1 sum g1.  Branch-free:
+// lanes without a column read a clamped (valid) address and their sums are never stored (a predicated version compiled to
+// divergent code with reconvergence barriers: 90 instructions per sample).
+template <int H, int PP, int NC3>
+__device__ __forceinline__ void nf_reduce_tile_bias(const float* __restrict__ stage, int stg, int lane, float (&accb3)[NC3], float& accb21) {
+    const int l2 = lane < 2 * H ? lane : 2 * H - 1;
+    const float* c21 = stage + (l2 < H ? PP + H + l2 : PP + 3 * H + (l2 - H));
+    const float* c3[NC3];
+#pragma unroll
+    for (int c = 0; c < NC3; ++c) c3[c] = stage + (lane + 32 * c < PP ? lane + 32 * c : PP - 1);
+#pragma unroll 8
+    for (int ss = 0; ss < 32; ++ss) {
+#pragma unroll
+        for (int c = 0; c < NC3; ++c) accb3[c] += c3[c][ss * stg];
+        accb21 += c21[ss * stg];
+    }
+}
+
+// The warp's accumulated gradient fragments -> its partial-gradient row wg (block-local packed layout of conditioner i).
+template <int H, int PP>
+__device__ __forceinline__ void nf_store_grad_acc(const NfGradAcc<H, PP>& acc, float* __restrict__ wg, int i, int lane, int oW1,
+                                                  int oW2, int oW3) {
+    constexpr int MT3 = NfGradAcc<H, PP>::MT3, NT = H / 8, MTX = NfGradAcc<H, PP>::MTX;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const int k = 8 * n + 2 * t;               // column pair of the C fragment
+#pragma unroll
+        for (int m = 0; m < MT3; ++m) {
+            const int p0 = 16 * m + g, p1 = p0 + 8;
+            if (p0 < PP) { wg[oW3 + k * PP + p0] = acc.c3[m][n][0]; wg[oW3 + (k + 1) * PP + p0] = acc.c3[m][n][1]; }
+            if (p1 < PP) { wg[oW3 + k * PP + p1] = acc.c3[m][n][2]; wg[oW3 + (k + 1) * PP + p1] = acc.c3[m][n][3]; }
+        }
+        // dW2[j][k] lives at W2t[k][j]
+        wg[oW2 + k * H + g] = acc.c2[n][0];
+        wg[oW2 + (k + 1) * H + g] = acc.c2[n][1];
+        if (H > 8) { wg[oW2 + k * H + g + 8] = acc.c2[n][2]; wg[oW2 + (k + 1) * H + g + 8] = acc.c2[n][3]; }
+        // cx rows are input columns kk, columns are hidden units j = k, k + 1: dW1[j][kk] lives at W1t[kk][j]
+#pragma unroll
+        for (int m = 0; m < MTX; ++m) {
+            const int kk0 = 16 * m + g, kk1 = kk0 + 8;
+            if (kk0 < i) { wg[oW1 + kk0 * H + k] = acc.cx[m][n][0]; wg[oW1 + kk0 * H + k + 1] = acc.cx[m][n][1]; }
+            if (kk1 < i) { wg[oW1 + kk1 * H + k] = acc.cx[m][n][2]; wg[oW1 + kk1 * H + k + 1] = acc.cx[m][n][3]; }
+        }
+    }
+}
+
+#ifndef NF_TRAIN_MMA
+#define NF_TRAIN_MMA 1      // 0: the lane-owned FFMA outer products of round 1 (A/B builds)
+#endif
 
 // Outer products of one 32-sample tile, accumulated into lane-owned registers.  The tile's per-sample vectors
 // (gout | h2 | g2 | h1 | g1) sit in the warp's staging rows; lane ownership:
@@ -195,8 +390,9 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     float* s_v = s_m + Gs;                          // [Gs]
     float* s_loss = s_v + Gs;                       // [W]
     float* s_misc = s_loss + W;                     // [8]
-    float* s_stage = s_misc + 8;                    // [W][32][STG]
-    s_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_stage) + 15) & ~uintptr_t(15));
+    // [W][32][STG], 16-byte aligned.  The offset is rounded, not the pointer: a round trip through uintptr_t turns every later
+    // access into a generic-address load (LD.E instead of LDS in the SASS).
+    float* s_stage = smem + (((2 + W) * G + 2 * Gs + W + 8 + 3) & ~3);
     float* s_x = s_stage + W * 32 * STG;            // [W][mt_res][32][dp]
 
     // val_pass: this launch only evaluates the validation loss (forward pass over a.val) for check `launch_idx`
@@ -265,18 +461,35 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
         s_m[p - p_lo] = a.adam_m[goff + p];
         s_v[p - p_lo] = a.adam_v[goff + p];
     }
+    // A warp's 32-row tile of the training set, columns 0..i, into padded shared-memory rows.  Asynchronous copies
+    // (cp.async, 4 bytes each: the rows are not 16-byte aligned) with incremental (row, column) indices; rows past n are zero.
+    // The caller commits / waits: in the non-resident (large-batch) mode the NEXT tile streams in while the current one is
+    // processed (round 1 loaded each tile with one dependent LDG -> STS per element and an integer division per index: 40 % of
+    // the stall samples of the large-batch kernel).
+    const int ls_cols = i + 1, ls_step_r = 32 / ls_cols, ls_step_c = 32 - ls_step_r * ls_cols;
+    const int ls_r0 = lane / ls_cols, ls_c0 = lane - ls_r0 * ls_cols;
     auto load_slot = [&](float* slot, int64_t tile) {
         const int64_t s0 = tile * 32;
-        const int cols = i + 1;
-        for (int t = lane; t < 32 * cols; t += 32) {
-            const int rr = t / cols, c = t - rr * cols;
+        int rr = ls_r0, c = ls_c0;
+        for (int t = lane; t < 32 * ls_cols; t += 32) {
             const int64_t s = s0 + rr;
-            slot[rr * dp + c] = s < n ? data[s * d + c] : 0.0f;
+            float* dst = slot + rr * dp + c;
+            if (s < n) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(data + s * d + c) : "memory");
+            } else {
+                *dst = 0.0f;
+            }
+            c += ls_step_c;
+            rr += ls_step_r;
+            if (c >= ls_cols) { c -= ls_cols; ++rr; }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (resident) {
         int m = 0;
         for (int64_t tile = gw; tile < ntiles; tile += TW, ++m) load_slot(xslots + (size_t)m * 32 * dp, tile);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 
@@ -284,7 +497,12 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     const int adam0 = a.step0 + it_begin;                       // Adam steps taken before this launch
     double b1t = pow((double)a.beta1, (double)adam0), b2t = pow((double)a.beta2, (double)adam0);
 
+#ifdef NF_TRAIN_TIMING
+    const bool tm_on = threadIdx.x == 0 && r == 0 && i == d - 1;
+    long long tm_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tm_last = clock64();
+#endif
     for (int it = it_begin; it < it_end; ++it) {
+        NF_T(9);
         if (slower > 0 && !(slower_fresh && it == it_begin) && it + 1 >= slower) {
             // reached slower_stop_iter: the reference breaks before training this iteration
             if (i == 0 && r == 0 && threadIdx.x == 0) {
@@ -296,11 +514,18 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
             break;
         }
         // ---------------- local gradient over this warp's tiles ----------------
+        float accb3[NC3], floss = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NC3; ++c) accb3[c] = 0.0f;
+#if NF_TRAIN_MMA
+        NfGradAcc<H, PP> gacc;
+        gacc.clear();
+        float accb21 = 0.0f;
+#else
         float2 acc3[NC3][H / 2];
-        float accb3[NC3], acc2[N2], accb2 = 0.0f, acc1[M1], accb1 = 0.0f, floss = 0.0f;
+        float acc2[N2], accb2 = 0.0f, acc1[M1], accb1 = 0.0f;
 #pragma unroll
         for (int c = 0; c < NC3; ++c) {
-            accb3[c] = 0.0f;
 #pragma unroll
             for (int k = 0; k < H / 2; ++k) acc3[c][k] = make_float2(0.0f, 0.0f);
         }
@@ -308,11 +533,23 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
         for (int m = 0; m < N2; ++m) acc2[m] = 0.0f;
 #pragma unroll
         for (int m = 0; m < M1; ++m) acc1[m] = 0.0f;
+#endif
 
-        int mslot = 0;
+        int mslot = 0, pbuf = 0;
+        if (!resident && gw < ntiles) load_slot(xslots, gw);      // two slots per warp: the first tile of this warp
         for (int64_t tile = gw; tile < ntiles; tile += TW, ++mslot) {
-            float* slot = resident ? xslots + (size_t)mslot * 32 * dp : xslots;
-            if (!resident) { __syncwarp(); load_slot(slot, tile); __syncwarp(); }
+            float* slot = resident ? xslots + (size_t)mslot * 32 * dp : xslots + (size_t)pbuf * 32 * dp;
+            if (!resident) {
+                // every lane finished the previous tile (the __syncwarp that ends an iteration of this loop): its slot is free
+                if (tile + TW < ntiles) {
+                    load_slot(xslots + (size_t)(pbuf ^ 1) * 32 * dp, tile + TW);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
+                __syncwarp();
+                pbuf ^= 1;
+            }
             const int64_t s = tile * 32 + lane;
             const bool valid = s < n;
             const float* xrow = slot + lane * dp;
@@ -324,7 +561,9 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                 nf_mlp_hidden<H>(s_w, i, xrow, h1, h2);
                 nf_mlp_out<H, PP>(s_w, i, h2, o2);
             }
+            NF_T(0);
             float f = nf_rqs_grad<K>(o2, B, xrow[i], -inv_n);
+            NF_T(1);
             if (!valid) {
                 f = 0.0f;
 #pragma unroll
@@ -377,6 +616,7 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                 }
             }
             __syncwarp();
+            NF_T(2);
             // ------------- outer products over the tile, lane-owned accumulators -------------
             if (i == 0) {
                 for (int ss = 0; ss < 32; ++ss) {
@@ -388,6 +628,11 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                     }
                 }
             } else {
+#if NF_TRAIN_MMA
+                if (i <= 16) nf_reduce_tile_mma<H, PP, 1>(stage, slot, STG, dp, i, lane, gacc);     // uniform over the block
+                else nf_reduce_tile_mma<H, PP, 2>(stage, slot, STG, dp, i, lane, gacc);
+                nf_reduce_tile_bias<H, PP, NC3>(stage, STG, lane, accb3, accb21);
+#else
                 const int mcnt = (i + LG - 1) / LG;       // W1 chunks this dim needs (uniform over the block)
 #define NF_RED(MCV) nf_reduce_tile<H, PP, NC3, N2, LG, M1, MCV>(stage, slot, STG, dp, i, lane, acc3, accb3, acc2, accb2, acc1, accb1)
                 switch (mcnt) {
@@ -400,12 +645,32 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                     default: NF_RED(M1); break;
                 }
 #undef NF_RED
+#endif
             }
             __syncwarp();
+            NF_T(3);
         }
         // ---------------- per-warp partials -> shared ----------------
         {
             float* wg = s_wg + warp * G;
+#if NF_TRAIN_MMA
+            if (i == 0) {
+#pragma unroll
+                for (int c = 0; c < NC3; ++c) {
+                    const int p = lane + 32 * c;
+                    if (p < PP) wg[ob3 + p] = accb3[c];
+                }
+            } else {
+                nf_store_grad_acc<H, PP>(gacc, wg, i, lane, oW1, oW2, oW3);
+#pragma unroll
+                for (int c = 0; c < NC3; ++c) {
+                    const int p = lane + 32 * c;
+                    if (p < PP) wg[ob3 + p] = accb3[c];
+                }
+                if (lane < H) wg[ob2 + lane] = accb21;
+                else if (lane < 2 * H) wg[ob1 + lane - H] = accb21;
+            }
+#else
 #pragma unroll
             for (int c = 0; c < NC3; ++c) {
                 const int p = lane + 32 * c;
@@ -431,11 +696,13 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                 }
                 if (lane < H) { wg[ob2 + lane] = accb2; wg[ob1 + lane] = accb1; }
             }
+#endif
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) floss += __shfl_xor_sync(0xffffffffu, floss, off);
             if (lane == 0) s_loss[warp] = floss;
         }
         __syncthreads();
+        NF_T(4);
         for (int p = threadIdx.x; p < G; p += T) {
             float acc = 0.0f;
 #pragma unroll
@@ -465,15 +732,26 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
             if (threadIdx.x == 0) a.loss_partials[r * d + i] = s_misc[0];
             return;                                               // one iteration per launch in this mode
         }
+        NF_T(5);
         cluster.sync();                                           // (A) every block's s_g / loss ready
+        NF_T(6);
         // ---------------- slice reduce over the cluster + fused Adam ----------------
+        // The C remote (DSMEM) loads of a parameter are issued together and summed in rank order afterwards: one remote
+        // latency per parameter instead of C dependent ones (the loop form `g += remote[q][p]` serialised them: 2.1 of the
+        // 14.7 k cycles of an iteration at n = 2000).  The iteration loss is gathered the same way by another warp.
+        // (Measured alternative: every block reducing ALL parameters redundantly, which needs only one cluster barrier per
+        // iteration, multiplies the DSMEM traffic by C and came out slower: 2.5 k cycles for the reduction alone.)
         b1t *= (double)a.beta1;
         b2t *= (double)a.beta2;
         const float step = (float)((double)a.lr / (1.0 - b1t));
         const float bc2s = (float)sqrt(1.0 - b2t);
         for (int p = p_lo + threadIdx.x; p < p_hi; p += T) {
+            float gq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gq[q] = q < C ? cluster.map_shared_rank(s_g, q)[p] : 0.0f;
             float g = 0.0f;
-            for (int q = 0; q < C; ++q) g += cluster.map_shared_rank(s_g, q)[p];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) g += gq[q];               // ranks >= C contribute +0.0f: same value as a rank loop
             if (a.grad_only) {
                 a.grad_out[goff + p] = g;
             } else {
@@ -484,19 +762,35 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
                 s_v[p - p_lo] = v;
                 const float den = sqrtf(v) / bc2s + a.eps;
                 const float th = s_w[p] - step * (m / den);
-                for (int q = 0; q < C; ++q) cluster.map_shared_rank(s_w, q)[p] = th;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < C) cluster.map_shared_rank(s_w, q)[p] = th;
             }
         }
-        if (r == 0 && threadIdx.x == 0) {
+        if (r == 0 && threadIdx.x == T - 32) {                     // lane 0 of the last warp: off warp 0's path
+            float lq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) lq[q] = q < C ? cluster.map_shared_rank(s_misc, q)[0] : 0.0f;
             float acc = 0.0f;
-            for (int q = 0; q < C; ++q) acc += cluster.map_shared_rank(s_misc, q)[0];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += lq[q];
             a.loss_part[(size_t)it * d + i] = -acc * inv_n;
         }
+        NF_T(7);
         cluster.sync();                                           // (B) new weights visible, s_g reusable
+        NF_T(8);
     }
+#ifdef NF_TRAIN_TIMING
+    if (tm_on && it_end > it_begin)
+        printf("train timing d=%d C=%d W=%d iters=%d cycles/iter: mlp_fwd %lld rqs_grad %lld mlp_bwd+stage %lld reduce_tile %lld partials+syncthreads %lld block_reduce %lld "
+               "cluster_sync_A %lld slice_adam %lld cluster_sync_B %lld loop %lld\n", d, C, W, it_end - it_begin,
+               tm_acc[0] / (it_end - it_begin), tm_acc[1] / (it_end - it_begin), tm_acc[2] / (it_end - it_begin), tm_acc[3] / (it_end - it_begin),
+               tm_acc[4] / (it_end - it_begin), tm_acc[5] / (it_end - it_begin), tm_acc[6] / (it_end - it_begin), tm_acc[7] / (it_end - it_begin),
+               tm_acc[8] / (it_end - it_begin), tm_acc[9] / (it_end - it_begin));
+#endif
     // ---------------- write back ----------------
     if (!a.grad_only) {
-        for (int p = p_lo + threadIdx.x; p < p_hi; p += T) {
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += T) {      // every block holds the whole conditioner: each stores its slice
             a.pk[goff + p] = s_w[p];
             a.adam_m[goff + p] = s_m[p - p_lo];
             a.adam_v[goff + p] = s_v[p - p_lo];
@@ -563,7 +857,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
     const int window = a.grad_only ? 1 : (a.average_window > 0 ? a.average_window : 64);
     if (a.partials != nullptr && a.loss_partials != nullptr) {
         // ---- large-batch mode: two launches per iteration, about two blocks per SM over all dims
-        const size_t smem = train_smem_bytes<K, H, W>(d - 1, 1, 1);
+        const size_t smem = train_smem_bytes<K, H, W>(d - 1, 1, 2);    // two tile slots per warp: the next tile is prefetched
         if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
         NF_CUDA(cudaFuncSetAttribute(kern_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -589,7 +883,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         const int adam_blocks = (a.n_packed + 255) / 256;
         for (int it = 0; it < a.max_iters; ++it) {
             const int launch_idx = it / window;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern_big, a, d, fd.B, 1, 0, it, it + 1, launch_idx, 1, 0);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern_big, a, d, fd.B, 2, 0, it, it + 1, launch_idx, 1, 0);
             if (e != cudaSuccess) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, plain)");
             nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
             nf_count_launch(2);
@@ -604,7 +898,8 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         if (mt < 1) mt = 1;
         int resident = 1;
         size_t smem = train_smem_bytes<K, H, W>(d - 1, C, mt);
-        if (smem > 100 * 1024) { resident = 0; mt = 1; smem = train_smem_bytes<K, H, W>(d - 1, C, 1); }
+        if (smem > 100 * 1024) { resident = 0; mt = 2; smem = train_smem_bytes<K, H, W>(d - 1, C, 2); }    // streamed: 2 slots per warp
+        if (a.n_val > 0 && mt < 2) { mt = 2; smem = train_smem_bytes<K, H, W>(d - 1, C, 2); }            // the validation pass streams its tiles
         if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
         // several runs in flight (clique scheduler): the <= 128-register build lets two blocks -- two cliques -- share an
         // SM, which hides the latency chains of one run behind the other; same arithmetic, bit-identical results
@@ -631,7 +926,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
                 const int it1 = ((launch_idx + 1) * vi - 1) < a.max_iters ? ((launch_idx + 1) * vi - 1) : a.max_iters;
                 cudaError_t e = cudaSuccess;
                 if (launch_idx > 0) {
-                    e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, 1, 0, it0, it0 + 1, launch_idx, 0, 1);
+                    e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, 0, it0, it0 + 1, launch_idx, 0, 1);
                     nf_count_launch();
                 }
                 if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0, 0);

@@ -8,7 +8,8 @@ import torch
 from .. import _lib
 
 _TYPES = {"se2_prior": _lib.NF_FACTOR_SE2_PRIOR, "se2_between": _lib.NF_FACTOR_SE2_BETWEEN,
-          "range": _lib.NF_FACTOR_RANGE, "gauss": _lib.NF_FACTOR_GAUSS_PRIOR}
+          "range": _lib.NF_FACTOR_RANGE, "gauss": _lib.NF_FACTOR_GAUSS_PRIOR, "r2_between": _lib.NF_FACTOR_R2_BETWEEN,
+          "range_prior": _lib.NF_FACTOR_RANGE_PRIOR}
 
 
 def pack_descs(groups):

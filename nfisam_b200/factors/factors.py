@@ -10,13 +10,15 @@ clique training sets.
   R2RangeGaussianLikelihoodFactor          Factors.py:2026-2224
   BinaryFactorMixture / AmbiguousDataAssociationFactor / BinaryFactorWithNullHypo
                                            Factors.py:3043-3462
-Out of scope (not in any BASELINE config): bearing, slip-grip, "uncertain" range, R2 relative factors.
+  R2RelativeGaussianLikelihoodFactor       Factors.py:912-1092   (toy_examples/R2*)
+  UnaryR2RangeGaussianPriorFactor          Factors.py:2226-2298
+Out of scope (not in any BASELINE config): bearing, slip-grip, "uncertain" range factors.
 """
 from typing import Dict, Iterable, List
 
 import numpy as np
 
-from ..slam.variables import R1Variable, SE2Variable, Variable, VariableType
+from ..slam.variables import R1Variable, R2Variable, SE2Variable, Variable, VariableType
 from .. import _lib
 from . import _gpu
 from .geometry import SE2Pose, se2_compose, se2_exp, se2_inverse
@@ -159,9 +161,11 @@ class UnaryR2GaussianPriorFactor(PriorFactor):
 
     is_gaussian = True
 
-    def __init__(self, var: Variable, mu: np.ndarray, covariance: np.ndarray):
+    def __init__(self, var: Variable, mu: np.ndarray, covariance: np.ndarray = None, precision: np.ndarray = None):
+        if covariance is None and precision is None:
+            raise ValueError("None of cov and info. were defined.")
         self._var, self._mu = var, np.asarray(mu, float)
-        self._covariance = np.asarray(covariance, float)
+        self._covariance = np.asarray(covariance, float) if covariance is not None else np.linalg.inv(np.asarray(precision, float))
         self._precision = np.linalg.inv(self._covariance)
         self._chol = np.linalg.cholesky(self._covariance)
         self._lnorm = gaussian_lnorm(self._covariance)
@@ -336,6 +340,125 @@ class SE2R2RangeGaussianLikelihoodFactor(LikelihoodFactor, BinaryFactor):
 
 class R2RangeGaussianLikelihoodFactor(SE2R2RangeGaussianLikelihoodFactor):
     """Same density on two R2 variables (Factors.py:2026-2224)."""
+
+
+class R2RelativeGaussianLikelihoodFactor(LikelihoodFactor, BinaryFactor):
+    """Displacement between two Euclidean variables of equal dimension 2 plus Gaussian noise: the density is Gaussian in
+    delta = var2 - var1 - observation (Factors.py:912-1092; evaluate_loglike 1070-1074, sample 995-1036)."""
+
+    is_gaussian = True
+    measurement_dim = 2
+    measurement_type = R2Variable
+
+    def __init__(self, var1, var2, observation, covariance=None, precision=None):
+        if var1.dim != var2.dim:
+            raise ValueError("The two variables must have the same dimensionality")
+        if len(observation) != var1.dim:
+            raise ValueError("The observation must have the same dimensionality as the two variables")
+        if var1.dim != 2:
+            raise NotImplementedError("the device path covers the reference's R2 use of this factor (dimension 2)")
+        if covariance is None and precision is None:
+            raise ValueError("None of cov and info. were defined.")
+        self._vars, self._observation = [var1, var2], np.asarray(observation, float)
+        self._covariance = np.asarray(covariance, float) if covariance is not None else np.linalg.inv(np.asarray(precision, float))
+        self._precision = np.asarray(precision, float) if covariance is None else np.linalg.inv(self._covariance)
+        self._chol = np.linalg.cholesky(self._covariance)
+        self._lnorm = gaussian_lnorm(self._covariance)
+        self._observation_var = R2Variable("O" + str(var1.name) + str(var2.name), VariableType.Measurement)
+
+    vars = property(lambda self: self._vars)
+    observation = property(lambda self: self._observation)
+    observation_var = property(lambda self: self._observation_var)
+    covariance = property(lambda self: self._covariance)
+    circular_dim_list = property(lambda self: self._observation_var.circular_dim_list)
+
+    def components(self, col_of):
+        a, b = col_of[self._vars[0]], col_of[self._vars[1]]
+        return [dict(type="r2_between", cols=[a, a + 1, b, b + 1], obs=self._observation, info=self._precision.ravel(),
+                     lnorm=self._lnorm, weight=1.0)]
+
+    def _noise(self, n):
+        return np.random.standard_normal((n, 2)) @ self._chol.T
+
+    def sample(self, var1=None, var2=None):
+        """var2 given -> var1 = var2 - noise - obs; var1 given -> var2 = var1 + noise + obs; both -> observation samples
+        var2 - var1 + noise (Factors.py:995-1036)."""
+        if var1 is None:
+            if var2 is None:
+                raise ValueError("Samples of at least one variable must be specified")
+            return var2 - self._noise(var2.shape[0]) - self._observation
+        if var2 is None:
+            return var1 + self._noise(var1.shape[0]) + self._observation
+        return var2 - var1 + self._noise(var1.shape[0])
+
+    def sim_gen(self, prog, given, new, rows=None, slot=None):
+        kind = _lib.NF_SIM_R2_GEN_FWD if given == self._vars[0] else _lib.NF_SIM_R2_GEN_BWD
+        prog.add(kind, in_a=prog.col(given), out=prog.col(new), n_out=2, obs=self._observation, chol=self._chol, slots=1,
+                 rows=rows, slot=slot)
+
+    def sim_obs(self, prog, out_col, rows=None, slot=None):
+        prog.add(_lib.NF_SIM_R2_OBS, in_a=prog.col(self._vars[0]), in_b=prog.col(self._vars[1]), out=out_col, n_out=2,
+                 chol=self._chol, slots=1, rows=rows, slot=slot)
+
+    @classmethod
+    def construct_from_text(cls, line, variables):
+        tok = line.strip().split()
+        by_name = {v.name: v for v in variables}
+        mat = np.array([float(t) for t in tok[6:10]]).reshape(2, 2)
+        return cls(by_name[tok[1]], by_name[tok[2]], np.array([float(tok[3]), float(tok[4])]), **{tok[5]: mat})
+
+    def __str__(self):
+        return " ".join(["Factor", type(self).__name__, str(self._vars[0].name), str(self._vars[1].name)] +
+                        [str(v) for v in self._observation] + ["covariance"] + [str(v) for v in self._covariance.ravel()])
+
+
+class UnaryR2RangeGaussianPriorFactor(PriorFactor):
+    """Prior on an R2 variable: its distance to a fixed centre is N(mu, sigma^2), direction uniform (Factors.py:2226-2298,
+    GaussianRangeDistribution src/stats/Distributions.py:113-150).  The reference's class can only be SAMPLED: its
+    distribution defines no log_pdf and its evaluate_loglike subtracts the scalar range from the position vector
+    (Factors.py:2291-2293).  `log_pdf` here is the density its name and `_lnorm` describe, N(|x - centre| - mu; 0, sigma^2)."""
+
+    is_gaussian = False
+
+    def __init__(self, var, center, mu, sigma):
+        self._var, self._center = var, np.asarray(center, float)
+        if self._center.shape != (2,):
+            raise ValueError("The center has incorrect dimensionality")
+        self._mu, self._sigma = float(mu), float(sigma)
+        self._lnorm = float(-0.5 * np.log(TWO_PI) - np.log(self._sigma))
+
+    vars = property(lambda self: [self._var])
+    var = property(lambda self: self._var)
+    mu = property(lambda self: self._mu)
+    observation = mu
+    center = property(lambda self: self._center)
+    covariance = property(lambda self: self._sigma ** 2)
+
+    def components(self, col_of):
+        c = col_of[self._var]
+        return [dict(type="range_prior", cols=[c, c + 1], obs=[self._center[0], self._center[1], self._mu],
+                     info=[1.0 / self._sigma ** 2], lnorm=self._lnorm, weight=1.0)]
+
+    def sample(self, num_samples: int, **kwargs):
+        dist = self._mu + self._sigma * np.random.standard_normal((num_samples, 1))
+        ang = np.random.uniform(-np.pi, np.pi, (num_samples, 1))
+        return self._center[None, :] + np.hstack([dist * np.cos(ang), dist * np.sin(ang)])
+
+    def sim_prior(self, prog):
+        prog.add(_lib.NF_SIM_RANGE_PRIOR, out=prog.col(self._var), n_out=2, obs=[self._center[0], self._center[1], self._mu],
+                 chol=[[self._sigma]], slots=2)
+
+    @classmethod
+    def construct_from_text(cls, line, variables):
+        # the reference's own reader passes keywords its constructor does not take (Factors.py:2263-2277); the format it
+        # writes is "<var> center: cx cy mu: m sigma s^2" (__str__, :2255-2261)
+        tok = line.strip().split()
+        by_name = {v.name: v for v in variables}
+        return cls(by_name[tok[1]], np.array([float(tok[3]), float(tok[4])]), float(tok[6]), float(np.sqrt(float(tok[8]))))
+
+    def __str__(self):
+        return " ".join(["Factor", type(self).__name__, str(self._var.name), "center:", str(self._center[0]), str(self._center[1]),
+                         "mu:", str(self._mu), "sigma", str(self.covariance)])
 
 
 class BinaryFactorMixture(LikelihoodFactor):
@@ -517,8 +640,18 @@ class JointFactor(Factor):
 
 FACTOR_CLASSES = {c.__name__: c for c in (
     UnarySE2ApproximateGaussianPriorFactor, UnaryR2GaussianPriorFactor, SE2RelativeGaussianLikelihoodFactor,
-    SE2R2RangeGaussianLikelihoodFactor, R2RangeGaussianLikelihoodFactor, AmbiguousDataAssociationFactor,
-    BinaryFactorWithNullHypo)}
+    SE2R2RangeGaussianLikelihoodFactor, R2RangeGaussianLikelihoodFactor, R2RelativeGaussianLikelihoodFactor,
+    UnaryR2RangeGaussianPriorFactor, AmbiguousDataAssociationFactor, BinaryFactorWithNullHypo)}
+
+
+class GaussianPriorFactor(UnaryR2GaussianPriorFactor):
+    """Gaussian prior with the reference's generic constructor (Factors.py:329-359): `mean` instead of `mu`."""
+
+    def __init__(self, var, mean, covariance=None, precision=None):
+        super().__init__(var, mean, covariance=covariance, precision=precision)
+
+
+FACTOR_CLASSES["GaussianPriorFactor"] = GaussianPriorFactor
 
 
 def oracle_descriptor(factor: Factor, col_of=None):

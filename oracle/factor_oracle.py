@@ -7,6 +7,9 @@ Reference behaviour restated (file:line under /root/reference):
   SE2 prior log_pdf                  src/factors/Factors.py:823-827
   SE2 relative-pose log_pdf          src/factors/Factors.py:1443-1448
   range log_pdf (SE2-R2, R2-R2)      src/factors/Factors.py:2195-2201, 2724-2730
+  R2 relative (displacement)         src/factors/Factors.py:912-1092 (log-likelihood: AdditiveLinearGaussianLogLikelihood of
+                                     TransportMaps, restated by evaluate_loglike 1070-1074)
+  R2 range prior                     src/factors/Factors.py:2226-2298
   mixture pdf / log_pdf              src/factors/Factors.py:3126-3133   (plain log of a sum of exps)
   mixture posterior_weights          src/factors/Factors.py:3159-3180
   joint log_pdf                      src/sampler/sampler_utils.py:86-99
@@ -21,7 +24,7 @@ Parity status: PINNED -- tests/test_oracle_factors.py checks every function agai
 tests/golden/factors.npz, produced by the reference's own classes (tests/golden/make_factor_golden.py).
 
 A factor is described by a dict with the fields of the C ABI's nf_factor_desc:
-  type ('se2_prior' | 'se2_between' | 'range' | 'gauss'), cols, obs, info, lnorm, weight;
+  type ('se2_prior' | 'se2_between' | 'range' | 'gauss' | 'r2_between' | 'range_prior'), cols, obs, info, lnorm, weight;
 a mixture is a list of such dicts.
 """
 import numpy as np
@@ -93,6 +96,12 @@ def component_logpdf(f, x):
     if t == "range":
         r = np.sqrt((x[:, c[0]] - x[:, c[2]]) ** 2 + (x[:, c[1]] - x[:, c[3]]) ** 2)
         delta = r - f["obs"][0]
+        return -0.5 * delta * f["info"][0] * delta + f["lnorm"]
+    if t == "r2_between":        # R2RelativeGaussianLikelihoodFactor.evaluate_loglike, src/factors/Factors.py:1070-1074
+        v = np.stack([x[:, c[2]] - x[:, c[0]] - f["obs"][0], x[:, c[3]] - x[:, c[1]] - f["obs"][1]], axis=-1)
+        return _gauss(v, np.asarray(f["info"], float).ravel()[:4].reshape(2, 2), f["lnorm"])
+    if t == "range_prior":       # UnaryR2RangeGaussianPriorFactor, src/factors/Factors.py:2226-2298 (range to a fixed centre)
+        delta = np.sqrt((x[:, c[0]] - f["obs"][0]) ** 2 + (x[:, c[1]] - f["obs"][1]) ** 2) - f["obs"][2]
         return -0.5 * delta * f["info"][0] * delta + f["lnorm"]
     if t == "gauss":
         k = len(c)

@@ -7,6 +7,8 @@ Reference behaviour restated (file:line under /root/reference):
   SE2 prior sampling                      src/factors/Factors.py:725-731
   SE2 relative-pose sampling              src/factors/Factors.py:1196-1317 (correlated R,t branch)
   range sampling (ring / observation)     src/factors/Factors.py:2575-2621
+  R2 displacement sampling                src/factors/Factors.py:995-1036
+  R2 range-prior sampling                 src/stats/Distributions.py:125-130 (via Factors.py:2226-2298)
   mixture row ranges                      src/factors/Factors.py:3146-3157, 3260-3276, 3339-3374
   SE2Pose exp map, compose, inverse       src/geometry/TwoDimension.py:337-354, 475-477, 494-498
   normalize_training_samples              src/slam/NFiSAM.py:515-548 (scipy.stats.circmean for circular columns)
@@ -24,7 +26,8 @@ import numpy as np
 
 TWO_PI = 2.0 * np.pi
 
-SE2_PRIOR, GAUSS_PRIOR, SE2_GEN_FWD, SE2_GEN_BWD, SE2_OBS, RANGE_GEN, RANGE_OBS, COPY_F32 = range(8)
+SE2_PRIOR, GAUSS_PRIOR, SE2_GEN_FWD, SE2_GEN_BWD, SE2_OBS, RANGE_GEN, RANGE_OBS, COPY_F32, R2_GEN_FWD, R2_GEN_BWD, R2_OBS, \
+    RANGE_PRIOR = range(12)
 
 
 # ---- counter-based random numbers -------------------------------------------------------------------------------
@@ -159,6 +162,27 @@ def range_obs(var1_xy, var2_xy, range_noise):
     return np.sqrt(np.sum(d ** 2, axis=1)) + range_noise
 
 
+def r2_gen_fwd(var1, obs, noise):
+    """R2RelativeGaussianLikelihoodFactor.sample, Factors.py:1024-1030: var2 = var1 + noise + observation."""
+    return np.asarray(var1, float)[:, :2] + noise + np.asarray(obs, float)[:2]
+
+
+def r2_gen_bwd(var2, obs, noise):
+    """Factors.py:1013-1023: var1 = var2 - noise - observation."""
+    return np.asarray(var2, float)[:, :2] - noise - np.asarray(obs, float)[:2]
+
+
+def r2_obs(var1, var2, noise):
+    """Factors.py:1031-1036: observation = var2 - var1 + noise."""
+    return np.asarray(var2, float)[:, :2] - np.asarray(var1, float)[:, :2] + noise
+
+
+def range_prior(center, mu, range_noise, angle):
+    """UnaryR2RangeGaussianPriorFactor.sample = GaussianRangeDistribution.rvs, src/stats/Distributions.py:125-130."""
+    dist = mu + range_noise
+    return np.asarray(center, float)[None, :2] + np.column_stack([dist * np.cos(angle), dist * np.sin(angle)])
+
+
 # ---- op-list interpreter with the Philox noise of the CUDA kernel ---------------------------------------------
 def _lie_noise(op, seed, rows):
     e0, e1 = normal2(seed, rows, op["slot"])
@@ -201,6 +225,21 @@ def simulate(ops, seed, n, ld):
             e0, _ = normal2(seed, rows, op["slot"])
             s[lo:hi, o] = range_obs(s[lo:hi, op["in_a"]:op["in_a"] + 2], s[lo:hi, op["in_b"]:op["in_b"] + 2],
                                     op["chol"][0] * e0)
+        elif t in (R2_GEN_FWD, R2_GEN_BWD, R2_OBS):
+            e0, e1 = normal2(seed, rows, op["slot"])
+            c = op["chol"]
+            noise = np.column_stack([c[0] * e0, c[1] * e0 + c[2] * e1])
+            a = s[lo:hi, op["in_a"]:op["in_a"] + 2]
+            if t == R2_GEN_FWD:
+                s[lo:hi, o:o + 2] = r2_gen_fwd(a, op["obs"], noise)
+            elif t == R2_GEN_BWD:
+                s[lo:hi, o:o + 2] = r2_gen_bwd(a, op["obs"], noise)
+            else:
+                s[lo:hi, o:o + 2] = r2_obs(a, s[lo:hi, op["in_b"]:op["in_b"] + 2], noise)
+        elif t == RANGE_PRIOR:
+            e0, _ = normal2(seed, rows, op["slot"])
+            u0, _ = uniform2(seed, rows, op["slot"] + 1)
+            s[lo:hi, o:o + 2] = range_prior(op["obs"][:2], op["obs"][2], op["chol"][0] * e0, -np.pi + TWO_PI * u0)
         elif t == COPY_F32:
             s[lo:hi, o:o + op["n_out"]] = np.asarray(op["src"], np.float32)[lo:hi, :op["n_out"]].astype(np.float64)
         else:

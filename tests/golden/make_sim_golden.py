@@ -10,7 +10,6 @@ their bearing with `np.random.uniform(-pi, pi, m)` (Factors.py:2585, 2599) and m
 swapped for queues of pre-drawn arrays while a reference method runs."""
 import os
 import sys
-from collections import deque
 
 import numpy as np
 
@@ -28,37 +27,7 @@ from geometry.TwoDimension import SE2Pose  # noqa: E402
 from slam.Variables import R2Variable, SE2Variable, VariableType  # noqa: E402
 
 
-class Replay:
-    """Feeds queued arrays to np.random.standard_normal / uniform / multinomial."""
-
-    def __init__(self, normals=(), uniforms=(), multinomials=()):
-        self.q = {"n": deque(normals), "u": deque(uniforms), "m": deque(multinomials)}
-
-    def __enter__(self):
-        self.saved = (np.random.standard_normal, np.random.uniform, np.random.multinomial)
-
-        def std_normal(size=None):
-            a = self.q["n"].popleft()
-            assert tuple(np.atleast_1d(size)) == a.shape, (size, a.shape)
-            return a
-
-        def uniform(low=0.0, high=1.0, size=None):
-            a = self.q["u"].popleft()
-            assert np.prod(np.atleast_1d(size)) == a.size
-            return low + (high - low) * a.reshape(size)
-
-        def multinomial(n, pvals, size=None):
-            a = self.q["m"].popleft()
-            assert a.sum() == n and len(a) == len(pvals)
-            return a
-
-        np.random.standard_normal, np.random.uniform, np.random.multinomial = std_normal, uniform, multinomial
-        return self
-
-    def __exit__(self, *exc):
-        np.random.standard_normal, np.random.uniform, np.random.multinomial = self.saved
-        assert not any(self.q.values()), "a replayed draw was not consumed"
-
+from make_sim_golden_replay import Replay  # noqa: E402
 
 rng = np.random.default_rng(7)
 out = {}

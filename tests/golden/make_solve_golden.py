@@ -67,7 +67,9 @@ def run(case, seed=0):
         out[f"step{i}_tree"] = np.array(sorted("".join(sorted(x.name for x in c.frontal)) + "|" + "".join(sorted(x.name for x in c.separator))
                                                for c in solver.physical_bayes_tree.clique_nodes))
         if mixtures:
-            out[f"step{i}_hypo"] = np.array([f.posterior_weights(cur) for f in mixtures if set(f.vars).issubset(cur.keys())])
+            ws = [np.asarray(f.posterior_weights(cur), float) for f in mixtures if set(f.vars).issubset(cur.keys())]
+            k = max(len(w) for w in ws)             # 2- and 3-way associations: rows padded with NaN
+            out[f"step{i}_hypo"] = np.array([np.concatenate([w, np.full(k - len(w), np.nan)]) for w in ws])
         print(case, "step", i, "%.1f s" % (time.time() - t0), [round(t, 2) for t in timer], flush=True)
     np.savez_compressed(os.path.join(HERE, f"solve_{case}.npz" if seed == 0 else f"solve_{case}_seed{seed}.npz"), **out)
 

@@ -87,3 +87,26 @@ def test_device_tensor_input_and_bad_descriptor():
     assert torch.allclose(out, -0.5 * (r - 5.0) ** 2 - 0.5 * np.log(2 * np.pi), atol=1e-12)
     with pytest.raises(_lib.NfisamError):
         _gpu.logpdf([[dict(type="range", cols=[0, 1, 2, 9], obs=[1.0], info=[1.0], lnorm=0.0)]], x)
+
+
+def test_r2_factor_classes_golden():
+    """R2RelativeGaussianLikelihoodFactor / UnaryR2RangeGaussianPriorFactor (the toy_examples/R2* factor classes): kernel
+    densities against the reference's evaluate_loglike values (factors_r2.npz) and the oracle, |diff| <= 1e-6."""
+    from nfisam_b200.factors import JointFactor, oracle_descriptor
+    from tests.test_oracle_factors import r2_factors
+
+    g2 = dict(np.load(os.path.join(HERE, "golden", "factors_r2.npz")))
+    fs = r2_factors(g2)
+    for tag in ("cov", "prec"):
+        got = fs["r2rel_" + tag].log_pdf(g2[f"r2rel_{tag}_x"])
+        assert np.max(np.abs(got - g2[f"r2rel_{tag}_lp"])) <= TOL
+    rng = np.random.default_rng(5)
+    x = np.array([3.0, -1.0]) + rng.standard_normal((1000, 2)) * 6.0
+    got = fs["range_prior"].log_pdf(x)
+    assert np.max(np.abs(got - fo.factor_logpdf(oracle_descriptor(fs["range_prior"]), x))) <= TOL
+    # fused joint over a row holding both variables
+    A, B = fs["r2rel_cov"].vars
+    jf = JointFactor([fs["range_prior"], fs["r2rel_cov"]], [A, B])
+    x = np.hstack([x, x + np.array([5.0, -5.0]) + rng.standard_normal((1000, 2))])
+    exp = fo.joint_logpdf([oracle_descriptor(f, jf._col_of) for f in jf.factors], x)
+    assert np.max(np.abs(jf.log_pdf(x) - exp)) <= TOL

@@ -129,3 +129,58 @@ def test_sampling_statistics():
     d = np.linalg.norm(lm - xi[:, :2], axis=1)
     assert abs(d.mean() - 10.0) < 0.02 and abs(d.std() - 0.5) < 0.02
     assert r.sample(var1=xi, var2=lm).shape == (20000, 1)
+
+
+# ---- R2 factor classes of the reference's toy examples (tests/golden/make_r2_factor_golden.py) -----------------------
+def r2_factors(g2):
+    from nfisam_b200.factors import R2RelativeGaussianLikelihoodFactor, UnaryR2RangeGaussianPriorFactor
+    from nfisam_b200.slam import R2Variable
+
+    A, B = R2Variable("x0"), R2Variable("x1")
+    cx, cy, mu, sigma = g2["range_prior_params"]
+    return {"r2rel_cov": R2RelativeGaussianLikelihoodFactor(A, B, g2["r2rel_obs"], covariance=np.array([[0.3, 0.05], [0.05, 0.1]])),
+            "r2rel_prec": R2RelativeGaussianLikelihoodFactor(A, B, g2["r2rel_obs"], precision=np.array([[10.0, 0.0], [0.0, 10.0]])),
+            "range_prior": UnaryR2RangeGaussianPriorFactor(A, np.array([cx, cy]), mu, sigma)}
+
+
+@pytest.fixture(scope="module")
+def g2():
+    return dict(np.load(os.path.join(HERE, "golden", "factors_r2.npz")))
+
+
+def test_r2_relative_factor_matches_reference(g2):
+    """Density (the reference's evaluate_loglike, Factors.py:1070-1074) and the three sampling directions with replayed
+    draws (Factors.py:995-1036), through the host classes and the numpy oracles."""
+    from nfisam_b200.factors import oracle_descriptor
+    from oracle import sim_oracle as so
+
+    fs = r2_factors(g2)
+    for tag in ("cov", "prec"):
+        f = fs["r2rel_" + tag]
+        np.testing.assert_allclose(f.covariance, g2[f"r2rel_{tag}_covariance"], rtol=1e-12)
+        check(fo.factor_logpdf(oracle_descriptor(f), g2[f"r2rel_{tag}_x"]), g2[f"r2rel_{tag}_lp"], tol=1e-9)
+        chol = np.linalg.cholesky(f.covariance)
+        pts, pts2 = g2[f"r2rel_{tag}_pts"], g2[f"r2rel_{tag}_pts2"]
+        tol = dict(rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(so.r2_gen_fwd(pts, g2["r2rel_obs"], g2[f"r2rel_{tag}_fwd_eps"] @ chol.T), g2[f"r2rel_{tag}_fwd_out"], **tol)
+        np.testing.assert_allclose(so.r2_gen_bwd(pts, g2["r2rel_obs"], g2[f"r2rel_{tag}_bwd_eps"] @ chol.T), g2[f"r2rel_{tag}_bwd_out"], **tol)
+        np.testing.assert_allclose(so.r2_obs(pts, pts2, g2[f"r2rel_{tag}_obs_eps"] @ chol.T), g2[f"r2rel_{tag}_obs_out"], **tol)
+    text = str(fs["r2rel_cov"])
+    from nfisam_b200.factors import Factor
+
+    back = Factor.construct_from_text(text, fs["r2rel_cov"].vars)
+    np.testing.assert_allclose(back.covariance, fs["r2rel_cov"].covariance)
+    assert [v.name for v in back.vars] == ["x0", "x1"] and back.observation_var.dim == 2
+
+
+def test_r2_range_prior_sampler_matches_reference(g2):
+    from nfisam_b200.factors import Factor
+    from oracle import sim_oracle as so
+
+    cx, cy, mu, sigma = g2["range_prior_params"]
+    ang = -np.pi + 2 * np.pi * g2["range_prior_u"]
+    got = so.range_prior([cx, cy], mu, sigma * g2["range_prior_eps"][:, 0], ang)
+    np.testing.assert_allclose(got, g2["range_prior_out"], rtol=1e-12, atol=1e-12)
+    f = r2_factors(g2)["range_prior"]
+    back = Factor.construct_from_text(str(f), f.vars)
+    assert back.mu == mu and abs(back.covariance - sigma ** 2) < 1e-15 and np.allclose(back.center, [cx, cy])

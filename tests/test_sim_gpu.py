@@ -94,13 +94,17 @@ def _all_ops(n):
         mk(type=so.RANGE_OBS, in_a=0, in_b=14, out=16, n_out=1, slot=12, chol=sig(0.3)),                  # r   col 16
         mk(type=so.COPY_F32, out=17, n_out=3, slot=0, src=src[:, 1:4].copy()),                            # cols 17-19
         mk(type=so.GAUSS_PRIOR, out=20, n_out=3, slot=13, obs=[1.0, 2.0, 3.0], chol=chol),                # cols 20-22
+        mk(type=so.RANGE_PRIOR, out=23, n_out=2, slot=15, obs=[3.0, -1.0, 7.5], chol=sig(0.4)),           # P   cols 23-24
+        mk(type=so.R2_GEN_FWD, in_a=23, out=25, n_out=2, slot=17, obs=[5.0, -5.0, 0], chol=c2),            # Q   cols 25-26
+        mk(type=so.R2_GEN_BWD, in_a=25, out=27, n_out=2, slot=18, obs=[5.0, -5.0, 0], chol=c2),            # P'  cols 27-28
+        mk(type=so.R2_OBS, in_a=23, in_b=25, out=29, n_out=2, slot=19, chol=c2),                          # O   cols 29-30
     ]
 
 
 @pytest.mark.parametrize("n", [1, 257, 20_000])
 def test_simulate_every_op_matches_oracle(n):
     torch, _lib, lib, st = _ctx()
-    ops, keep, ld, seed = _all_ops(n), [], 23, 987654321
+    ops, keep, ld, seed = _all_ops(n), [], 31, 987654321
     arr = _op_dicts_to_ctypes(_lib, ops, keep, torch)
     s = torch.zeros((n, ld), dtype=torch.float64, device="cuda")
     _lib.check(lib.nfisam_simulate(arr, len(ops), ctypes.c_uint64(seed), s.data_ptr(), n, ld, 0, st))

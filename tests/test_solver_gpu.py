@@ -292,3 +292,47 @@ def test_device_resident_posterior_equals_host_loop():
     assert set(a.keys()) == set(b.keys())
     for v in a:
         assert np.array_equal(a[v], b[v]), v.name
+
+
+def test_r2_toy_example_solves_incrementally():
+    """example/slam/toy_examples/R2RangeGaussian_example/five_node_range_gaussian_incremental.py through the drop-in API: R2
+    variables, GaussianPriorFactor, R2RangeGaussianLikelihoodFactor and R2RelativeGaussianLikelihoodFactor (the factor class
+    round 1 lacked), three incremental steps.  Posterior means land on the example's geometry: l1 = (5, 5), x0 at range
+    5 sqrt(2) of l1, x1 = x0 + (5, -5), x2 = x1 + (5, 5), l2 = (10, 5)."""
+    import torch
+
+    from nfisam_b200.factors import GaussianPriorFactor, R2RangeGaussianLikelihoodFactor, R2RelativeGaussianLikelihoodFactor
+    from nfisam_b200.slam import R2Variable
+    from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
+
+    x0, x1, x2, l1, l2 = (R2Variable(n) for n in ("x0", "x1", "x2", "l1", "l2"))
+    sigma = 0.5
+    prior_l1 = GaussianPriorFactor(var=l1, mean=np.array([5.0, 5.0]), covariance=np.identity(2) * 0.5)
+    prior_l2 = GaussianPriorFactor(var=l2, mean=np.array([10.0, 5.0]), covariance=np.identity(2) * 0.5)
+    f_x0_l1 = R2RangeGaussianLikelihoodFactor(var1=x0, var2=l1, observation=5 * np.sqrt(2), sigma=sigma)
+    f_l1_x1 = R2RangeGaussianLikelihoodFactor(var1=l1, var2=x1, observation=10, sigma=sigma)
+    f_x0_x1 = R2RelativeGaussianLikelihoodFactor(var1=x0, var2=x1, observation=np.array([5, -5]), precision=np.array([[10, 0.0], [0.0, 10]]))
+    f_x1_x2 = R2RelativeGaussianLikelihoodFactor(var1=x1, var2=x2, observation=np.array([5, 5]), precision=np.array([[10, 0.0], [0.0, 10]]))
+    f_l2_x2 = R2RangeGaussianLikelihoodFactor(var1=l2, var2=x2, observation=5, sigma=sigma)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    model = NFiSAM(NFiSAMArgs(posterior_sample_num=500, flow_number=1, flow_type="NSF_AR", flow_iterations=800, local_sample_num=1000,
+                              cuda_training=True, store_clique_samples=False, num_knots=15))
+    for nodes, factors in (([l1, x0], [prior_l1, f_x0_l1]), ([x1], [f_x0_x1, f_l1_x1]), ([x2, l2], [prior_l2, f_x1_x2, f_l2_x2])):
+        for v in nodes:
+            model.add_node(v)
+        for f in factors:
+            model.add_factor(f)
+        model.update_physical_and_working_graphs()
+        samples = model.incremental_inference()
+    assert set(samples) == {x0, x1, x2, l1, l2} and all(s.shape == (500, 2) for s in samples.values())
+    m = {v.name: samples[v].mean(0) for v in samples}
+    assert np.linalg.norm(m["l1"] - [5.0, 5.0]) < 1.0 and np.linalg.norm(m["l2"] - [10.0, 5.0]) < 1.0
+    d = samples[x1] - samples[x0]
+    assert np.linalg.norm(d.mean(0) - [5.0, -5.0]) < 0.5 and np.all(d.std(0) < 1.0)          # the displacement factor binds x0 -> x1
+    d = samples[x2] - samples[x1]
+    assert np.linalg.norm(d.mean(0) - [5.0, 5.0]) < 0.5
+    r = np.linalg.norm(samples[x0] - samples[l1], axis=1)
+    assert abs(np.median(r) - 5 * np.sqrt(2)) < 1.0
+    r = np.linalg.norm(samples[x2] - samples[l2], axis=1)
+    assert abs(np.median(r) - 5.0) < 1.0
