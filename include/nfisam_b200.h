@@ -274,6 +274,13 @@ int nfisam_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const dou
 int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_desc, const double* x_dev, int64_t n,
                                      int D, double* weights_out_host, int device, void* stream);
 
+/* posterior_weights of n_groups mixtures in ONE launch ("next" row N2: the reference calls posterior_weights once per mixture
+ * factor and incremental step, src/slam/FactorGraphSolver.py:913-922).  descs_host holds the components of all groups back to
+ * back, group g owning group_sizes_host[g] (1..16) consecutive descriptors; columns index ONE sample matrix x_dev (n, D) that
+ * holds every variable.  weights_out_host: n_desc doubles, normalised per group.  Synchronous. */
+int nfisam_mixture_posterior_weights_batch(const nf_factor_desc* descs_host, int n_desc, const int32_t* group_sizes_host, int n_groups,
+                                           const double* x_dev, int64_t n, int D, double* weights_out_host, int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Clique training-set simulator ("next" row N1)  -- replaces SimulationBasedSampler.sample
  * (src/sampler/SimulationBasedSampler.py:14-134) and the factor .sample methods it calls
@@ -359,6 +366,15 @@ typedef enum nf_mmd_kind {
  * Replaces the dense n x n host matrices of the reference.  Synchronous (the result is a host scalar). */
 int nfisam_mmd(const double* x_dev, int64_t m, const double* y_dev, int64_t n, int d, double sigma, int kind,
                double* result_host, double* sums_host, int device, void* stream);
+
+/* Per-variable mean and covariance of a posterior sample matrix ("next" row N2), s_dev (n, ld) float32 on `device`:
+ * variable v owns columns col0_host[v] .. + dim_host[v] (1..3).  sample_mean (src/utils/Statistics.py:151-171): circular columns
+ * (circular_host[column] != 0, ld entries) get the circular mean scipy.stats.circmean(high = pi, low = -pi), the others the
+ * arithmetic mean; the covariance block is the population covariance of the deviations from it, circular deviations wrapped
+ * to [-pi, pi) (the convention of src/slam/NFiSAM.py:519-546).  mean_out_host: n_vars x 3, cov_out_host: n_vars x 9 (row-major
+ * 3 x 3, entries past dim are 0).  One launch, float64 accumulation, fixed-order reductions.  Synchronous. */
+int nfisam_marginal_stats(const float* s_dev, int64_t n, int ld, const int32_t* col0_host, const int32_t* dim_host, int n_vars,
+                          const uint8_t* circular_host, double* mean_out_host, double* cov_out_host, int device, void* stream);
 
 #ifdef __cplusplus
 }

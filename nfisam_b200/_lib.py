@@ -137,6 +137,10 @@ SYMBOLS = {
     "nfisam_flow_loss_grad": (_INT, [_P, _P, _I64, _P, _P, _P]),
     "nfisam_factor_logpdf": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _P, _INT, _P]),
     "nfisam_mixture_posterior_weights": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _INT, _P]),
+    "nfisam_mixture_posterior_weights_batch": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, ctypes.POINTER(ctypes.c_int32), _INT, _P, _I64,
+                                               _INT, _P, _INT, _P]),
+    "nfisam_marginal_stats": (_INT, [_P, _I64, _INT, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _INT, _P, _P, _P,
+                                     _INT, _P]),
     "nfisam_simulate": (_INT, [ctypes.POINTER(nf_sim_op), _INT, ctypes.c_uint64, _P, _I64, _INT, _INT, _P]),
     "nfisam_sim_noise": (_INT, [ctypes.c_uint64, _INT, _INT, _P, _I64, _INT, _P]),
     "nfisam_randn_f32": (_INT, [ctypes.c_uint64, _INT, _P, _I64, _INT, _INT, _INT, _P]),

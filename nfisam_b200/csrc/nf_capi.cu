@@ -1017,6 +1017,95 @@ int nfisam_mixture_posterior_weights(const nf_factor_desc* descs_host, int n_des
     return NF_OK;
 }
 
+int nfisam_mixture_posterior_weights_batch(const nf_factor_desc* descs_host, int n_desc, const int32_t* group_sizes_host, int n_groups,
+                                           const double* x_dev, int64_t n, int D, double* weights_out_host, int device, void* stream) {
+    if (!descs_host || n_desc < 1 || !group_sizes_host || n_groups < 1 || !x_dev || !weights_out_host || n < 1 || D < 1)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    std::vector<nf_factor_desc> tmp(descs_host, descs_host + n_desc);
+    std::vector<int2> groups((size_t)n_groups);
+    int at = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const int nc = group_sizes_host[g];
+        if (nc < 1 || nc > 16 || at + nc > n_desc) return nf_set_error(NF_ERR_BAD_ARG, "group %d: bad size %d (1..16 components)", g, nc);
+        groups[(size_t)g] = make_int2(at, nc);
+        tmp[(size_t)at].n_comp = nc;
+        for (int c = 1; c < nc; ++c) tmp[(size_t)at + c].n_comp = 0;
+        at += nc;
+    }
+    if (at != n_desc) return nf_set_error(NF_ERR_BAD_ARG, "group sizes sum to %d, %d descriptors given", at, n_desc);
+    int n_check = 0;
+    int rc = validate_descs(tmp.data(), n_desc, D, &n_check);
+    if (rc != NF_OK) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int bpg = (int)((n + 127) / 128);
+    if (bpg > 8) bpg = 8;
+    const size_t desc_bytes = sizeof(nf_factor_desc) * (size_t)n_desc, grp_bytes = sizeof(int2) * (size_t)n_groups;
+    const size_t part_elems = (size_t)n_groups * bpg * 16;
+    unsigned char* d_buf = static_cast<unsigned char*>(nf_pool_alloc(device, desc_bytes + grp_bytes + 256 + part_elems * sizeof(double)));
+    if (!d_buf) return nf_set_error(NF_ERR_OOM, "device allocation failed");
+    const size_t part_off = (desc_bytes + grp_bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMemcpyAsync(d_buf, tmp.data(), desc_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_buf + desc_bytes, groups.data(), grp_bytes, cudaMemcpyHostToDevice, st);
+    double* d_part = reinterpret_cast<double*>(d_buf + part_off);
+    if (e == cudaSuccess)
+        rc = nf_launch_mixture_weights_batch(reinterpret_cast<const nf_factor_desc*>(d_buf), reinterpret_cast<const int2*>(d_buf + desc_bytes),
+                                             n_groups, x_dev, n, D, d_part, bpg, st);
+    std::vector<double> part(part_elems);
+    if (e == cudaSuccess && rc == NF_OK) e = cudaMemcpyAsync(part.data(), d_part, part_elems * sizeof(double), cudaMemcpyDeviceToHost, st);
+    const cudaError_t es = cudaStreamSynchronize(st);
+    nf_pool_free(device, d_buf, nullptr);
+    if (e != cudaSuccess) return nf_cuda_fail(e, "nfisam_mixture_posterior_weights_batch");
+    if (es != cudaSuccess) return nf_cuda_fail(es, "cudaStreamSynchronize");
+    if (rc != NF_OK) return rc;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        double total = 0.0;
+        double w[16];
+        for (int c = 0; c < groups[(size_t)gi].y; ++c) {
+            double v = 0.0;
+            for (int b = 0; b < bpg; ++b) v += part[((size_t)gi * bpg + b) * 16 + c];
+            w[c] = v;
+            total += v;
+        }
+        for (int c = 0; c < groups[(size_t)gi].y; ++c) weights_out_host[groups[(size_t)gi].x + c] = w[c] / total;
+    }
+    return NF_OK;
+}
+
+int nfisam_marginal_stats(const float* s_dev, int64_t n, int ld, const int32_t* col0_host, const int32_t* dim_host, int n_vars,
+                          const uint8_t* circular_host, double* mean_out_host, double* cov_out_host, int device, void* stream) {
+    if (!s_dev || n < 1 || ld < 1 || n_vars < 1 || !col0_host || !dim_host || !circular_host || !mean_out_host || !cov_out_host)
+        return nf_set_error(NF_ERR_BAD_ARG, "bad argument");
+    for (int v = 0; v < n_vars; ++v)
+        if (dim_host[v] < 1 || dim_host[v] > 3 || col0_host[v] < 0 || col0_host[v] + dim_host[v] > ld)
+            return nf_set_error(NF_ERR_BAD_ARG, "variable %d: bad column range (1..3 columns inside the matrix)", v);
+    DeviceGuard g(device);
+    if (!g.ok) return nf_set_error(NF_ERR_BAD_ARG, "cannot select device %d", device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t idx_bytes = ((sizeof(int32_t) * 2 * (size_t)n_vars + (size_t)ld + 255) & ~(size_t)255);
+    const size_t out_bytes = sizeof(double) * 12 * (size_t)n_vars;
+    unsigned char* d_buf = static_cast<unsigned char*>(nf_pool_alloc(device, idx_bytes + out_bytes));
+    if (!d_buf) return nf_set_error(NF_ERR_OOM, "device allocation failed");
+    int32_t* d_col0 = reinterpret_cast<int32_t*>(d_buf);
+    int32_t* d_dim = d_col0 + n_vars;
+    uint8_t* d_circ = reinterpret_cast<uint8_t*>(d_dim + n_vars);
+    double* d_mean = reinterpret_cast<double*>(d_buf + idx_bytes);
+    double* d_cov = d_mean + 3 * (size_t)n_vars;
+    cudaError_t e = cudaMemcpyAsync(d_col0, col0_host, sizeof(int32_t) * (size_t)n_vars, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_dim, dim_host, sizeof(int32_t) * (size_t)n_vars, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_circ, circular_host, (size_t)ld, cudaMemcpyHostToDevice, st);
+    int rc = NF_OK;
+    if (e == cudaSuccess) rc = nf_launch_marginal_stats(s_dev, n, ld, d_col0, d_dim, d_circ, n_vars, d_mean, d_cov, st);
+    if (e == cudaSuccess && rc == NF_OK) e = cudaMemcpyAsync(mean_out_host, d_mean, sizeof(double) * 3 * (size_t)n_vars, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == NF_OK) e = cudaMemcpyAsync(cov_out_host, d_cov, sizeof(double) * 9 * (size_t)n_vars, cudaMemcpyDeviceToHost, st);
+    const cudaError_t es = cudaStreamSynchronize(st);
+    nf_pool_free(device, d_buf, nullptr);
+    if (e != cudaSuccess) return nf_cuda_fail(e, "nfisam_marginal_stats");
+    if (es != cudaSuccess) return nf_cuda_fail(es, "cudaStreamSynchronize");
+    return rc;
+}
+
 // ---- training-set simulator (nf_sim_kernels.cu) ----------------------------------------------------------------------
 int nfisam_simulate(const nf_sim_op* ops_host, int n_ops, uint64_t seed, double* s_dev, int64_t n, int ld, int device,
                     void* stream) {

@@ -223,6 +223,50 @@ nf_mixture_weights_kernel(const nf_factor_desc* __restrict__ descs, int n_desc, 
     }
 }
 
+// posterior_weights of MANY mixture groups in one launch ("next" row N2: FactorGraphSolver.py:913-922 calls
+// posterior_weights once per mixture factor and step): blockIdx.y = group, the blocks of a group split the rows.
+// groups[g] = (first descriptor, number of components); partial[(g * gridDim.x + blockIdx.x) * 16 + c].
+__global__ void __launch_bounds__(FTPB)
+nf_mixture_weights_batch_kernel(const nf_factor_desc* __restrict__ descs, const int2* __restrict__ groups, const double* __restrict__ x,
+                                int64_t n, int D, double* __restrict__ partial) {
+    __shared__ double red[FTPB / 32][16];
+    const int2 grp = groups[blockIdx.y];
+    const nf_factor_desc* gd = descs + grp.x;
+    const int nc = grp.y;
+    double acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.0;
+    for (int64_t s = (int64_t)blockIdx.x * FTPB + threadIdx.x; s < n; s += (int64_t)gridDim.x * FTPB) {
+        const double* xr = x + s * D;
+        double lik[16];
+        double sum = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            lik[c] = 0.0;
+            if (c < nc) {
+                lik[c] = exp(component_logpdf(gd[c], xr, 1)) * gd[c].weight;
+                sum += lik[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            if (c < nc) acc[c] += (sum == 0.0) ? 0.5 : lik[c] / sum;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        double v = acc[c];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double v = 0.0;
+        for (int w = 0; w < FTPB / 32; ++w) v += red[w][threadIdx.x];
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + threadIdx.x] = v;
+    }
+}
+
 template <typename KernelT>
 int factor_grid(KernelT kern, size_t smem, int64_t n, int device) {
     int per_sm = 0;
@@ -291,4 +335,13 @@ int nf_launch_mixture_weights(const nf_factor_desc* descs_dev, int n_desc, const
     nf_count_launch();
     *n_partial = (int)blocks;
     return nf_check_launch("nf_mixture_weights_kernel");
+}
+
+int nf_launch_mixture_weights_batch(const nf_factor_desc* descs_dev, const int2* groups_dev, int n_groups, const double* x, int64_t n,
+                                    int D, double* partial_dev, int blocks_per_group, cudaStream_t st) {
+    if (n_groups <= 0 || n <= 0) return NF_OK;
+    const dim3 grid((unsigned)blocks_per_group, (unsigned)n_groups);
+    nf_mixture_weights_batch_kernel<<<grid, FTPB, 0, st>>>(descs_dev, groups_dev, x, n, D, partial_dev);
+    nf_count_launch();
+    return nf_check_launch("nf_mixture_weights_batch_kernel");
 }

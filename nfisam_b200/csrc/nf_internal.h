@@ -110,6 +110,9 @@ int nf_launch_posterior_pass(const NfFlowDims& fd, const NfPassItem* items_dev, 
                              int max_wcount, int max_d, const float* z, int ld_z, float* s_mat, int ld_s, int64_t n,
                              unsigned long long* bad, int device, cudaStream_t st);
 
+int nf_launch_mixture_weights_batch(const nf_factor_desc* descs_dev, const int2* groups_dev, int n_groups, const double* x, int64_t n,
+                                    int D, double* partial_dev, int blocks_per_group, cudaStream_t st);
+
 // nf_sim_kernels.cu
 int nf_launch_simulate(const nf_sim_op* ops, int n_ops, uint64_t seed, double* s_mat, int64_t n, int ld, cudaStream_t st);
 int nf_launch_sim_noise(uint64_t seed, int slot, int normal, double* out, int64_t n, cudaStream_t st);
@@ -121,6 +124,9 @@ int nf_launch_normalize(const double* s_mat, int64_t n_rows, int ld, const int32
 size_t nf_rbf_sum_workspace(int64_t m, int64_t n);
 int nf_launch_rbf_sum(const double* x, int64_t m, const double* y, int64_t n, int d, double sigma, int skip_diag,
                       double* partial, double* out, cudaStream_t st);
+
+int nf_launch_marginal_stats(const float* s_mat, int64_t n, int ld, const int32_t* col0_dev, const int32_t* dim_dev,
+                             const uint8_t* circular_dev, int n_vars, double* mean_dev, double* cov_dev, cudaStream_t st);
 
 // nf_pool.cu: cached device memory, reuse ordered by events instead of the device-wide synchronisation of cudaFree
 struct NfEvent {

@@ -167,3 +167,95 @@ int nf_launch_rbf_sum(const double* x, int64_t m, const double* y, int64_t n, in
     nf_count_launch();
     return nf_check_launch("nf_rbf_sum_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Posterior post-processing on the device ("next" row N2): per-variable mean and covariance of the posterior sample matrix.
+//   sample_mean (src/utils/Statistics.py:151-171): circular columns get scipy.stats.circmean(high = pi, low = -pi), the others
+//   the arithmetic mean.  The covariance block of a variable is the population covariance of the deviations from that mean,
+//   circular deviations wrapped to [-pi, pi) (the convention of NFiSAM.normalize_training_samples, src/slam/NFiSAM.py:519-546).
+// One block per variable (<= 3 columns, float32 sample matrix with row stride ld); float64 accumulation, fixed-order
+// reductions: bitwise reproducible.  n is a posterior sample count (500 - 1000): the launch is latency-bound by design.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int MS_T = 128;
+constexpr double MS_PI = 3.14159265358979323846, MS_TWO_PI = 6.28318530717958647692;
+
+__device__ __forceinline__ double ms_wrap(double t) {
+    double r = fmod(t + MS_PI, MS_TWO_PI);
+    if (r < 0.0) r += MS_TWO_PI;
+    return r - MS_PI;
+}
+
+template <int NV>
+__device__ __forceinline__ void ms_block_sum(double (&v)[NV], double (*red)[NV]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = v[k];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (lane == 0) red[warp][k] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+        for (int w = 0; w < MS_T / 32; ++w) t += red[w][k];
+        v[k] = t;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MS_T)
+nf_marginal_stats_kernel(const float* __restrict__ s_mat, int64_t n, int ld, const int32_t* __restrict__ col0, const int32_t* __restrict__ dim,
+                         const uint8_t* __restrict__ circular, double* __restrict__ mean_out, double* __restrict__ cov_out) {
+    __shared__ double red6[MS_T / 32][6];
+    const int v = blockIdx.x, c0 = col0[v], dv = dim[v];
+    bool circ[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) circ[k] = k < dv && circular[c0 + k] != 0;
+    // pass 1: sums of (x) or (sin x, cos x)
+    double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t r = threadIdx.x; r < n; r += MS_T) {
+        const float* row = s_mat + r * ld + c0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k < dv) {
+                const double x = (double)row[k];
+                if (circ[k]) { double sn, cs; sincos(x, &sn, &cs); a[2 * k] += sn; a[2 * k + 1] += cs; }
+                else a[2 * k] += x;
+            }
+    }
+    ms_block_sum<6>(a, red6);
+    double mean[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        if (k < dv) mean[k] = circ[k] ? ms_wrap(atan2(a[2 * k], a[2 * k + 1])) : a[2 * k] / (double)n;
+    // pass 2: second moments of the (wrapped) deviations: xx xy xz yy yz zz
+    double m2[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t r = threadIdx.x; r < n; r += MS_T) {
+        const float* row = s_mat + r * ld + c0;
+        double e[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k < dv) { e[k] = (double)row[k] - mean[k]; if (circ[k]) e[k] = ms_wrap(e[k]); }
+        m2[0] += e[0] * e[0]; m2[1] += e[0] * e[1]; m2[2] += e[0] * e[2];
+        m2[3] += e[1] * e[1]; m2[4] += e[1] * e[2]; m2[5] += e[2] * e[2];
+    }
+    ms_block_sum<6>(m2, red6);
+    if (threadIdx.x == 0) {
+        const double inv = 1.0 / (double)n;
+        for (int k = 0; k < 3; ++k) mean_out[3 * v + k] = mean[k];
+        double* cv = cov_out + 9 * (size_t)v;
+        cv[0] = m2[0] * inv; cv[1] = cv[3] = m2[1] * inv; cv[2] = cv[6] = m2[2] * inv;
+        cv[4] = m2[3] * inv; cv[5] = cv[7] = m2[4] * inv; cv[8] = m2[5] * inv;
+    }
+}
+}  // namespace
+
+int nf_launch_marginal_stats(const float* s_mat, int64_t n, int ld, const int32_t* col0_dev, const int32_t* dim_dev,
+                             const uint8_t* circular_dev, int n_vars, double* mean_dev, double* cov_dev, cudaStream_t st) {
+    if (n_vars <= 0) return NF_OK;
+    nf_marginal_stats_kernel<<<n_vars, MS_T, 0, st>>>(s_mat, n, ld, col0_dev, dim_dev, circular_dev, mean_dev, cov_dev);
+    nf_count_launch();
+    return nf_check_launch("nf_marginal_stats_kernel");
+}

@@ -82,3 +82,26 @@ def mixture_posterior_weights(components, x, device=None):
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(lib.nfisam_mixture_posterior_weights(arr, nd, xd.data_ptr(), n, D, w.ctypes.data_as(ctypes.c_void_p), di, stream))
     return w
+
+
+def mixture_posterior_weights_batch(groups, x, device=None):
+    """posterior_weights of several mixtures over ONE sample matrix x (n, D) in one launch
+    (nfisam_mixture_posterior_weights_batch).  groups: list of component lists with global column indices.  Returns a list of
+    weight vectors."""
+    lib = _lib.load()
+    _lib.require_device()
+    di = _device_index(device if not torch.is_tensor(x) or not x.is_cuda else x.device)
+    dev = torch.device("cuda", di)
+    xd = (x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))).to(dev, torch.float64).contiguous()
+    n, D = xd.shape
+    arr, nd = pack_descs(groups)
+    sizes = (ctypes.c_int32 * len(groups))(*[len(g) for g in groups])
+    w = np.zeros(nd, np.float64)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(lib.nfisam_mixture_posterior_weights_batch(arr, nd, sizes, len(groups), xd.data_ptr(), n, D,
+                                                          w.ctypes.data_as(ctypes.c_void_p), di, stream))
+    out, at = [], 0
+    for g in groups:
+        out.append(w[at:at + len(g)].copy())
+        at += len(g)
+    return out

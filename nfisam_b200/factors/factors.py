@@ -514,6 +514,22 @@ class BinaryFactorMixture(LikelihoodFactor):
         return _gpu.mixture_posterior_weights(self.components(_local_cols(self.vars)), x)
 
 
+def posterior_weights_batch(mixtures: List["BinaryFactorMixture"], var2x: Dict[Variable, np.ndarray]) -> List[np.ndarray]:
+    """BinaryFactorMixture.posterior_weights (Factors.py:3159-3180) of every mixture of a step in ONE kernel launch over one
+    sample matrix (the reference's driver calls it once per factor, src/slam/FactorGraphSolver.py:913-922)."""
+    if not mixtures:
+        return []
+    variables, col_of, off = [], {}, 0
+    for f in mixtures:
+        for v in f.vars:
+            if v not in col_of:
+                col_of[v] = off
+                off += v.dim
+                variables.append(v)
+    x = np.concatenate([np.asarray(var2x[v], dtype=np.float64) for v in variables], axis=1)
+    return _gpu.mixture_posterior_weights_batch([f.components(col_of) for f in mixtures], x)
+
+
 class AmbiguousDataAssociationFactor(BinaryFactorMixture, KWayFactor):
     """k candidate landmarks for one measurement, same observation and sigma (Factors.py:3192-3297)."""
 

@@ -13,7 +13,7 @@ from typing import Dict, List
 
 import numpy as np
 
-from ..factors.factors import BinaryFactorMixture, Factor, ImplicitPriorFactor
+from ..factors.factors import BinaryFactorMixture, Factor, ImplicitPriorFactor, posterior_weights_batch
 from .bayes_tree import BayesTreeNode
 from .factor_graph import FactorGraph
 from .simulation_sampler import SimulationBasedSampler
@@ -38,6 +38,16 @@ class SolverArgs:
 class CliqueSeparatorFactor(ImplicitPriorFactor):
     def sample(self, num_samples: int, **kwargs):
         raise NotImplementedError("implementation depends on density models")
+
+
+class _SymbolicSeparatorFactor(CliqueSeparatorFactor):
+    """Stand-in for a child clique's separator factor in FactorGraphSolver.dry_run_schedule: a prior over the separator
+    variables that is never sampled."""
+
+    def __init__(self, variables):
+        self._vars = list(variables)
+
+    vars = property(lambda self: self._vars)
 
 
 class ConditionalSampler:
@@ -83,6 +93,15 @@ class FactorGraphSolver:
 
     # -- ordering -----------------------------------------------------------------------------------
     def generate_ordering(self) -> None:
+        """Elimination ordering of all variables (physical + new).
+          natural       the order in which variables were added                      (FactorGraphSolver.py:157-161)
+          pose_first    natural order, landmarks moved to the end                    (FactorGraphSolver.py:163-175)
+          prior_rooted  ("next" row N3) poses by graph distance from the nearest prior-carrying pose, the regions of the priors
+                        interleaved, landmarks last -- see `_prior_rooted_order`.
+        The reference's third method, constrained COLAMD on the working graph with the newest pose last
+        (FactorGraph.py:106-154), cannot run in the reference (the import is commented out and its Cython wrapper returns
+        None); orderings of that family (minimum degree, nested dissection) produce leaf cliques without a
+        prior, which the simulation-based sampler cannot start from."""
         natural = self._physical_graph.vars + self._new_nodes
         method = self._args.elimination_method
         if method == "natural":
@@ -90,10 +109,56 @@ class FactorGraphSolver:
         elif method == "pose_first":
             order = [v for v in natural if v.type != VariableType.Landmark] + \
                     [v for v in natural if v.type == VariableType.Landmark]
+        elif method == "prior_rooted":
+            order = self._prior_rooted_order(natural)
         else:
             raise ValueError(f"elimination method {method!r} is not supported (the reference's ccolamd path is dead code)")
         self._elimination_ordering = order
         self._reverse_ordering_map = {v: k for k, v in enumerate(order[::-1])}
+
+    def _prior_rooted_order(self, natural: List[Variable]) -> List[Variable]:
+        """Ordering that attains the width the simulation-based sampler allows.
+
+        Ancestral sampling of a clique (SimulationBasedSampler.py:14-134) has to START somewhere: from an explicit prior among
+        the clique's factors or from the separator factor of a child clique.  A leaf clique has no children, so every leaf of
+        the Bayes tree must contain a prior-carrying variable, and the number of cliques that can train concurrently is
+        bounded by the number of priors: a single-robot graph (one prior) is necessarily a chain, whatever the ordering; an
+        R-robot graph has width at most R.  This ordering attains the bound without relying on how the variables are named or
+        in which order they were added (pose_first reaches it only when the robots' poses arrive time step by time step):
+        every non-landmark variable is assigned to the nearest prior-carrying variable (multi-source breadth-first search over
+        the factor graph, landmarks not traversed) and poses are eliminated by increasing distance, the regions of the priors
+        interleaved; landmarks (shared between regions) come last.  Distances are assigned when a variable is first linked and
+        never change, so the relative order of known variables is stable across incremental steps."""
+        info = self.__dict__.setdefault("_prior_rooted_info", {})       # variable -> (distance, region, arrival)
+        regions = self.__dict__.setdefault("_prior_rooted_regions", {})  # prior-carrying variable -> region index
+        factors = self._new_factors if info else self._physical_graph.factors + self._new_factors
+        for f in factors:
+            vs = f.vars
+            if len(vs) == 1 and vs[0].type != VariableType.Landmark and vs[0] not in regions and not isinstance(f, ImplicitPriorFactor):
+                regions[vs[0]] = len(regions)
+                info[vs[0]] = (0, regions[vs[0]], len(info))
+        adjacency = {}
+        for f in factors:
+            poses = [v for v in f.vars if v.type != VariableType.Landmark]
+            for a in poses:
+                for b in poses:
+                    if a is not b:
+                        adjacency.setdefault(a, []).append(b)
+        frontier = [v for v in adjacency if v in info]
+        while frontier:
+            nxt = []
+            for a in frontier:
+                da, ra, _ = info[a]
+                for b in adjacency.get(a, ()):
+                    if b not in info:
+                        info[b] = (da + 1, ra, len(info))
+                        nxt.append(b)
+            frontier = nxt
+        far = 1 << 30
+        poses = [v for v in natural if v.type != VariableType.Landmark]
+        arrival = {v: k for k, v in enumerate(natural)}
+        poses.sort(key=lambda v: info.get(v, (far, far, 0))[:2] + (arrival[v],))
+        return poses + [v for v in natural if v.type == VariableType.Landmark]
 
     # -- graph building -----------------------------------------------------------------------------
     def add_node(self, var: Variable = None, name: str = None, dim: int = None) -> "FactorGraphSolver":
@@ -213,6 +278,34 @@ class FactorGraphSolver:
         else:
             self._working_graph = self._working_graph.eliminate_clique_variables(clique=clique, new_factor=new_factor)
 
+    def dry_run_schedule(self):
+        """Symbolic pass over the working tree, leaves first, without sampling or training: for every clique the schedule its
+        simulation-based sampler would follow (SimulationBasedSampler.plan) or the reason it cannot be sampled ancestrally
+        (no prior / separator factor to start from, a pose reachable only from a landmark, ...).  Returns a list of levels,
+        each a list of (clique, plan-or-None, error-or-None).  The solver's graphs are not modified.  Lets a caller validate an
+        elimination ordering before spending a step on it (the reference's sampler loops forever on such cliques,
+        SimulationBasedSampler.py:42-92)."""
+        graph = self._working_graph
+        out = []
+        for level in self._working_bayes_tree.levels():
+            row = []
+            for c in level:
+                if c in self._clique_density_model:
+                    row.append((c, None, None))
+                    continue
+                sub = graph.get_clique_factor_graph(c)
+                placeholder = None
+                if c.separator:
+                    placeholder = _SymbolicSeparatorFactor(sorted(c.separator, key=lambda v: self._reverse_ordering_map[v]))
+                graph = graph.eliminate_clique_variables(clique=c, new_factor=placeholder)
+                try:
+                    plan = SimulationBasedSampler(factors=sub.factors, vars=self._working_bayes_tree.clique_variable_pattern(c)).plan()
+                    row.append((c, plan, None))
+                except ValueError as e:
+                    row.append((c, None, str(e)))
+            out.append(row)
+        return out
+
     def fit_tree_density_models(self, timer: List[float] = None, clique_dim_timer: List[List[float]] = None, *args, **kwargs):
         """Leaves -> root: simulate a training set, fit the clique density, turn it into a separator
         factor for the parent.  Serial version (one clique at a time, like FactorGraphSolver.py:409-477);
@@ -267,6 +360,16 @@ class FactorGraphSolver:
     def results(self):
         return list(self._samples.values()), list(self._physical_graph.vars)
 
+    def posterior_statistics(self):
+        """{variable: (mean, covariance)} of the current posterior samples: circular-aware means like the reference's
+        sample_mean (src/utils/Statistics.py:151-171) plus the per-variable covariance blocks, one kernel launch for the whole
+        graph (nfisam_marginal_stats, "next" row N2)."""
+        from ..utils.statistics import marginal_mean_cov
+
+        order = [v for v in self._elimination_ordering if v in self._samples]
+        _, var2mean, var2cov = marginal_mean_cov(np.hstack([self._samples[v] for v in order]), order)
+        return {v: (var2mean[v], var2cov[v]) for v in order}
+
 
 def run_incrementally(case_dir: str, solver: FactorGraphSolver, nodes_factors_by_step, truth=None, traj_plot=False,
                       plot_args=None, check_root_transform=False) -> str:
@@ -312,11 +415,11 @@ def run_incrementally(case_dir: str, solver: FactorGraphSolver, nodes_factors_by
             with open(f"{run_dir}/{name}", "w") as fh:
                 fh.write(" ".join(str(t) for t in arr))
         if mixtures:
+            # all mixtures of the step in one launch (the reference loops over the factors, FactorGraphSolver.py:913-922)
+            active = [factor for factor in mixtures if set(factor.vars).issubset(cur.keys())]
+            weights = posterior_weights_batch(active, cur)
             with open(f"{run_dir}/step{i}.hypoweights", "w") as fh:
-                for factor, history in mixtures.items():
-                    if not set(factor.vars).issubset(cur.keys()):
-                        continue
-                    w = factor.posterior_weights(cur)
-                    history.append(w)
+                for factor, w in zip(active, weights):
+                    mixtures[factor].append(w)
                     fh.write(" ".join(str(v.name) for v in factor.vars) + " : " + ",".join(str(x) for x in w) + "\n")
     return run_dir

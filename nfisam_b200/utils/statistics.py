@@ -1,5 +1,6 @@
-"""Two-sample statistics of the reference's post-processing (src/utils/Statistics.py:13-84) on the device:
-`mmd`, `MMDu2`, `MMDb` with the reference's names, arguments and return values.  The Gaussian-kernel sums run in
+"""Statistics of the reference's post-processing (src/utils/Statistics.py) on the device: the two-sample estimators
+`mmd`, `MMDu2`, `MMDb` (:13-84) and `sample_mean` (:151-171, circular-aware means; `marginal_mean_cov` adds the per-variable
+covariance blocks) with the reference's names, arguments and return values.  The Gaussian-kernel sums run in
 float64 in libnfisam_b200.so (nfisam_mmd, csrc/nf_stats_kernels.cu); there is no host fallback."""
 import ctypes
 
@@ -48,3 +49,43 @@ def mmd(samples1, samples2, k_sigma2: float = 1.0):
     """sqrt of the unbiased estimate with the Gaussian pdf ratio N(delta; 0, k_sigma2 I) / N(0; 0, k_sigma2 I)
     as kernel (src/utils/Statistics.py:13-44)."""
     return _mmd(samples1, samples2, float(np.sqrt(k_sigma2)), 2)
+
+
+def marginal_mean_cov(samples, var_ordering):
+    """Per-variable mean and covariance of posterior samples whose columns follow `var_ordering`, in one kernel launch
+    (nfisam_marginal_stats): circular columns get the circular mean and wrapped deviations.  `samples`: (n, D) numpy array or
+    CUDA tensor (float32 on the device is used as it is).  Returns (means (D,), {var: mean}, {var: covariance (dim, dim)})."""
+    lib = _lib.load()
+    _lib.require_device()
+    if torch.is_tensor(samples) and samples.is_cuda:
+        t = samples.detach().to(torch.float32).contiguous()
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(samples, dtype=np.float32))).to(torch.device("cuda", torch.cuda.current_device()))
+    n, D = t.shape
+    col0, dims, circ, off = [], [], [], 0
+    for v in var_ordering:
+        if v.dim > 3:
+            raise ValueError("marginal statistics cover variables of dimension <= 3 (SE(2) poses, R2 landmarks)")
+        col0.append(off)
+        dims.append(v.dim)
+        circ += [1 if c else 0 for c in v.circular_dim_list]
+        off += v.dim
+    if off != D:
+        raise ValueError(f"samples have {D} columns, the variables need {off}")
+    nv = len(col0)
+    mean = np.zeros((nv, 3))
+    cov = np.zeros((nv, 9))
+    stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    _lib.check(lib.nfisam_marginal_stats(t.data_ptr(), n, D, (ctypes.c_int32 * nv)(*col0), (ctypes.c_int32 * nv)(*dims), nv,
+                                         (ctypes.c_uint8 * D)(*circ), mean.ctypes.data_as(ctypes.c_void_p),
+                                         cov.ctypes.data_as(ctypes.c_void_p), t.device.index, stream))
+    means = np.concatenate([mean[k, :d] for k, d in enumerate(dims)])
+    var2mean = {v: mean[k, :v.dim].copy() for k, v in enumerate(var_ordering)}
+    var2cov = {v: cov[k].reshape(3, 3)[:v.dim, :v.dim].copy() for k, v in enumerate(var_ordering)}
+    return means, var2mean, var2cov
+
+
+def sample_mean(samples, var_ordering):
+    """(means, {var: mean}) like the reference's sample_mean (src/utils/Statistics.py:151-171)."""
+    means, var2mean, _ = marginal_mean_cov(samples, var_ordering)
+    return means, var2mean

@@ -40,3 +40,18 @@ def mmd(x, y, k_sigma2=1.0):
     """Statistics.py:13-44: the pdf normalisation cancels against gaussian.pdf(0)."""
     with np.errstate(invalid="ignore"):
         return float(np.sqrt(MMDu2(x, y, np.sqrt(k_sigma2))))
+
+
+def sample_mean_cov(samples, circular):
+    """Column means like the reference's sample_mean (src/utils/Statistics.py:151-171: scipy.stats.circmean(high = pi, low = -pi)
+    on circular columns, arithmetic mean elsewhere) and the population covariance of the deviations from them, circular
+    deviations wrapped to [-pi, pi) (the convention of NFiSAM.normalize_training_samples, src/slam/NFiSAM.py:519-546)."""
+    x = np.asarray(samples, np.float64)
+    circ = np.asarray(circular, bool)
+    mean = x.mean(0)
+    if circ.any():
+        res = np.arctan2(np.sin(x[:, circ]).sum(0), np.cos(x[:, circ]).sum(0))
+        mean[circ] = (res + np.pi) % (2 * np.pi) - np.pi
+    dev = x - mean
+    dev[:, circ] = (dev[:, circ] + np.pi) % (2 * np.pi) - np.pi
+    return mean, dev.T @ dev / x.shape[0]

@@ -31,5 +31,14 @@ x = rng.normal(size=(50, 4))
 out["same_x"] = x
 out["same_mmdb"] = MMDb(x, x.copy(), 1.5)
 out["same_mmdu2"] = MMDu2(x, x.copy(), 1.5)
+# sample_mean (src/utils/Statistics.py:151-171) on a posterior-like matrix: X0 (SE2), L1 (R2), X1 (SE2) with angles straddling +-pi
+from slam.Variables import R2Variable, SE2Variable  # noqa: E402
+from utils.Statistics import sample_mean  # noqa: E402
+
+order = [SE2Variable("X0"), R2Variable("L1"), SE2Variable("X1")]
+xs = rng.normal(size=(700, 8)) * np.array([2.0, 3.0, 0.4, 5.0, 1.0, 0.5, 0.7, 1.2]) + np.array([10.0, -4.0, 3.0, 1.0, 2.0, -7.0, 8.0, -3.1])
+xs[:, [2, 7]] = (xs[:, [2, 7]] + np.pi) % (2 * np.pi) - np.pi
+out["sm_x"] = xs
+out["sm_mean"], _ = sample_mean(xs, order)
 np.savez(os.path.join(HERE, "stats.npz"), **out)
 print({k: float(v) for k, v in out.items() if np.ndim(v) == 0})

@@ -17,8 +17,11 @@ def main(spec, steps, rows=400):
     name = f"solve_{case}.npz" if not seed or seed == "0" else f"solve_{case}_seed{seed}.npz"
     path = os.path.join(HERE, name)
     g = np.load(path)
-    out = {"truth": g["truth"], "names": g["names"], "kept_steps": np.array(steps), "timers": np.array(
-        [g[f"step{i}_timer"] for i in range(len([k for k in g.files if k.endswith("_order")]))])}
+    n_steps = len([k for k in g.files if k.endswith("_order")])
+    # per step [graph update, sampling + training of every clique of the step, posterior sampling] (a step that re-trains two
+    # cliques has two [sampler, train] pairs: FactorGraphSolver.py:437-468)
+    timers = np.array([[g[f"step{i}_timer"][0], float(np.sum(g[f"step{i}_timer"][1:-1])), g[f"step{i}_timer"][-1]] for i in range(n_steps)])
+    out = {"truth": g["truth"], "names": g["names"], "kept_steps": np.array(steps), "timers": timers}
     for i in steps:
         x = g[f"step{i}_samples"]
         out[f"step{i}_order"] = g[f"step{i}_order"]
@@ -27,6 +30,8 @@ def main(spec, steps, rows=400):
         out[f"step{i}_samples"] = x[:rows].astype(np.float32)
         out[f"step{i}_tree"] = g[f"step{i}_tree"]
         out[f"step{i}_clique_dims"] = g[f"step{i}_clique_dims"]
+        if f"step{i}_hypo" in g.files:
+            out[f"step{i}_hypo"] = g[f"step{i}_hypo"]
     np.savez_compressed(path, **out)
     print(name, os.path.getsize(path) / 1e6, "MB")
 

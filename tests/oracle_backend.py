@@ -22,7 +22,7 @@ def oracle_backend():
 
     cls = F.NSF_AR
     saved = {k: getattr(cls, k) for k in ("forward", "log_prob", "_inverse", "fit_launch", "fit_finish", "loss_and_grad", "handle")}
-    saved_gpu = (_gpu.logpdf, _gpu.mixture_posterior_weights)
+    saved_gpu = (_gpu.logpdf, _gpu.mixture_posterior_weights, _gpu.mixture_posterior_weights_batch)
 
     def cfg(self):
         return self.flat_parameters(), self.dim, self.K, self.hidden_dim, float(self.B)
@@ -109,10 +109,13 @@ def oracle_backend():
     for k, v in (("forward", forward), ("log_prob", log_prob), ("_inverse", _inverse), ("fit_launch", fit_launch),
                  ("fit_finish", fit_finish), ("loss_and_grad", loss_and_grad), ("handle", handle)):
         setattr(cls, k, v)
-    _gpu.logpdf, _gpu.mixture_posterior_weights = logpdf, mix_w
+    def mix_w_batch(groups, x, device=None):
+        return [mix_w(g, x) for g in groups]
+
+    _gpu.logpdf, _gpu.mixture_posterior_weights, _gpu.mixture_posterior_weights_batch = logpdf, mix_w, mix_w_batch
     try:
         yield
     finally:
         for k, v in saved.items():
             setattr(cls, k, v)
-        _gpu.logpdf, _gpu.mixture_posterior_weights = saved_gpu
+        _gpu.logpdf, _gpu.mixture_posterior_weights, _gpu.mixture_posterior_weights_batch = saved_gpu

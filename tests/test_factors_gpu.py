@@ -110,3 +110,21 @@ def test_r2_factor_classes_golden():
     x = np.hstack([x, x + np.array([5.0, -5.0]) + rng.standard_normal((1000, 2))])
     exp = fo.joint_logpdf([oracle_descriptor(f, jf._col_of) for f in jf.factors], x)
     assert np.max(np.abs(jf.log_pdf(x) - exp)) <= TOL
+
+
+def test_batched_posterior_weights_equal_per_factor_calls(g):
+    """nfisam_mixture_posterior_weights_batch (row N2): all mixtures of a step in one launch == one call per factor (the reference's
+    loop, FactorGraphSolver.py:913-922), and both equal the reference's stored weights."""
+    from nfisam_b200.factors import posterior_weights_batch
+    from nfisam_b200.slam import R2Variable, SE2Variable
+
+    fs = build_factors(g)
+    X0, L1, L2, L3 = SE2Variable("X0"), R2Variable("L1"), R2Variable("L2"), R2Variable("L3")
+    x = g["ada3_x"]
+    var2x = {X0: x[:, :3], L1: x[:, 3:5], L2: x[:, 5:7], L3: x[:, 7:9]}
+    mixtures = [fs["ada3"], fs["ada2"], fs["nullhypo"], fs["ada3"]]
+    got = posterior_weights_batch(mixtures, var2x)
+    for f, w in zip(mixtures, got):
+        assert np.allclose(w, f.posterior_weights(var2x), rtol=0, atol=1e-12)
+    assert np.allclose(got[0], g["ada3_post_w"], atol=1e-9) and abs(sum(got[2]) - 1.0) < 1e-12
+    assert posterior_weights_batch([], var2x) == []

@@ -246,3 +246,70 @@ def test_deep_chain_tree_needs_no_recursion():
     assert {x.name for x in affected} == {f"X{n - 1}", f"X{n - 2}"} and len(removed) == 2
     assert len(subs) == 1 and subs[0].root.parent is None and v[f"X{n - 3}"] in subs[0].root.frontal    # handed over, not copied
     assert subs[0].root is owner[v[f"X{n - 3}"]]
+
+
+def test_prior_rooted_ordering_keeps_every_leaf_sampleable():
+    """Row N3.  Ancestral sampling of a clique starts from a prior or from a child's separator factor, so every leaf clique needs
+    a prior-carrying variable and the tree width is bounded by the number of priors.  With the poses arriving in shuffled
+    order `pose_first` (arrival order) builds leaves that cannot be sampled; `prior_rooted` (breadth-first from the priors)
+    reaches the bound -- one chain per robot -- and the reference's own single-prior graph stays a chain under any ordering."""
+    import random
+
+    from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
+    from nfisam_b200.slam.run_batch import graph_file_parser
+    from nfisam_b200.slam.synthetic import make_manhattan_range_graph
+
+    def schedule(nodes, factors, method):
+        s = NFiSAM(NFiSAMArgs(elimination_method=method))
+        for v in nodes:
+            s.add_node(v)
+        for f in factors:
+            s.add_factor(f)
+        s.update_physical_and_working_graphs()
+        levels = s.dry_run_schedule()
+        return [len(row) for row in levels], [e for row in levels for _, _, e in row if e], s
+
+    nodes, truth, factors = make_manhattan_range_graph(robots=4, poses=6, landmarks=3, seed=1)
+    shuffled = list(nodes)
+    random.Random(3).shuffle(shuffled)
+    widths, errors, _ = schedule(shuffled, factors, "pose_first")
+    assert errors and "cannot be reached from any prior" in errors[0]
+    widths, errors, s = schedule(shuffled, factors, "prior_rooted")
+    assert not errors and max(widths) == 4 and widths[0] == 4
+    assert [v.name for v in s.elimination_ordering[:8]] == ["A0", "B0", "C0", "D0", "A1", "B1", "C1", "D1"]
+    assert all(v.type.value == "Landmark" for v in s.elimination_ordering[-3:])
+    # arrival in time order: both orderings coincide
+    w_a, e_a, s_a = schedule(nodes, factors, "pose_first")
+    w_b, e_b, s_b = schedule(nodes, factors, "prior_rooted")
+    assert not e_a and not e_b and w_a == w_b and s_a.elimination_ordering == s_b.elimination_ordering
+    # the reference's own 136-pose graph has ONE prior: a chain under either ordering, never an unsampleable clique
+    nodes, truth, factors = graph_file_parser(os.path.join(HERE, "data", "manhattan_plaza_ada.fg"))
+    for method in ("pose_first", "prior_rooted"):
+        widths, errors, _ = schedule(nodes, factors, method)
+        assert not errors and max(widths) == 1 and len(widths) >= 130
+
+
+def test_prior_rooted_order_is_stable_across_incremental_steps():
+    from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
+    from nfisam_b200.slam.run_batch import group_nodes_factors_incrementally
+    from nfisam_b200.slam.synthetic import make_manhattan_range_graph
+
+    nodes, truth, factors = make_manhattan_range_graph(robots=3, poses=5, landmarks=2, seed=2)
+    steps = group_nodes_factors_incrementally(nodes, factors, incremental_step=1)
+    s = NFiSAM(NFiSAMArgs(elimination_method="prior_rooted"))
+    previous = []
+    with oracle_backend():
+        s._args.flow_iterations, s._args.local_sample_num, s._args.posterior_sample_num, s._args.num_knots = 2, 64, 16, 5
+        for sn, sf in steps:
+            for v in sn:
+                s.add_node(v)
+            for f in sf:
+                s.add_factor(f)
+            s.update_physical_and_working_graphs()
+            order = list(s.elimination_ordering)
+            kept = [v for v in order if v in previous]
+            assert kept == previous                      # known variables keep their relative order
+            previous = order
+            assert not [e for row in s.dry_run_schedule() for _, _, e in row if e]
+            s.incremental_inference()
+    assert len(previous) == len(nodes)

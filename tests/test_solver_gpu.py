@@ -63,6 +63,11 @@ def solve(case, _reseed=True, **kw):
     return per_step
 
 
+# Runs of this solver per statistical comparison.  A solve of the small graphs takes well under a second on the GPU, and the
+# median of 15 seeds is stable where the median of 5 (round 1) flipped with any change of summation order in the kernels.
+N_SEEDS = 15
+
+
 def solve_seeded(case, seed, **kw):
     np.random.seed(seed)
     torch.manual_seed(seed)
@@ -71,9 +76,9 @@ def solve_seeded(case, seed, **kw):
 
 @pytest.mark.parametrize("case", ["small_case1", "small_case1_da", "manhattan_r1_p10", "manhattan_r2_p5"])
 def test_incremental_solve_matches_reference_posterior(case):
-    """Five independently seeded runs of this solver against the reference's stored posterior(s).  NF-iSAM's
+    """N_SEEDS independently seeded runs of this solver against the reference's stored posterior(s).  NF-iSAM's
     run-to-run spread is large (the reference itself, seeds 0 vs 1: pose means up to 0.52 sigma apart, landmark
-    means up to 1.3 sigma, stds up to 1.8x, joint MMD_b up to 0.30), so every statistic is the MEDIAN over our five
+    means up to 1.3 sigma, stds up to 1.8x, joint MMD_b up to 0.30), so every statistic is the MEDIAN over our
     runs of the distance to the CLOSEST reference run."""
     path = os.path.join(HERE, "golden", f"solve_{case}.npz")
     if not os.path.exists(path):
@@ -82,7 +87,7 @@ def test_incremental_solve_matches_reference_posterior(case):
     alt = os.path.join(HERE, "golden", f"solve_{case}_seed1.npz")
     if os.path.exists(alt):
         refs.append(dict(np.load(alt)))
-    runs = [solve_seeded(case, seed) for seed in (0, 1, 2, 3, 4)]
+    runs = [solve_seeded(case, seed) for seed in range(N_SEEDS)]
     n_steps = len(runs[0])
     report = []
     for i in range(n_steps):
@@ -126,7 +131,7 @@ def test_incremental_solve_matches_reference_posterior(case):
         assert np.median(mean_excess) <= 1.0, (case, i, mean_excess)
         assert np.median(std_bad) <= 3.0, (case, i, std_bad)
         report.append(float(np.median(mmds)))
-    print(f"\n[{case}] joint MMD_b vs reference per step (median of 5 runs):", np.round(report, 4))
+    print(f"\n[{case}] joint MMD_b vs reference per step (median over the seeds):", np.round(report, 4))
     assert max(report) < 0.45, report
     g = refs[0]
     key = f"step{n_steps - 1}_hypo"
@@ -140,6 +145,46 @@ def test_incremental_solve_matches_reference_posterior(case):
         w = np.median(np.array(ws), axis=0)
         print("hypothesis weights:", np.round(w, 3).tolist(), "reference:", np.round(g[key], 3).tolist())
         assert np.all(np.abs(w - g[key]) < 0.2)
+
+
+def test_small_graph_posterior_vs_nested_sampling():
+    """The reference checkout ships an independent ground truth for its small range graph: nested-sampling ("dynesty") posteriors
+    of steps 0-3 (journal_paper/case1/dyn1/step{i}.sample) next to its own stored NF-iSAM run (run1/step{i}); fixture
+    tests/golden/small_case1_nested.npz (make_nested_golden.py).  With the reference's settings for this case
+    (run_nfisam.py:12-27: K 9, hidden 8, 2000 training samples, <= 2000 iterations, lr .025, tol .01, 1000 posterior samples) and
+    its evaluation protocol (mmd_rmse_time_da_plot_grid.py:180-254: translation columns only, MMDb with sigma = sqrt(#columns),
+    500 rows) this solver must be as close to the nested-sampling posterior as the reference's own runs are.  Three runs of
+    the reference exist for this graph: the stored journal run (run1) and the two runs of tests/golden/solve_small_case1*.npz
+    (make_solve_golden.py, iteration cap 600).  Their MMDb against the nested-sampling posterior is 0.063 / 0.064 / 0.063-0.072
+    at steps 0-2 (the noise floor of 500 against 500 samples) and 0.146 / 0.259 / 0.274 at step 3.  Bound, at every step:
+        median over seeds of MMDb(ours, nested)  <=  median over the reference's runs of MMDb(reference, nested) + 0.03."""
+    g = dict(np.load(os.path.join(HERE, "golden", "small_case1_nested.npz")))
+    extra = [dict(np.load(os.path.join(HERE, "golden", f))) for f in ("solve_small_case1.npz", "solve_small_case1_seed1.npz")]
+    runs = [solve_seeded("small_case1", seed, flow_iterations=2000) for seed in range(N_SEEDS)]
+
+    def xy_of(names, x, order):
+        cols, off = {}, 0
+        for nm in names:
+            cols[nm] = [off, off + 1]
+            off += 2 if nm.startswith("L") else 3
+        return x[:500][:, np.concatenate([cols[nm] for nm in order])].astype(np.float64)
+
+    ours, theirs = [], []
+    for i in range(4):
+        order = [str(n) for n in g[f"order{i}"]]
+        dyn = g[f"dyn{i}"][:500].astype(np.float64)
+        sigma = np.sqrt(dyn.shape[1])
+        ref_vals = [mmd_b(g[f"nf{i}"][:500].astype(np.float64), dyn, sigma)]
+        ref_vals += [mmd_b(xy_of([str(n) for n in e[f"step{i}_order"]], e[f"step{i}_samples"], order), dyn, sigma) for e in extra]
+        theirs.append(ref_vals)
+        ours.append([mmd_b(xy_of(run[i][0], run[i][1], order), dyn, sigma) for run in runs])
+    med = [float(np.median(v)) for v in ours]
+    ref_med = [float(np.median(v)) for v in theirs]
+    print("\nMMDb against the nested-sampling posterior, steps 0-3: ours (median of %d seeds)" % N_SEEDS, np.round(med, 4),
+          "min", np.round([min(v) for v in ours], 4), "max", np.round([max(v) for v in ours], 4),
+          "| reference runs (journal run1, 600-iteration seeds 0 / 1)", [np.round(v, 4).tolist() for v in theirs])
+    for i in range(4):
+        assert med[i] <= ref_med[i] + 0.03, (i, med, theirs)
 
 
 def _step_distance(m, s_, xs, names, g, i, rows=400):
@@ -181,8 +226,18 @@ def _pose_error(mean, order, names_all, truth):
     return float(np.mean(errs))
 
 
-def test_100_pose_solve_matches_reference_posterior():
-    """BASELINE configs[3]: a 100-pose Manhattan-world range-SLAM graph (4 landmarks, 302 factors, 100 incremental steps)
+# reference settings of example/slam/manhattan_world_with_range/manhattan_plaza/run_nfisam.py:5-10, 42-46
+PLAZA_ARGS = dict(num_knots=9, flow_iterations=500, local_sample_num=2000, learning_rate=.01, hidden_dim=8, loss_delta_tol=1e-9,
+                  average_window=50, posterior_sample_num=500)
+
+
+@pytest.mark.parametrize("case,n_steps,kwargs", [("manhattan_r1_p100", 100, dict(flow_iterations=500)),
+                                                 ("manhattan_plaza_ada", 136, PLAZA_ARGS)])
+def test_100_pose_solve_matches_reference_posterior(case, n_steps, kwargs):
+    """manhattan_plaza_ada: the REFERENCE'S OWN large graph, example/slam/manhattan_world_with_range/manhattan_plaza/res/seed0/
+    pada0.4_r2_odom0.01_mada3/factor_graph.fg (136 poses, 4 landmarks, 59 ambiguous 2- / 3-way data associations), with the
+    settings of its run_nfisam.py, two stored runs of the reference (~65 min of CPU each), compared after 34 / 68 / 102 / 136 steps.
+    manhattan_r1_p100: BASELINE configs[3] stand-in of round 1: a 100-pose Manhattan-world range-SLAM graph (4 landmarks, 302 factors, 100 incremental steps)
     solved by the reference (tests/golden/make_solve_golden.py, 500 iterations per clique, ~25 min of CPU per run) and by
     this solver, compared after 25, 50, 75 and 100 steps.
 
@@ -196,7 +251,6 @@ def test_100_pose_solve_matches_reference_posterior():
     Stored reference runs, seed 0 vs seed 1 (tests/golden/slim_solve_golden.py): mean pose error 3.1 / 4.2, 5.8 / 6.3, 7.3 / 8.9,
     8.9 / 12.6 after 25 / 50 / 75 / 100 steps; between the two runs MMD_b 0.70, 0.87, 0.92, 1.05 and mean excess 2.9, 196, 236,
     228 (a landmark collapsed onto different modes)."""
-    case = "manhattan_r1_p100"
     path = os.path.join(HERE, "golden", f"solve_{case}.npz")
     if not os.path.exists(path):
         pytest.skip("golden posterior not generated")
@@ -207,8 +261,8 @@ def test_100_pose_solve_matches_reference_posterior():
     kept = [int(i) for i in refs[0]["kept_steps"]]
     truth = refs[0]["truth"]
     names_all = [str(n) for n in refs[0]["names"]]
-    runs = [solve_seeded(case, seed, flow_iterations=500) for seed in (0, 1, 2)]
-    assert len(runs[0]) == 100
+    runs = [solve_seeded(case, seed, **kwargs) for seed in (0, 1, 2, 3, 4)]
+    assert len(runs[0]) == n_steps
     report = []
     for i in kept:
         names = runs[0][i][0]
@@ -238,6 +292,29 @@ def test_100_pose_solve_matches_reference_posterior():
     print(f"\n[{case}]")
     for row in report:
         print("  ", row)
+    key = f"step{kept[-1]}_hypo"
+    if key in refs[0]:
+        # data-association probabilities of every ambiguous factor after the last step (FactorGraphSolver.py:913-922), all
+        # mixtures in one launch.  Two runs of the reference agree on the most likely association of 95 % of the 59 factors
+        # (mean absolute difference of the weights 0.011); every run of this solver must agree with the closest reference run
+        # at least as well as that, minus 10 points / plus 0.03.
+        from nfisam_b200.factors import BinaryFactorMixture, posterior_weights_batch
+
+        ref_w = [np.nan_to_num(g[key]) for g in refs]
+        agree, diff = [], []
+        for run in runs:
+            solver = run[kept[-1]][3]
+            mix = [f for f in solver.physical_factors if isinstance(f, BinaryFactorMixture)]
+            w = np.zeros_like(ref_w[0])
+            for k, wk in enumerate(posterior_weights_batch(mix, solver._samples)):
+                w[k, :len(wk)] = wk
+            agree.append(max(float(np.mean(w.argmax(1) == r.argmax(1))) for r in ref_w))
+            diff.append(min(float(np.abs(w - r).mean()) for r in ref_w))
+        ref_agree = float(np.mean(ref_w[0].argmax(1) == ref_w[-1].argmax(1))) if len(ref_w) > 1 else 1.0
+        ref_diff = float(np.abs(ref_w[0] - ref_w[-1]).mean()) if len(ref_w) > 1 else 0.0
+        print(f"   association weights of {len(ref_w[0])} mixtures: argmax agreement with the closest reference run", np.round(agree, 3),
+              "mean |dw|", np.round(diff, 4), "| reference seed 0 vs 1:", round(ref_agree, 3), round(ref_diff, 4))
+        assert np.median(agree) >= ref_agree - 0.10 and np.median(diff) <= ref_diff + 0.03
 
 
 def test_clique_parallel_equals_serial_loop_statistically():

@@ -8,6 +8,8 @@ import pytest
 
 from oracle import stats_oracle as so
 
+HERE = os.path.dirname(os.path.abspath(__file__))
+
 pytestmark = pytest.mark.gpu
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "stats.npz"))
@@ -65,3 +67,33 @@ def test_bad_arguments_fail_loudly():
         MMDu2(x[:1], x, 1.0)
     with pytest.raises(ValueError):
         MMDb(x, np.zeros((4, 2)), 1.0)
+
+
+def test_marginal_statistics_kernel_matches_reference_and_oracle():
+    """nfisam_marginal_stats (row N2): means equal the reference's sample_mean (stats.npz), covariance blocks equal the oracle's;
+    float32 device matrix, float64 accumulation."""
+    from nfisam_b200.slam import R2Variable, SE2Variable
+    from nfisam_b200.utils import marginal_mean_cov, sample_mean
+
+    g = np.load(os.path.join(HERE, "golden", "stats.npz"))
+    order = [SE2Variable("X0"), R2Variable("L1"), SE2Variable("X1")]
+    x = g["sm_x"]
+    means, var2mean = sample_mean(x, order)
+    assert np.max(np.abs(means - g["sm_mean"])) < 2e-6          # the kernel reads float32 samples
+    x32 = x.astype(np.float32).astype(np.float64)
+    mean_o, cov_o = so.sample_mean_cov(x32, [0, 0, 1, 0, 0, 0, 0, 1])
+    means, var2mean, var2cov = marginal_mean_cov(x, order)
+    assert np.max(np.abs(means - mean_o)) < 1e-12
+    off = 0
+    for v in order:
+        assert np.max(np.abs(var2cov[v] - cov_o[off:off + v.dim, off:off + v.dim])) < 1e-10, v.name
+        off += v.dim
+    # device-resident float32 input, many variables
+    import torch
+    rng = np.random.default_rng(0)
+    many = [SE2Variable(f"X{k}") for k in range(200)]
+    xs = (rng.standard_normal((1000, 600)) * 2.0).astype(np.float32)
+    means, _, var2cov = marginal_mean_cov(torch.from_numpy(xs).cuda(), many)
+    circ = np.tile([0, 0, 1], 200)
+    mo, co = so.sample_mean_cov(xs.astype(np.float64), circ)
+    assert np.max(np.abs(means - mo)) < 1e-10 and np.max(np.abs(var2cov[many[57]] - co[171:174, 171:174])) < 1e-10
