@@ -218,6 +218,27 @@ int nfisam_flow_state_floats(const nf_flow_t* f, int32_t max_iters, int64_t* n_f
 int nfisam_flow_train_export(nf_flow_t* f, float* dst_dev, int32_t max_iters, void* stream);
 int nfisam_flow_import_state(nf_flow_t* f, const float* src_dev, void* stream);
 
+/* Row-sharded training of one clique flow over the GPUs of a node (second way the path shards; the reference
+ * trains every clique on one device, src/slam/NFiSAM.py:451-491).  One process per GPU; every rank holds the same flow
+ * parameters and a share of the training rows.  Per Adam iteration each rank pushes its reduced gradient into every peer's
+ * receive area over NVLink peer memory (CUDA IPC) from inside the Adam kernel, publishes an iteration stamp and waits on its
+ * own flag words: no NCCL call and no host round trip per iteration; the ranks apply the identical update, so their
+ * parameters, loss curves and early-stop decisions stay bitwise equal.
+ *   _create   allocates this rank's receive area (slots of slot_floats floats: >= packed parameter count + dim) and returns its
+ *             64-byte CUDA IPC handle; the caller all-gathers the handles (any transport) and passes all `world` of them, in
+ *             rank order, to _connect.  1 <= world <= 8; the GPUs must have peer access.
+ *   nfisam_flow_train_launch_sharded   like nfisam_flow_train_launch on this rank's n_local rows of the n_total-row training set
+ *             (validation sets are not supported); every rank of the group must make the same sequence of sharded launches.
+ *             _train_finish / _train_export complete the run as usual.
+ *   _error    non-zero when a wait on a peer timed out (~2 s: a peer died or skipped a launch); the run's result is then invalid. */
+typedef struct nf_shard_group nf_shard_group_t;
+int nfisam_shard_group_create(int device, int rank, int world, int64_t slot_floats, nf_shard_group_t** out, void* ipc_handle_out);
+int nfisam_shard_group_connect(nf_shard_group_t* g, const void* all_handles);
+int nfisam_shard_group_destroy(nf_shard_group_t* g);
+int nfisam_shard_group_error(nf_shard_group_t* g, int32_t* timed_out);
+int nfisam_flow_train_launch_sharded(nf_flow_t* f, const float* data_dev, int64_t n_local, int64_t n_total, const nf_train_cfg* cfg,
+                                     nf_shard_group_t* group, void* stream);
+
 /* loss and d loss / d theta (state_dict order, host) at the current parameters, no update:
  * what loss.backward() leaves in .grad (src/slam/NFiSAM.py:470-474).  Synchronous. */
 int nfisam_flow_loss_grad(nf_flow_t* f, const float* data_dev, int64_t n, float* loss_host, float* grad_host,

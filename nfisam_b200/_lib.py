@@ -134,6 +134,11 @@ SYMBOLS = {
     "nfisam_flow_state_floats": (_INT, [_P, ctypes.c_int32, ctypes.POINTER(_I64)]),
     "nfisam_flow_train_export": (_INT, [_P, _P, ctypes.c_int32, _P]),
     "nfisam_flow_import_state": (_INT, [_P, _P, _P]),
+    "nfisam_shard_group_create": (_INT, [_INT, _INT, _INT, _I64, ctypes.POINTER(_P), _P]),
+    "nfisam_shard_group_connect": (_INT, [_P, _P]),
+    "nfisam_shard_group_destroy": (_INT, [_P]),
+    "nfisam_shard_group_error": (_INT, [_P, ctypes.POINTER(ctypes.c_int32)]),
+    "nfisam_flow_train_launch_sharded": (_INT, [_P, _P, _I64, _I64, ctypes.POINTER(nf_train_cfg), _P, _P]),
     "nfisam_flow_loss_grad": (_INT, [_P, _P, _I64, _P, _P, _P]),
     "nfisam_factor_logpdf": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _P, _INT, _P]),
     "nfisam_mixture_posterior_weights": (_INT, [ctypes.POINTER(nf_factor_desc), _INT, _P, _I64, _INT, _P, _INT, _P]),

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <array>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -128,7 +129,7 @@ struct nf_flow {
 // widths and heights are interleaved, (uw_0, uh_0, uw_1, uh_1, ...), derivatives follow (nf_common.cuh)
 static inline int packed_col(int p, int K) { return p < K ? 2 * p : (p < 2 * K ? 2 * (p - K) + 1 : p); }
 
-static void build_index_map(nf_flow* f) {
+static void build_index_map_uncached(nf_flow* f) {
     const int d = f->fd.d, K = f->fd.K, H = f->fd.H, P = f->fd.P, Pp = f->fd.Pp;
     f->pk2th.assign((size_t)f->n_packed, -1);
     for (int p = 0; p < P; ++p) f->pk2th[packed_col(p, K)] = p;
@@ -152,6 +153,18 @@ static void build_index_map(nf_flow* f) {
         for (int p = 0; p < P; ++p) f->pk2th[ob3 + packed_col(p, K)] = (int32_t)(th + p);
         th += P;
     }
+}
+
+// the map only depends on (dim, K, hidden): the solver creates one flow per clique and step, mostly of a few shapes
+static void build_index_map(nf_flow* f) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::array<int, 3>, std::vector<int32_t>>> cache;
+    const std::array<int, 3> key = {f->fd.d, f->fd.K, f->fd.H};
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto& e : cache)
+        if (e.first == key) { f->pk2th = e.second; return; }
+    build_index_map_uncached(f);
+    if (cache.size() < 256) cache.emplace_back(key, f->pk2th);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -707,7 +720,7 @@ int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_s
 // training
 // ------------------------------------------------------------------------------------------------
 static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const nf_train_cfg* cfg, NfTrainArgs* a,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool force_plain = false) {
     if (cfg->max_iters < 1) return nf_set_error(NF_ERR_BAD_ARG, "max_iters < 1");
     if (!(cfg->lr > 0.0f) || !(cfg->beta1 >= 0.0f && cfg->beta1 < 1.0f) || !(cfg->beta2 >= 0.0f && cfg->beta2 < 1.0f))
         return nf_set_error(NF_ERR_BAD_ARG, "bad Adam hyper-parameters");
@@ -761,7 +774,7 @@ static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const n
         }
         a->val_part = f->d_val_part;
     }
-    if (n >= NF_TRAIN_PLAIN_MIN_N && cfg->n_val <= 0) {
+    if ((n >= NF_TRAIN_PLAIN_MIN_N || force_plain) && cfg->n_val <= 0) {
         if (!f->d_partials) {
             f->d_partials = f->pooled(sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->n_packed);
             f->d_loss_partials = f->pooled(sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->fd.d);
@@ -780,6 +793,27 @@ int nfisam_flow_train_launch(nf_flow_t* f, const float* data_dev, int64_t n, con
     DeviceGuard g(f->device);
     NfTrainArgs a;
     int rc = fill_train_args(f, data_dev, n, cfg, &a, (cudaStream_t)stream);
+    if (rc != NF_OK) return rc;
+    rc = nf_launch_train(f->fd, a, f->device, (cudaStream_t)stream);
+    f->touch((cudaStream_t)stream);
+    if (rc < 0) return rc;
+    f->pending_launches = rc;
+    f->pending_iters = cfg->max_iters;
+    return NF_OK;
+}
+
+int nfisam_flow_train_launch_sharded(nf_flow_t* f, const float* data_dev, int64_t n_local, int64_t n_total, const nf_train_cfg* cfg,
+                                     nf_shard_group_t* group, void* stream) {
+    if (!f || !data_dev || !cfg || !group) return nf_set_error(NF_ERR_BAD_ARG, "NULL argument");
+    if (n_local < 1 || n_total < n_local) return nf_set_error(NF_ERR_BAD_ARG, "bad n_local / n_total");
+    if (cfg->n_val > 0) return nf_set_error(NF_ERR_UNSUPPORTED, "row-sharded training does not take a validation set");
+    if (f->pending_launches) return nf_set_error(NF_ERR_BAD_ARG, "a training run is already pending on this handle");
+    DeviceGuard g(f->device);
+    NfTrainArgs a;
+    int rc = fill_train_args(f, data_dev, n_local, cfg, &a, (cudaStream_t)stream, true);
+    if (rc != NF_OK) return rc;
+    a.n_total = n_total;
+    rc = nf_shard_view(group, f->n_packed + f->fd.d, cfg->max_iters, &a.shard);
     if (rc != NF_OK) return rc;
     rc = nf_launch_train(f->fd, a, f->device, (cudaStream_t)stream);
     f->touch((cudaStream_t)stream);

@@ -44,6 +44,19 @@ int nf_launch_inverse_gather(const NfFlowDims& fd, const float* pk, const float*
                              unsigned long long* bad, int device, cudaStream_t st);
 
 // nf_train_kernel.cu
+// One rank's view of a shard group (nf_shard.cu): receive areas and flag words of every rank, mapped into this process with
+// CUDA IPC; rank q's area holds world x 2 slots of slot_floats floats, slot (src, parity).
+#define NF_SHARD_MAX_RANKS 8
+struct NfShardView {
+    float* data[NF_SHARD_MAX_RANKS];        // data[q]: receive area of rank q
+    unsigned* flags[NF_SHARD_MAX_RANKS];    // flags[q][src]: last iteration stamp rank src pushed to rank q
+    unsigned* arrive;                       // local block-arrival counter
+    unsigned* error;                        // local: set when a wait timed out
+    long long slot_floats;
+    unsigned stamp0;                        // stamp of iteration it = stamp0 + it + 1
+    int rank, world;
+};
+
 struct NfTrainCtrl {
     int stop;               // 1: the stopping rule fired (or the loss went NaN)
     int iters_run;          // valid when stop = 1
@@ -80,6 +93,9 @@ struct NfTrainArgs {
     float* partials;        // (NF_TRAIN_PLAIN_MAX_BLOCKS, n_packed)
     float* loss_partials;   // (NF_TRAIN_PLAIN_MAX_BLOCKS, d)
     int n_packed;
+    // row-sharded training over several GPUs (nf_shard.cu): this rank holds `n` of the n_total rows; 0 = not sharded
+    int64_t n_total;
+    NfShardView shard;
 };
 #define NF_TRAIN_PLAIN_MIN_N 16384
 #define NF_TRAIN_PLAIN_MAX_BLOCKS 64
@@ -112,6 +128,10 @@ int nf_launch_posterior_pass(const NfFlowDims& fd, const NfPassItem* items_dev, 
 
 int nf_launch_mixture_weights_batch(const nf_factor_desc* descs_dev, const int2* groups_dev, int n_groups, const double* x, int64_t n,
                                     int D, double* partial_dev, int blocks_per_group, cudaStream_t st);
+
+// nf_shard.cu
+struct nf_shard_group;
+int nf_shard_view(nf_shard_group* g, int64_t floats_needed, int max_iters, NfShardView* out);
 
 // nf_sim_kernels.cu
 int nf_launch_simulate(const nf_sim_op* ops, int n_ops, uint64_t seed, double* s_mat, int64_t n, int ld, cudaStream_t st);

@@ -493,7 +493,8 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     }
     __syncthreads();
 
-    const float inv_n = 1.0f / (float)n;
+    // row-sharded run: this rank sees n of the n_total rows, the loss is the mean over all of them
+    const float inv_n = 1.0f / (float)(!val_pass && a.n_total > 0 ? a.n_total : n);
     const int adam0 = a.step0 + it_begin;                       // Adam steps taken before this launch
     double b1t = pow((double)a.beta1, (double)adam0), b2t = pow((double)a.beta2, (double)adam0);
 
@@ -829,6 +830,97 @@ nf_adam_kernel(NfTrainArgs a, int d, int blocks, int it, int launch_idx) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-sharded large-batch mode, second half of an iteration: gradient exchange over NVLink peer memory FUSED with the Adam
+// update (see nf_shard.cu for the memory layout).  One launch per iteration, every block:
+//   1. reduces the per-block partial gradients of its 256 parameters (fixed order) -- the last d entries of the exchange
+//      vector are the per-dim loss sums;
+//   2. pushes the result into slot (my rank, iteration parity) of EVERY rank's receive area (remote stores over NVLink);
+//   3. after a system-scope fence the last block to arrive publishes the iteration stamp in every rank's flag word;
+//   4. waits until its own flag words show the stamp of every rank (bounded spin), then sums the ranks' gradients in rank
+//      order (L1-bypassing loads) and applies Adam.
+// Every rank adds the same numbers in the same order: parameters, loss curves and stop decisions stay bitwise equal, which
+// is what keeps the ranks in lock step without any host synchronisation.  Parity slots let a rank run one iteration ahead
+// of a peer that is still reading; it cannot run two ahead, because publishing iteration t + 1 requires having seen every
+// peer's stamp of iteration t.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned nf_ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void nf_st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+nf_adam_sharded_kernel(NfTrainArgs a, int d, int blocks, int it, int launch_idx) {
+    if (a.ctrl[(launch_idx + 1) & 1].stop) return;         // identical decision on every rank: nobody pushes, nobody waits
+    const NfShardView& sv = a.shard;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_x = a.n_packed + d;                          // exchange vector: gradient | per-dim loss sums
+    const unsigned stamp = sv.stamp0 + (unsigned)it + 1u;
+    const long long slot = ((long long)sv.rank * 2 + (it & 1)) * sv.slot_floats;
+    if (p < n_x) {
+        float g = 0.0f;
+        if (p < a.n_packed) {
+            for (int b = 0; b < blocks; ++b) g += a.partials[(size_t)b * a.n_packed + p];
+        } else {
+            for (int b = 0; b < blocks; ++b) g += a.loss_partials[b * d + (p - a.n_packed)];
+        }
+        for (int q = 0; q < sv.world; ++q) sv.data[q][slot + p] = g;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) {
+        s_timeout = 0;
+        const unsigned arrived = atomicAdd(sv.arrive, 1u);
+        if (arrived == gridDim.x - 1) {                      // every block of this rank has pushed and fenced
+            *sv.arrive = 0u;
+            __threadfence_system();
+            for (int q = 0; q < sv.world; ++q) nf_st_release_sys(sv.flags[q] + sv.rank, stamp);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < sv.world) {
+        const unsigned* flag = sv.flags[sv.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        // signed distance: correct across the 32-bit wrap of the stamp
+        while ((int)(nf_ld_acquire_sys(flag) - stamp) < 0) {
+            if (clock64() - t0 > 4000000000LL) {             // ~2 s: a peer died or skipped a launch; do not hang the device
+                s_timeout = 1;
+                atomicExch(sv.error, 1u);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (s_timeout) return;
+    const float* mine = sv.data[sv.rank];
+    const long long par = (long long)(it & 1) * sv.slot_floats;
+    if (p < a.n_packed) {
+        float g = 0.0f;
+        for (int q = 0; q < sv.world; ++q) g += __ldcg(mine + (long long)q * 2 * sv.slot_floats + par + p);
+        const int tstep = a.step0 + it + 1;
+        const double b1t = pow((double)a.beta1, (double)tstep), b2t = pow((double)a.beta2, (double)tstep);
+        const float step = (float)((double)a.lr / (1.0 - b1t));
+        const float bc2s = (float)sqrt(1.0 - b2t);
+        float m = a.adam_m[p], v = a.adam_v[p];
+        m = m + (g - m) * (1.0f - a.beta1);
+        v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+        a.adam_m[p] = m;
+        a.adam_v[p] = v;
+        a.pk[p] = a.pk[p] - step * (m / (sqrtf(v) / bc2s + a.eps));
+    } else if (p < n_x) {
+        const int i = p - a.n_packed;
+        float acc = 0.0f;
+        for (int q = 0; q < sv.world; ++q) acc += __ldcg(mine + (long long)q * 2 * sv.slot_floats + par + p);
+        a.loss_part[(size_t)it * d + i] = -acc / (float)a.n_total;
+    }
+}
+
 template <int K, int H, int W>
 size_t train_smem_bytes(int i_max, int C, int mt_res) {
     constexpr int PP = ((3 * K - 1) + 3) & ~3;
@@ -880,12 +972,14 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         attrs[0].val.clusterDim.z = 1;
         cfg.attrs = attrs;
         cfg.numAttrs = 1;
-        const int adam_blocks = (a.n_packed + 255) / 256;
+        const bool sharded = a.n_total > 0;
+        const int adam_blocks = (a.n_packed + (sharded ? d : 0) + 255) / 256;
         for (int it = 0; it < a.max_iters; ++it) {
             const int launch_idx = it / window;
             cudaError_t e = cudaLaunchKernelEx(&cfg, kern_big, a, d, fd.B, 2, 0, it, it + 1, launch_idx, 1, 0);
             if (e != cudaSuccess) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, plain)");
-            nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
+            if (sharded) nf_adam_sharded_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
+            else nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
             nf_count_launch(2);
         }
         int rc = nf_check_launch("nf_adam_kernel");

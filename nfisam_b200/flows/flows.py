@@ -410,7 +410,8 @@ class NSF_AR(nn.Module):
 
     # ------------------------------------------------------------------ training on device
     def fit_launch(self, data, iters, lr, betas=(0.9, 0.999), eps=1e-8, average_window=50, loss_delta_tol=1e-2,
-                   reset_optimizer=True, stream=None, val=None, validation_interval=10, slower_stop_rate=2.0, concurrency=1):
+                   reset_optimizer=True, stream=None, val=None, validation_interval=10, slower_stop_rate=2.0, concurrency=1,
+                   shard=None, n_total=None):
         """Enqueue the whole Adam loop (src/slam/NFiSAM.py:451-491) on `stream` (a torch.cuda.Stream, default:
         the current one) and return immediately; several flows launched on different streams / devices train
         concurrently.  Call fit_finish() to collect the loss history."""
@@ -433,7 +434,13 @@ class NSF_AR(nn.Module):
         st = stream if stream is not None else torch.cuda.current_stream(self._dev())
         if stream is not None:
             stream.wait_stream(torch.cuda.current_stream(self._dev()))   # data upload happened on the current stream
-        _lib.check(lib.nfisam_flow_train_launch(h, xd.data_ptr(), n, ctypes.byref(cfg), ctypes.c_void_p(st.cuda_stream)))
+        if shard is not None:
+            # `data` holds this rank's rows of an n_total-row training set; the ranks of the ShardGroup exchange gradients inside
+            # the kernels (nfisam_flow_train_launch_sharded) and end up with bitwise identical parameters
+            _lib.check(lib.nfisam_flow_train_launch_sharded(h, xd.data_ptr(), n, int(n_total), ctypes.byref(cfg), shard._h,
+                                                            ctypes.c_void_p(st.cuda_stream)))
+        else:
+            _lib.check(lib.nfisam_flow_train_launch(h, xd.data_ptr(), n, ctypes.byref(cfg), ctypes.c_void_p(st.cuda_stream)))
         self._pending = (xd, int(iters), st, vd)
 
     def fit_finish(self, pull=True):
@@ -505,6 +512,51 @@ class NSF_AR(nn.Module):
 
 
 LOG_2PI = math.log(2.0 * math.pi)
+
+
+class ShardGroup:
+    """The ranks of a torch.distributed process group (one process per GPU of ONE node) that train a clique flow together on
+    row shards of its training set (nfisam_shard_group_*, include/nfisam_b200.h): receive areas allocated once, exchanged as
+    CUDA IPC handles through the process group, then every gradient exchange runs inside the kernels over NVLink.
+    torch.distributed only carries the 64-byte handles."""
+
+    def __init__(self, process_group, device_index: int, slot_floats: int):
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        self.group = process_group
+        self.rank, self.world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        self.device_index, self.slot_floats = int(device_index), int(slot_floats)
+        handle = (ctypes.c_uint8 * 64)()
+        h = ctypes.c_void_p()
+        _lib.check(lib.nfisam_shard_group_create(self.device_index, self.rank, self.world, self.slot_floats, ctypes.byref(h), handle))
+        self._h = h
+        on_cuda = "nccl" in str(dist.get_backend(process_group))
+        dev = torch.device("cuda", self.device_index) if on_cuda else torch.device("cpu")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=process_group)
+        blob = bytes(torch.cat(gathered).cpu().numpy().tobytes())
+        _lib.check(lib.nfisam_shard_group_connect(self._h, ctypes.c_char_p(blob)))
+
+    def rows(self, n: int):
+        """[begin, end) of this rank's share of n training rows (equal shares, the remainder spread over the first ranks)."""
+        base, extra = divmod(int(n), self.world)
+        begin = self.rank * base + min(self.rank, extra)
+        return begin, begin + base + (1 if self.rank < extra else 0)
+
+    def timed_out(self) -> bool:
+        v = ctypes.c_int32(0)
+        _lib.check(_lib.load().nfisam_shard_group_error(self._h, ctypes.byref(v)))
+        return bool(v.value)
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.load().nfisam_shard_group_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 def posterior_pass(items, z_dev, s_dev, counter=None):

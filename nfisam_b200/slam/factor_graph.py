@@ -11,8 +11,7 @@ class FactorGraph:
         self._vars: List[Variable] = []
         self._factors: List[Factor] = []
         self._var_set: Set[Variable] = set()
-        self._var_index: Dict[Variable, int] = {}         # insertion position of a variable
-        self._incident: Dict[Variable, List[int]] = {}    # variable -> indices of the factors that touch it
+        self._incidence = None            # (variable -> insertion position, variable -> indices of its factors), built lazily
         self._adjacency = None            # built lazily: sub-graphs are created far more often than eliminated
 
     vars = property(lambda self: self._vars)
@@ -21,8 +20,9 @@ class FactorGraph:
     def add_node(self, var: Variable) -> "FactorGraph":
         if var in self._var_set:
             raise KeyError("The node has already existed in the graph")
-        self._var_index[var] = len(self._vars)
-        self._incident[var] = []
+        if self._incidence is not None:
+            self._incidence[0][var] = len(self._vars)
+            self._incidence[1][var] = []
         self._vars.append(var)
         self._var_set.add(var)
         self._adjacency = None
@@ -32,11 +32,40 @@ class FactorGraph:
         for v in factor.vars:
             if v not in self._var_set:
                 raise KeyError(f"factor touches a variable that is not in the graph: {v.name}")
-        for v in factor.vars:
-            self._incident[v].append(len(self._factors))
+        if self._incidence is not None:
+            for v in factor.vars:
+                self._incidence[1][v].append(len(self._factors))
         self._factors.append(factor)
         self._adjacency = None
         return self
+
+    def _incidence_maps(self):
+        """(variable -> insertion position, variable -> indices of the factors that touch it); kept up to date by add_node /
+        add_factor once built (the physical graph only ever grows), rebuilt after an in-place removal."""
+        if self._incidence is None:
+            index = {v: k for k, v in enumerate(self._vars)}
+            incident = {v: [] for v in self._vars}
+            for fi, f in enumerate(self._factors):
+                for v in f.vars:
+                    incident[v].append(fi)
+            self._incidence = (index, incident)
+        return self._incidence
+
+    def take_clique(self, clique: BayesTreeNode) -> List[Factor]:
+        """Symbolic elimination of a clique IN PLACE: removes the clique's frontal variables and every factor that lies inside
+        the clique, and returns those factors in insertion order (= get_clique_factor_graph(clique).factors followed by
+        eliminate_clique_variables(clique, None), FactorGraph.py:230-259, without building two new graphs per clique)."""
+        cv = clique.vars
+        frontal = clique.frontal
+        taken, kept = [], []
+        for f in self._factors:
+            (taken if cv.issuperset(f.vars) else kept).append(f)
+        self._factors = kept
+        self._vars = [v for v in self._vars if v not in frontal]
+        self._var_set -= frontal
+        self._adjacency = None
+        self._incidence = None
+        return taken
 
     @property
     def _neighbors(self) -> Dict[Variable, Set[Variable]]:
@@ -92,11 +121,12 @@ class FactorGraph:
         roots = [t.root.vars for t in sub_trees]
         # only the factors incident to the affected variables are looked at (the physical graph grows with the trajectory,
         # the affected part does not); variables and factors keep their insertion order, as a scan of the whole graph would
+        var_index, incident = self._incidence_maps()
         candidates = set()
         for v in variables:
-            candidates.update(self._incident[v])
+            candidates.update(incident[v])
         g = FactorGraph()
-        for v in sorted(variables, key=self._var_index.__getitem__):
+        for v in sorted(variables, key=var_index.__getitem__):
             g.add_node(v)
         for fi in sorted(candidates):
             f = self._factors[fi]

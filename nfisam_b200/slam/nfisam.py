@@ -52,7 +52,8 @@ class NFiSAMArgs(SolverArgs):
                  average_window=50, loss_delta_tol=1e-2, training_set_frac=1.0, validation_interval=10,
                  slower_stop_rate=2.0, data_parallel=False, training_loss_dir=None,
                  clique_parallel: bool = True, deterministic_cliques: bool = False, seed: int = 0, device=None,
-                 device_simulation: bool = True, device_latents: bool = True, process_group=None, *args, **kwargs):
+                 device_simulation: bool = True, device_latents: bool = True, process_group=None, shard_min_rows: int = 32768,
+                 *args, **kwargs):
         super().__init__(elimination_method=elimination_method, posterior_sample_num=posterior_sample_num,
                          local_sample_num=local_sample_num, store_clique_samples=store_clique_samples,
                          local_sampling_method=local_sampling_method, *args, **kwargs)
@@ -86,6 +87,9 @@ class NFiSAMArgs(SolverArgs):
         # cliques of a tree level; "world" = the default group.  None (default) = this process alone -- the solver never
         # picks up a process group the application initialised for something else.
         self.process_group = process_group
+        # a tree level with ONE clique and at least this many training rows is trained by all ranks together on row shards
+        # (gradient exchange over NVLink peer memory inside the Adam kernel); 0 disables
+        self.shard_min_rows = shard_min_rows
         # Limit of this implementation (not of the reference): the augmented dimension of a clique (simulated observations +
         # separator + frontal columns) must not exceed nfisam_b200._lib.NFISAM_MAX_DIM = 32; larger cliques raise a
         # ValueError that names the clique.

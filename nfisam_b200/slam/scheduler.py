@@ -126,6 +126,16 @@ class CliqueScheduler:
         a = self.solver._args
         return (zlib.crc32(_clique_name(clique).encode()) + 7919 * self.solver._step_counter + 104729 * salt + int(a.seed)) % (2 ** 31 - 1)
 
+    def _shard_group(self):
+        """The ShardGroup of this solver's process group (created on first use: a collective, every rank gets here together)."""
+        if self.__dict__.get("_shard") is None:
+            from ..flows.flows import ShardGroup
+
+            a = self.solver._args
+            slot = NSF_AR.packed_size(_lib.NFISAM_MAX_DIM, a.num_knots, a.hidden_dim) + _lib.NFISAM_MAX_DIM
+            self._shard = ShardGroup(self._group(), self._device().index, slot)
+        return self._shard
+
     def _pinned_f32(self, which: str, count: int):
         buf = getattr(self, which)
         if buf is None or buf.numel() < count:
@@ -150,10 +160,9 @@ class CliqueScheduler:
                 # deterministic part, identical on every rank: which factors the clique consumes (claimed one
                 # clique at a time, so a factor on variables shared by sibling cliques is used exactly once,
                 # as in the reference's serial loop), column order and observation vector
-                graph = s._working_graph.get_clique_factor_graph(c)
-                s._working_graph = s._working_graph.eliminate_clique_variables(clique=c, new_factor=None)
+                clique_factors = s._working_graph.take_clique(c)
                 pattern = s._working_bayes_tree.clique_variable_pattern(c)
-                sampler = SimulationBasedSampler(factors=graph.factors, vars=pattern)
+                sampler = SimulationBasedSampler(factors=clique_factors, vars=pattern)
                 _, var_order, true_obs = sampler.plan()
                 plans[id(c)] = (sampler, var_order, true_obs)
             if todo:
@@ -194,6 +203,13 @@ class CliqueScheduler:
         pg = self._group()
         dev = self._device()
         iters = int(a.flow_iterations)
+        # A level with a single clique (the root, typically) leaves every other GPU idle: with a large training set the ranks
+        # train it TOGETHER on row shards (ShardGroup: gradients exchanged inside the Adam kernel over NVLink peer memory).
+        # Every rank simulates and normalises the same full training set (same seeds: microseconds of redundant work, no
+        # collective for the statistics), trains on its rows and ends with bitwise identical parameters: nothing to gather.
+        shard_min = int(getattr(a, "shard_min_rows", 0) or 0)
+        sharded = (world > 1 and len(todo) == 1 and shard_min > 0 and int(a.local_sample_num * min(a.training_set_frac, 1.0)) >= shard_min
+                   and a.training_set_frac >= 1.0)
         shapes, offs, per_rank = [], [], [4] * world
         for k, c in enumerate(todo):
             circular = self._circular(plans[id(c)][1])
@@ -201,10 +217,15 @@ class CliqueScheduler:
             n_state = NSF_AR.packed_size(d, a.num_knots, a.hidden_dim) + iters + 4
             length = (n_state + 2 * d + 3) & ~3
             shapes.append((d, circular, n_state, length))
-            offs.append(per_rank[k % world])
-            per_rank[k % world] += length
+            if sharded:
+                offs.append(per_rank[0])
+                per_rank = [v + length for v in per_rank]
+            else:
+                offs.append(per_rank[k % world])
+                per_rank[k % world] += length
         width = max(per_rank)
-        mine = [(k, c) for k, c in enumerate(todo) if k % world == rank]
+        mine = [(k, c) for k, c in enumerate(todo) if sharded or k % world == rank]
+        group = self._shard_group() if sharded else None
         current = torch.cuda.current_stream(dev)
         gathered = torch.empty(world * width, dtype=torch.float32, device=dev)
         send = gathered[rank * width:(rank + 1) * width]
@@ -244,9 +265,17 @@ class CliqueScheduler:
             t1 = time.time()
             times[0] += t1 - t0
             flow = model.flows[0]
-            flow.fit_launch(data, iters, a.learning_rate, average_window=a.average_window, loss_delta_tol=a.loss_delta_tol,
-                            stream=stream, val=model._validation_data, validation_interval=a.validation_interval,
-                            slower_stop_rate=a.slower_stop_rate, concurrency=len(mine))
+            if sharded and torch.is_tensor(data) and data.is_cuda:
+                r0, r1 = group.rows(data.shape[0])
+                flow.fit_launch(data[r0:r1], iters, a.learning_rate, average_window=a.average_window, loss_delta_tol=a.loss_delta_tol,
+                                stream=stream, shard=group, n_total=int(data.shape[0]))
+                model._shard_keep = data
+            else:
+                if sharded:
+                    raise RuntimeError("row-sharded training needs the device simulation pipeline")
+                flow.fit_launch(data, iters, a.learning_rate, average_window=a.average_window, loss_delta_tol=a.loss_delta_tol,
+                                stream=stream, val=model._validation_data, validation_interval=a.validation_interval,
+                                slower_stop_rate=a.slower_stop_rate, concurrency=len(mine))
             flow.fit_export(send.data_ptr() + 4 * offs[k], iters)
             local[k] = model
             used_streams.append(stream)
@@ -255,19 +284,21 @@ class CliqueScheduler:
         for stream in used_streams:
             current.wait_stream(stream)
         send[0:1].copy_(counter.to(torch.float32))
-        if world > 1:
+        if world > 1 and not sharded:
             dist.all_gather_into_tensor(gathered, send, group=pg)
         host_t = self._pinned_f32("_pinned", world * width)
         host_t.copy_(gathered, non_blocking=True)
         current.synchronize()                                  # the only host wait of the level
         host = host_t.numpy()
         times[1] += time.time() - t1
-        if any(host[r * width] != 0.0 for r in range(world)):
+        if any(host[r * width] != 0.0 for r in (range(world) if not sharded else [rank])):
             raise AssertionError("negative discriminant in the inverse spline while sampling a separator factor")
+        if sharded and group.timed_out():
+            raise RuntimeError("row-sharded training: a rank of the shard group did not answer (nfisam_shard_group_error)")
         out = {}
         for k, c in enumerate(todo):
             d, circular, n_state, length = shapes[k]
-            owner = k % world
+            owner = rank if sharded else k % world
             base = owner * width + offs[k]
             rec = host[base: base + n_state + 2 * d]
             n_packed = n_state - iters - 4
@@ -281,6 +312,7 @@ class CliqueScheduler:
                 model._norm_cache = None
                 model.__dict__.pop("_mean_std_dev", None)
                 model.__dict__.pop("_sim_keep", None)
+                model.__dict__.pop("_shard_keep", None)
                 flow = model.flows[0]
             else:
                 flow = NSF_AR(dim=d, K=a.num_knots, hidden_dim=a.hidden_dim, device=dev.index, initial_parameters="device")

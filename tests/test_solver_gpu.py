@@ -74,7 +74,7 @@ def solve_seeded(case, seed, **kw):
     return solve(case, _reseed=False, **kw)
 
 
-@pytest.mark.parametrize("case", ["small_case1", "small_case1_da", "manhattan_r1_p10", "manhattan_r2_p5"])
+@pytest.mark.parametrize("case", ["small_case1", "small_case1_da", "manhattan_r1_p10", "manhattan_r2_p5", "manhattan_r2_p8_ada"])
 def test_incremental_solve_matches_reference_posterior(case):
     """N_SEEDS independently seeded runs of this solver against the reference's stored posterior(s).  NF-iSAM's
     run-to-run spread is large (the reference itself, seeds 0 vs 1: pose means up to 0.52 sigma apart, landmark
