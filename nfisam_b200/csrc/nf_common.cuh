@@ -137,14 +137,37 @@ __device__ __forceinline__ float2 nf_add2(float2 a, float2 b) { return __fadd2_r
 __device__ __forceinline__ float2 nf_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 nf_dup(float v) { return make_float2(v, v); }
 
-// two tanh at once: 3 packed FP32 ops + 4 MUFU
+// -DNF_MUFU_LEAN=1 (A/B builds; OFF by default, see below).  The forward kernels sit at ~55 % of the MUFU pipe with bursts of
+// 32 tanh MUFU per dim (ncu: math_pipe_throttle 0.9 per issue).  Experiment: three pairs of special-function calls merged: two reciprocals become one (1/a = b * rcp(a b), 1/b = a * rcp(a b)) in tanh2 and in the softmax normalisation, and the
+// two logarithms of the spline's log-determinant become one (log dnum - 2 log den = log(dnum * rcp(den)^2), rcp(den) is needed
+// anyway).  57 -> 47 MUFU per sample-dim.
+#ifndef NF_MUFU_LEAN
+#define NF_MUFU_LEAN 0       // measured on B200 (1e7 x 12 log-prob): lean 2.836 ms, one MUFU per call 2.750 ms -- issue slots, not MUFU, bind
+#endif
+
+// (1/a, 1/b) with one MUFU.  a, b must be finite and a * b < 3.4e38.
+__device__ __forceinline__ float2 nf_rcp2(float a, float b) {
+#if NF_MUFU_LEAN && !NF_ACCURATE_MATH
+    const float r = nf_rcp(a * b);
+    return make_float2(r * b, r * a);
+#else
+    return make_float2(nf_rcp(a), nf_rcp(b));
+#endif
+}
+
+// two tanh at once: 3 packed FP32 ops + 4 MUFU (lean: 3 MUFU)
 __device__ __forceinline__ float2 nf_tanh2(float2 a) {
 #if NF_ACCURATE_MATH
     return make_float2(tanhf(a.x), tanhf(a.y));
 #else
-    const float2 t = nf_mul2(a, nf_dup(2.8853900817779268f));
+    float2 t = nf_mul2(a, nf_dup(2.8853900817779268f));
+#if NF_MUFU_LEAN
+    // exp(2a) is capped at 2^60 (tanh is 1 to float32 precision beyond 2^5 already): the product of the two denominators stays finite
+    t.x = fminf(t.x, 60.0f);
+    t.y = fminf(t.y, 60.0f);
+#endif
     const float2 d = nf_add2(make_float2(nf_ex2(t.x), nf_ex2(t.y)), nf_dup(1.0f));
-    return nf_fma2(nf_dup(-2.0f), make_float2(nf_rcp(d.x), nf_rcp(d.y)), nf_dup(1.0f));
+    return nf_fma2(nf_dup(-2.0f), nf_rcp2(d.x, d.y), nf_dup(1.0f));
 #endif
 }
 
@@ -185,6 +208,15 @@ __device__ __forceinline__ void nf_axpy_row(const float* __restrict__ wrow, floa
 #endif
 constexpr int NF_L1_UNROLL_V = NF_L1_UNROLL;
 
+#ifndef NF_L1_SWITCH
+#define NF_L1_SWITCH 1
+#endif
+template <int H, int I>
+__device__ __forceinline__ void nf_layer1(const float* __restrict__ W1t, const float* __restrict__ xrow, float2 (&a)[H / 2]) {
+#pragma unroll
+    for (int k = 0; k < I; ++k) nf_axpy_row<H>(W1t + k * H, xrow[k], a);
+}
+
 template <int H>
 __device__ __forceinline__ void nf_mlp_hidden(const float* __restrict__ w, int i, const float* __restrict__ xrow,
                                               float (&h1)[H], float (&h2)[H]) {
@@ -194,10 +226,23 @@ __device__ __forceinline__ void nf_mlp_hidden(const float* __restrict__ w, int i
     const float* b2 = W2t + H * H;
     float2 a[H / 2];
     nf_load_bias<H>(b1, a);
+#if NF_L1_SWITCH
+    // i (the number of inputs of conditioner i) is uniform over the block: a switch picks a fully unrolled first layer; the
+    // loop form spends a third of its instructions on register moves and loop control
+    switch (i) {
+#define NF_L1_CASE(I) case I: nf_layer1<H, I>(W1t, xrow, a); break;
+        NF_L1_CASE(1) NF_L1_CASE(2) NF_L1_CASE(3) NF_L1_CASE(4) NF_L1_CASE(5) NF_L1_CASE(6) NF_L1_CASE(7) NF_L1_CASE(8)
+        NF_L1_CASE(9) NF_L1_CASE(10) NF_L1_CASE(11) NF_L1_CASE(12) NF_L1_CASE(13) NF_L1_CASE(14) NF_L1_CASE(15)
+#undef NF_L1_CASE
+        default:
+            for (int k = 0; k < i; ++k) nf_axpy_row<H>(W1t + k * H, xrow[k], a);
+    }
+#else
 #if NF_L1_UNROLL > 0
 #pragma unroll NF_L1_UNROLL_V
 #endif
     for (int k = 0; k < i; ++k) nf_axpy_row<H>(W1t + k * H, xrow[k], a);
+#endif
 #pragma unroll
     for (int j = 0; j < H / 2; ++j) { const float2 t = nf_tanh2(a[j]); h1[2 * j] = t.x; h1[2 * j + 1] = t.y; }
     nf_load_bias<H>(b2, a);
@@ -266,7 +311,7 @@ __device__ __forceinline__ void nf_knots2(const float2 (&out2)[NP], float B, flo
         S = nf_add2(S, e[k]);
         pre[k] = S;
     }
-    const float2 inv = make_float2(nf_rcp(S.x), nf_rcp(S.y));
+    const float2 inv = nf_rcp2(S.x, S.y);          // S in [1, K]: the product is harmless
     const float scale2B = 2.0f * B * (float)(1.0 - 1e-3 * (double)K);
     const float2 A = nf_mul2(inv, nf_dup(scale2B));
     c[0] = nf_dup(-B);
@@ -493,6 +538,54 @@ __device__ __forceinline__ void nf_bin_derivs(const float* __restrict__ b3, cons
     dk1 = bin == K - 1 ? NF_EDGE_DERIV : NF_MIN_DERIV + nf_softplus(u1);
 }
 
+// Rational-quadratic segment, forward direction (src/flows/utils.py:148-164), as an EXPLICIT sequence of float32 operations
+// (no compiler contraction): nf_rq_forward2 below evaluates two samples with the same sequence in packed f32x2 instructions
+// and must give the same bits.
+__device__ __forceinline__ void nf_rq_forward(float x, float2 lo, float2 hi, float dk, float dk1, float& z, float& l) {
+    const float wk = __fadd_rn(hi.x, -lo.x), hk = __fadd_rn(hi.y, -lo.y);
+    const float rw = nf_rcp(wk);
+    const float delta = __fmul_rn(hk, rw);
+    const float th = __fmul_rn(__fadd_rn(x, -lo.x), rw);
+    const float omt = __fadd_rn(1.0f, -th);
+    const float t1 = __fmul_rn(th, omt), th2 = __fmul_rn(th, th);
+    const float num = __fmul_rn(hk, __fmaf_rn(delta, th2, __fmul_rn(dk, t1)));
+    const float den = __fmaf_rn(__fmaf_rn(-2.0f, delta, __fadd_rn(dk, dk1)), t1, delta);
+    const float w = __fmaf_rn(dk1, th2, __fmaf_rn(__fadd_rn(delta, delta), t1, __fmul_rn(dk, __fmul_rn(omt, omt))));
+    const float dnum = __fmul_rn(__fmul_rn(delta, delta), w);
+#if NF_ACCURATE_MATH
+    l = logf(dnum) - 2.0f * logf(den);
+    z = lo.y + num / den;
+#else
+    l = __fmul_rn(0.6931471805599453f, __fmaf_rn(-2.0f, nf_lg2(den), nf_lg2(dnum)));
+    z = __fmaf_rn(num, nf_rcp(den), lo.y);
+#endif
+}
+
+// the same for two samples (A, B): every quantity is a float2 (A, B)
+__device__ __forceinline__ void nf_rq_forward2(float2 x, float2 loA, float2 hiA, float2 loB, float2 hiB, float2 dk, float2 dk1,
+                                               float2& z, float2& l) {
+#if NF_ACCURATE_MATH
+    nf_rq_forward(x.x, loA, hiA, dk.x, dk1.x, z.x, l.x);
+    nf_rq_forward(x.y, loB, hiB, dk.y, dk1.y, z.y, l.y);
+#else
+    const float2 whA = nf_add2(hiA, make_float2(-loA.x, -loA.y)), whB = nf_add2(hiB, make_float2(-loB.x, -loB.y));   // (wk, hk) per sample
+    const float2 wk = make_float2(whA.x, whB.x), hk = make_float2(whA.y, whB.y);
+    const float2 xk = make_float2(loA.x, loB.x), yk = make_float2(loA.y, loB.y);
+    const float2 rw = make_float2(nf_rcp(wk.x), nf_rcp(wk.y));
+    const float2 delta = nf_mul2(hk, rw);
+    const float2 th = nf_mul2(nf_add2(x, make_float2(-xk.x, -xk.y)), rw);
+    const float2 omt = nf_add2(nf_dup(1.0f), make_float2(-th.x, -th.y));
+    const float2 t1 = nf_mul2(th, omt), th2 = nf_mul2(th, th);
+    const float2 num = nf_mul2(hk, nf_fma2(delta, th2, nf_mul2(dk, t1)));
+    const float2 den = nf_fma2(nf_fma2(nf_dup(-2.0f), delta, nf_add2(dk, dk1)), t1, delta);
+    const float2 w = nf_fma2(dk1, th2, nf_fma2(nf_add2(delta, delta), t1, nf_mul2(dk, nf_mul2(omt, omt))));
+    const float2 dnum = nf_mul2(nf_mul2(delta, delta), w);
+    l = nf_mul2(nf_dup(0.6931471805599453f),
+                nf_fma2(nf_dup(-2.0f), make_float2(nf_lg2(den.x), nf_lg2(den.y)), make_float2(nf_lg2(dnum.x), nf_lg2(dnum.y))));
+    z = nf_fma2(num, make_float2(nf_rcp(den.x), nf_rcp(den.y)), yk);
+#endif
+}
+
 // Forward spline of one value given the width / height outputs; derivs(bin, dk, dk1) supplies the two knot derivatives.
 // src/flows/utils.py:148-164.  Branch-free: values outside [-B, B] (identity, log-det 0) run on a dummy in-range value.
 template <int K, int NP, typename DerivFn>
@@ -505,23 +598,10 @@ __device__ __forceinline__ float nf_forward_tail(const float2 (&out2w)[NP], floa
     const int bin = nf_locate_bin<K, false>(c, x, lo, hi);
     float dk, dk1;
     derivs(bin, dk, dk1);
-    const float xk = lo.x, yk = lo.y;
-    const float wk = hi.x - xk, hk = hi.y - yk;
-    const float rw = nf_rcp(wk);
-    const float delta = hk * rw;
-    const float th = (x - xk) * rw;
-    const float t1 = th * (1.0f - th);
-    const float num = hk * (delta * th * th + dk * t1);
-    const float den = delta + (dk + dk1 - 2.0f * delta) * t1;
-    const float omt = 1.0f - th;
-    const float dnum = delta * delta * (dk1 * th * th + 2.0f * delta * t1 + dk * omt * omt);
-#if NF_ACCURATE_MATH
-    const float l = logf(dnum) - 2.0f * logf(den);
-#else
-    const float l = 0.6931471805599453f * fmaf(-2.0f, nf_lg2(den), nf_lg2(dnum));
-#endif
+    float z, l;
+    nf_rq_forward(x, lo, hi, dk, dk1, z, l);
     ld = inside ? l : 0.0f;
-    return inside ? yk + nf_div(num, den) : xin;
+    return inside ? z : xin;
 }
 
 // z_i and log|dz_i/dx_i| of dim i for one sample (src/flows/flows.py:77-89)
@@ -599,6 +679,16 @@ __device__ __forceinline__ void nf_axpy_row2(const float* __restrict__ wrow, flo
     }
 }
 
+#ifndef NF_L1_SWITCH
+#define NF_L1_SWITCH 1
+#endif
+template <int H, int I>
+__device__ __forceinline__ void nf_layer1_pair(const float* __restrict__ W1t, const float* __restrict__ xrowA,
+                                               const float* __restrict__ xrowB, float2 (&aA)[H / 2], float2 (&aB)[H / 2]) {
+#pragma unroll
+    for (int k = 0; k < I; ++k) nf_axpy_row2<H>(W1t + k * H, xrowA[k], xrowB[k], aA, aB);
+}
+
 template <int K, int H>
 __device__ __forceinline__ void nf_outputs_wh_pair(const float* __restrict__ wbase, int i, const float* __restrict__ xrowA,
                                                    const float* __restrict__ xrowB, float2 (&oA)[NfLazy<K>::PPW / 2],
@@ -623,7 +713,20 @@ __device__ __forceinline__ void nf_outputs_wh_pair(const float* __restrict__ wba
     nf_load_bias<H>(b1, aA);
 #pragma unroll
     for (int j = 0; j < H / 2; ++j) aB[j] = aA[j];
+#if NF_L1_SWITCH
+    // The first layer has i inputs, a runtime count: the loop form spends a third of its instructions on register moves and
+    // loop control (SASS of the pair kernel).  i is uniform over the block, so a switch picks a fully unrolled body.
+    switch (i) {
+#define NF_L1_CASE(I) case I: nf_layer1_pair<H, I>(W1t, xrowA, xrowB, aA, aB); break;
+        NF_L1_CASE(1) NF_L1_CASE(2) NF_L1_CASE(3) NF_L1_CASE(4) NF_L1_CASE(5) NF_L1_CASE(6) NF_L1_CASE(7) NF_L1_CASE(8)
+        NF_L1_CASE(9) NF_L1_CASE(10) NF_L1_CASE(11) NF_L1_CASE(12) NF_L1_CASE(13) NF_L1_CASE(14) NF_L1_CASE(15)
+#undef NF_L1_CASE
+        default:
+            for (int k = 0; k < i; ++k) nf_axpy_row2<H>(W1t + k * H, xrowA[k], xrowB[k], aA, aB);
+    }
+#else
     for (int k = 0; k < i; ++k) nf_axpy_row2<H>(W1t + k * H, xrowA[k], xrowB[k], aA, aB);
+#endif
 #pragma unroll
     for (int j = 0; j < H / 2; ++j) {
         const float2 ta = nf_tanh2(aA[j]), tb = nf_tanh2(aB[j]);
@@ -664,7 +767,13 @@ __device__ __forceinline__ void nf_outputs_wh_pair(const float* __restrict__ wba
     }
 }
 
-// z_i and log|dz_i/dx_i| of dim i for two samples
+// z_i and log|dz_i/dx_i| of dim i for two samples.  The spline tails of the two samples are evaluated TOGETHER: knots and bin
+// scans interleaved statement by statement (two independent dependency chains per scheduler slot instead of one after the
+// other: the tail phases showed 1.2 - 1.5 stall samples per instruction against 0.6 in the MLP phases), the segment arithmetic
+// in packed f32x2 over (A, B).  Same operations in the same order as the single-sample path: bit-identical results.
+#ifndef NF_PAIR_TAIL
+#define NF_PAIR_TAIL 0         // measured on B200 (1e7 x 12): 2.632 ms with, 2.627 ms without -- the compiler already interleaves the two tails
+#endif
 template <int K, int H>
 __device__ __forceinline__ void nf_forward_dim_pair(const float* __restrict__ wbase, int i, const float* __restrict__ xrowA,
                                                     const float* __restrict__ xrowB, float B, float& zA, float& zB, float& ldA,
@@ -674,8 +783,74 @@ __device__ __forceinline__ void nf_forward_dim_pair(const float* __restrict__ wb
     const float* b3;
     const float* W3t;
     nf_outputs_wh_pair<K, H>(wbase, i, xrowA, xrowB, oA, oB, h2A, h2B, b3, W3t);
+#if !NF_PAIR_TAIL
     zA = nf_forward_tail<K>(oA, B, xrowA[i], ldA, [&](int bin, float& dk, float& dk1) { nf_bin_derivs<K, H>(b3, W3t, h2A, bin, dk, dk1); });
     zB = nf_forward_tail<K>(oB, B, xrowB[i], ldB, [&](int bin, float& dk, float& dk1) { nf_bin_derivs<K, H>(b3, W3t, h2B, bin, dk, dk1); });
+#else
+    const float xinA = xrowA[i], xinB = xrowB[i];
+    const bool inA = (xinA >= -B && xinA <= B), inB = (xinB >= -B && xinB <= B);
+    const float xA = inA ? xinA : 0.0f, xB = inB ? xinB : 0.0f;
+    // ---- knots of both samples (nf_knots2 twice, interleaved)
+    float mwA = oA[0].x, mhA = oA[0].y, mwB = oB[0].x, mhB = oB[0].y;
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        mwA = fmaxf(mwA, oA[k].x); mhA = fmaxf(mhA, oA[k].y);
+        mwB = fmaxf(mwB, oB[k].x); mhB = fmaxf(mhB, oB[k].y);
+    }
+    const float L2E = 1.4426950408889634f;
+    const float2 nmA = make_float2(-mwA * L2E, -mhA * L2E), nmB = make_float2(-mwB * L2E, -mhB * L2E);
+    float2 preA[K], preB[K];
+    float2 SA = make_float2(0.0f, 0.0f), SB = SA;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#if NF_ACCURATE_MATH
+        const float2 eA = make_float2(expf(oA[k].x - mwA), expf(oA[k].y - mhA)), eB = make_float2(expf(oB[k].x - mwB), expf(oB[k].y - mhB));
+#else
+        const float2 tA = nf_fma2(oA[k], nf_dup(L2E), nmA), tB = nf_fma2(oB[k], nf_dup(L2E), nmB);
+        const float2 eA = make_float2(nf_ex2(tA.x), nf_ex2(tA.y)), eB = make_float2(nf_ex2(tB.x), nf_ex2(tB.y));
+#endif
+        SA = nf_add2(SA, eA);
+        SB = nf_add2(SB, eB);
+        preA[k] = SA;
+        preB[k] = SB;
+    }
+    const float scale2B = 2.0f * B * (float)(1.0 - 1e-3 * (double)K);
+    const float2 AA = nf_mul2(make_float2(nf_rcp(SA.x), nf_rcp(SA.y)), nf_dup(scale2B));
+    const float2 AB = nf_mul2(make_float2(nf_rcp(SB.x), nf_rcp(SB.y)), nf_dup(scale2B));
+    float2 cA[K + 1], cB[K + 1];
+    cA[0] = cB[0] = nf_dup(-B);
+    cA[K] = cB[K] = nf_dup(B);
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        const float2 off = nf_dup(2.0f * B * NF_MIN_BIN * (float)k - B);
+        cA[k] = nf_fma2(preA[k - 1], AA, off);
+        cB[k] = nf_fma2(preB[k - 1], AB, off);
+    }
+    // ---- bins (nf_locate_bin twice, interleaved)
+    float2 loA = cA[0], loB = cB[0], hiA = cA[K], hiB = cB[K];
+    int binA = 0, binB = 0;
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        const bool geA = xA >= cA[k].x, geB = xB >= cB[k].x;
+        loA.x = geA ? cA[k].x : loA.x; loA.y = geA ? cA[k].y : loA.y; binA += geA ? 1 : 0;
+        loB.x = geB ? cB[k].x : loB.x; loB.y = geB ? cB[k].y : loB.y; binB += geB ? 1 : 0;
+    }
+#pragma unroll
+    for (int k = K - 1; k >= 1; --k) {
+        const bool geA = xA >= cA[k].x, geB = xB >= cB[k].x;
+        hiA.x = geA ? hiA.x : cA[k].x; hiA.y = geA ? hiA.y : cA[k].y;
+        hiB.x = geB ? hiB.x : cB[k].x; hiB.y = geB ? hiB.y : cB[k].y;
+    }
+    float dkA, dk1A, dkB, dk1B;
+    nf_bin_derivs<K, H>(b3, W3t, h2A, binA, dkA, dk1A);
+    nf_bin_derivs<K, H>(b3, W3t, h2B, binB, dkB, dk1B);
+    float2 z, l;
+    nf_rq_forward2(make_float2(xA, xB), loA, hiA, loB, hiB, make_float2(dkA, dkB), make_float2(dk1A, dk1B), z, l);
+    ldA = inA ? l.x : 0.0f;
+    ldB = inB ? l.y : 0.0f;
+    zA = inA ? z.x : xinA;
+    zB = inB ? z.y : xinB;
+#endif
 }
 
 // theta_to_pipi (src/utils/Functions.py:20-21): (t + pi) mod 2pi - pi with Python's modulo sign.
