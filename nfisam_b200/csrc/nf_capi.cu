@@ -96,6 +96,8 @@ struct nf_flow {
     float* d_val_part = nullptr;
     size_t val_part_cap = 0;
     NfTrainCtrl* d_ctrl = nullptr;
+    float* d_scratch = nullptr;        // generic (runtime K / hidden) training: per-sample backward vectors
+    size_t scratch_cap = 0;
     float* d_partials = nullptr;       // large-batch training: per-block partial gradients / losses
     float* d_loss_partials = nullptr;
     int pending_iters = 0;
@@ -272,11 +274,10 @@ int nfisam_flow_create(int dim, int K, int hidden, float tail_bound, int device,
     *out = nullptr;
     if (dim < 1 || dim > NF_MAX_DIM) return nf_set_error(NF_ERR_UNSUPPORTED, "dim %d outside [1, %d]", dim, NF_MAX_DIM);
     if (K < 2 || hidden < 1 || !(tail_bound > 0.0f)) return nf_set_error(NF_ERR_BAD_ARG, "bad K / hidden / tail bound");
-    bool ok = false;
-#define NF_CASE(KK, HH) ok = ok || (K == KK && hidden == HH);
-    NF_FOREACH_KH(NF_CASE)
-#undef NF_CASE
-    if (!ok) return nf_set_error(NF_ERR_UNSUPPORTED, "(K=%d, hidden=%d) is not compiled into this build", K, hidden);
+    // (K, hidden) outside the template instantiations run on the generic kernels (nf_generic_kernels.cu): slower, same results
+    if (!nf_kh_compiled(K, hidden) && !nf_generic_supported(K, hidden))
+        return nf_set_error(NF_ERR_UNSUPPORTED, "(K=%d, hidden=%d): K must be in [2, %d], hidden in [1, %d]", K, hidden, NF_GENERIC_MAX_K,
+                            NF_GENERIC_MAX_H);
     int ndev = 0;
     NF_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return nf_set_error(NF_ERR_BAD_ARG, "device %d of %d", device, ndev);
@@ -322,7 +323,7 @@ int nfisam_flow_destroy(nf_flow_t* f) {
     DeviceGuard g(f->device);
     if (f->need_sync) cudaDeviceSynchronize();
     f->release(f->arena);
-    f->release(f->d_loss_part); f->release(f->d_partials); f->release(f->d_loss_partials); f->release(f->d_val_part);
+    f->release(f->d_loss_part); f->release(f->d_partials); f->release(f->d_loss_partials); f->release(f->d_val_part); f->release(f->d_scratch);
     for (int s = 0; s < 2; ++s) {
         f->release(f->d_stage_in[s]); f->release(f->d_stage_aux[s]); f->release(f->d_stage_out[s]);
         if (f->streams[s]) cudaStreamDestroy(f->streams[s]);
@@ -476,7 +477,8 @@ int nfisam_posterior_pass(const nf_gather_item* items, int n_items, const float*
         const bool any = it.norm.mean_dev || it.norm.std_dev || it.norm.circular_dev;
         if (any && !(it.norm.mean_dev && it.norm.std_dev && it.norm.circular_dev))
             return nf_set_error(NF_ERR_BAD_ARG, "item %d: incomplete nf_affine", k);
-        uniform = uniform && f->fd.K == items[0].flow->fd.K && f->fd.H == items[0].flow->fd.H && f->fd.B == items[0].flow->fd.B;
+        uniform = uniform && f->fd.K == items[0].flow->fd.K && f->fd.H == items[0].flow->fd.H && f->fd.B == items[0].flow->fd.B &&
+                  nf_kh_compiled(f->fd.K, f->fd.H);
         NfPassItem& h = host[(size_t)k];
         memset(&h, 0, sizeof(h));
         h.pk = f->d_pk;
@@ -719,6 +721,12 @@ int nfisam_flow_inverse_host(nf_flow_t* f, const float* z_host, const float* x_s
 // ------------------------------------------------------------------------------------------------
 // training
 // ------------------------------------------------------------------------------------------------
+static int launch_train_any(nf_flow* f, const NfTrainArgs& a, cudaStream_t st) {
+    if (nf_kh_compiled(f->fd.K, f->fd.H)) return nf_launch_train(f->fd, a, f->device, st);
+    if (a.n_total > 0) return nf_set_error(NF_ERR_UNSUPPORTED, "row-sharded training needs a compiled (K, hidden) combination");
+    return nf_generic_train(f->fd, a, f->device, st, f->d_scratch, f->scratch_cap);
+}
+
 static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const nf_train_cfg* cfg, NfTrainArgs* a,
                            cudaStream_t st, bool force_plain = false) {
     if (cfg->max_iters < 1) return nf_set_error(NF_ERR_BAD_ARG, "max_iters < 1");
@@ -774,7 +782,19 @@ static int fill_train_args(nf_flow* f, const float* data_dev, int64_t n, const n
         }
         a->val_part = f->d_val_part;
     }
-    if ((n >= NF_TRAIN_PLAIN_MIN_N || force_plain) && cfg->n_val <= 0) {
+    const bool generic = !nf_kh_compiled(f->fd.K, f->fd.H);
+    if (generic) {
+        const size_t stg = (size_t)f->fd.P + 4 * (size_t)f->fd.H + 1;
+        const int64_t rows = n < 65536 ? n : 65536;
+        const size_t want = (size_t)rows * f->fd.d * stg;
+        if (f->scratch_cap < want) {
+            f->release(f->d_scratch);
+            f->scratch_cap = 0;
+            if (!(f->d_scratch = f->pooled(want * sizeof(float)))) return nf_set_error(NF_ERR_OOM, "device allocation failed");
+            f->scratch_cap = want;
+        }
+    }
+    if ((n >= NF_TRAIN_PLAIN_MIN_N || force_plain || generic) && cfg->n_val <= 0) {
         if (!f->d_partials) {
             f->d_partials = f->pooled(sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->n_packed);
             f->d_loss_partials = f->pooled(sizeof(float) * (size_t)NF_TRAIN_PLAIN_MAX_BLOCKS * (size_t)f->fd.d);
@@ -794,7 +814,7 @@ int nfisam_flow_train_launch(nf_flow_t* f, const float* data_dev, int64_t n, con
     NfTrainArgs a;
     int rc = fill_train_args(f, data_dev, n, cfg, &a, (cudaStream_t)stream);
     if (rc != NF_OK) return rc;
-    rc = nf_launch_train(f->fd, a, f->device, (cudaStream_t)stream);
+    rc = launch_train_any(f, a, (cudaStream_t)stream);
     f->touch((cudaStream_t)stream);
     if (rc < 0) return rc;
     f->pending_launches = rc;
@@ -815,7 +835,7 @@ int nfisam_flow_train_launch_sharded(nf_flow_t* f, const float* data_dev, int64_
     a.n_total = n_total;
     rc = nf_shard_view(group, f->n_packed + f->fd.d, cfg->max_iters, &a.shard);
     if (rc != NF_OK) return rc;
-    rc = nf_launch_train(f->fd, a, f->device, (cudaStream_t)stream);
+    rc = launch_train_any(f, a, (cudaStream_t)stream);
     f->touch((cudaStream_t)stream);
     if (rc < 0) return rc;
     f->pending_launches = rc;
@@ -943,7 +963,7 @@ int nfisam_flow_loss_grad(nf_flow_t* f, const float* data_dev, int64_t n, float*
     if (rc != NF_OK) return rc;
     a.grad_only = 1;
     NF_CUDA(cudaMemsetAsync(f->d_grad, 0, sizeof(float) * (size_t)f->n_packed, (cudaStream_t)stream));
-    rc = nf_launch_train(f->fd, a, f->device, (cudaStream_t)stream);
+    rc = launch_train_any(f, a, (cudaStream_t)stream);
     if (rc < 0) return rc;
     NF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     if (grad_host) {

@@ -472,7 +472,7 @@ int nf_launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int
     if (fd.K == KK && fd.H == HH) return launch_forward<KK, HH>(fd, pk, x, n, d_in, z, logdet, logp, ws, mode, device, st);
     NF_FOREACH_KH(NF_CASE)
 #undef NF_CASE
-    return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
+    return nf_generic_forward(fd, pk, x, n, d_in, z, logdet, logp, ws, layout, st);      // runtime (K, hidden) fallback
 }
 
 int nf_launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep,
@@ -486,7 +486,7 @@ int nf_launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, c
                                              device, st);
     NF_FOREACH_KH(NF_CASE)
 #undef NF_CASE
-    return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
+    return nf_generic_inverse(fd, pk, zin, xsep, n, sep, out_dim, xout, logdet, mean, stdv, circ, bad, nullptr, nullptr, nullptr, 0, 0, 0, st);
 }
 
 int nf_launch_inverse_gather(const NfFlowDims& fd, const float* pk, const float* z, int ld_z, int z_col0, float* s_mat,
@@ -504,7 +504,16 @@ int nf_launch_inverse_gather(const NfFlowDims& fd, const float* pk, const float*
                                             device, st);
     NF_FOREACH_KH(NF_CASE)
 #undef NF_CASE
-    return nf_set_error(NF_ERR_UNSUPPORTED, "(K, hidden) combination not compiled in");
+    return nf_generic_inverse(fd, pk, z, nullptr, n, sep, out_dim, s_mat, nullptr, mean, stdv, circ, bad, sep_cols, sep_const, out_cols, ld_s,
+                              ld_z, z_col0, st);
+}
+
+bool nf_kh_compiled(int K, int H) {
+#define NF_CASE(KK, HH) \
+    if (K == KK && H == HH) return true;
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    return false;
 }
 
 int nf_launch_posterior_pass(const NfFlowDims& fd, const NfPassItem* items_dev, const int2* groups_dev, int n_groups,

@@ -129,6 +129,20 @@ int nf_launch_posterior_pass(const NfFlowDims& fd, const NfPassItem* items_dev, 
 int nf_launch_mixture_weights_batch(const nf_factor_desc* descs_dev, const int2* groups_dev, int n_groups, const double* x, int64_t n,
                                     int D, double* partial_dev, int blocks_per_group, cudaStream_t st);
 
+// nf_generic_kernels.cu: runtime (K, hidden) fallback for combinations outside NF_FOREACH_KH
+#define NF_GENERIC_MAX_K 64
+#define NF_GENERIC_MAX_H 64
+bool nf_generic_supported(int K, int H);
+bool nf_kh_compiled(int K, int H);
+int nf_generic_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_t n, int d_in, float* z, float* logdet, float* logp,
+                       float* ws, int layout, cudaStream_t st);
+int nf_generic_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep, int out_dim,
+                       float* xout, float* logdet, const float* mean, const float* stdv, const uint8_t* circ, unsigned long long* bad,
+                       const int32_t* sep_cols, const float* sep_const, const int32_t* out_cols, int ld_s, int ld_z, int z_col0,
+                       cudaStream_t st);
+int nf_generic_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st, float* scratch, size_t scratch_floats);
+int nf_launch_adam_plain(const NfTrainArgs& a, int d, int blocks, int it, int launch_idx, int adam_blocks, cudaStream_t st);
+
 // nf_shard.cu
 struct nf_shard_group;
 int nf_shard_view(nf_shard_group* g, int64_t floats_needed, int max_iters, NfShardView* out);

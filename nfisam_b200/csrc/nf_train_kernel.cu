@@ -1075,6 +1075,12 @@ int launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStr
 int nf_launch_train_part1(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st);
 
 #if NF_TRAIN_PART == 0
+int nf_launch_adam_plain(const NfTrainArgs& a, int d, int blocks, int it, int launch_idx, int adam_blocks, cudaStream_t st) {
+    nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
+    nf_count_launch();
+    return NF_OK;
+}
+
 size_t nf_train_loss_part_elems(const NfFlowDims& fd, int max_iters) { return (size_t)max_iters * fd.d; }
 
 int nf_launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st) {

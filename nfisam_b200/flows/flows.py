@@ -20,8 +20,10 @@ from .. import _lib
 
 
 class FCNN(nn.Module):
-    """Linear(in, H) - tanh - Linear(H, H) - tanh - Linear(H, out): parameter container only.
-    The conditioners are evaluated inside the fused CUDA kernels, never through this module."""
+    """Linear(in, H) - tanh - Linear(H, H) - tanh - Linear(H, out) (src/flows/flows.py:26-41).  In this package the module is
+    the host-side mirror of one conditioner's parameters: NSF_AR evaluates its conditioners inside the fused CUDA kernels, never
+    through this module.  `forward` is kept for user code that inspects a conditioner (``flow.layers[i](x)``, as the reference
+    allows): it is plain torch on whatever device the module's parameters and x live on, and no solver / kernel path calls it."""
 
     def __init__(self, in_dim, out_dim, hidden_dim):
         super().__init__()
@@ -34,7 +36,7 @@ class FCNN(nn.Module):
         )
 
     def forward(self, x):
-        raise RuntimeError("nfisam_b200.FCNN is a parameter container; conditioners run inside the CUDA kernels")
+        return self.network(x)
 
 
 def _cuda_index(device):

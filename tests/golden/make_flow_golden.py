@@ -143,8 +143,21 @@ CASES = [
     ("d7_K9_H16", 7, 9, 16, 32, 6, 20, 10),
     ("d1_K9_H8", 1, 9, 8, 16, 7, 0, 10),
 ]
+# (K, hidden) combinations outside the template instantiations of libnfisam_b200 (runtime-K / runtime-hidden kernels):
+# written as flowG_*.npz so that the fixtures above stay byte-identical
+GENERIC_CASES = [
+    ("d5_K7_H12", 5, 7, 12, 48, 21, 20, 15),
+    ("d9_K20_H8", 9, 20, 8, 40, 22, 20, 10),
+    ("d6_K3_H5", 6, 3, 5, 32, 23, 10, 10),
+]
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "generic":
+        for name, d, K, H, n, seed, pre, adam in GENERIC_CASES:
+            case = make_case(d, K, H, n, seed, pre, adam)
+            np.savez_compressed(os.path.join(HERE, f"flowG_{name}.npz"), **case)
+            print(name, "loss", case["loss"], "params", case["theta"].size)
+        sys.exit(0)
     for name, d, K, H, n, seed, pre, adam in CASES:
         case = make_case(d, K, H, n, seed, pre, adam)
         np.savez_compressed(os.path.join(HERE, f"flow_{name}.npz"), **case)

@@ -339,9 +339,11 @@ def test_unsupported_configuration_fails_loudly():
     from nfisam_b200 import _lib
     from nfisam_b200.flows import NSF_AR
 
-    f = NSF_AR(dim=3, K=7, hidden_dim=8)
-    with pytest.raises(_lib.NfisamError):
-        f.forward(torch.zeros(4, 3))
+    # outside the generic kernels' range (K <= 64, hidden <= 64) and beyond NFISAM_MAX_DIM: a named error, never a fallback
+    for kw, d in ((dict(K=65, hidden_dim=8), 3), (dict(K=9, hidden_dim=65), 3), (dict(K=9, hidden_dim=8), 33)):
+        f = NSF_AR(dim=d, **kw)
+        with pytest.raises(_lib.NfisamError):
+            f.forward(torch.zeros(4, d))
 
 
 def test_large_batch_training_mode_matches_oracle():
@@ -755,3 +757,50 @@ def test_sharded_training_on_two_gpus_matches_single_gpu(tmp_path):
     assert np.allclose(r["hist"][:int(r["ran"])], r["hist1"][:int(r["ran"])], rtol=2e-4)
     assert np.max(np.abs(r["theta"] - r["theta1"])) < 5e-3
     print(f"\nrow-sharded training, {int(r['world'])} GPUs: {float(r['sharded_ms']):.2f} ms against {float(r['single_ms']):.2f} ms on one GPU (80 iterations, 50001 x 12)")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (K, hidden) combinations outside the template instantiations: runtime-K / runtime-hidden kernels (nf_generic_kernels.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["d5_K7_H12", "d9_K20_H8", "d6_K3_H5"])
+def test_generic_knots_and_hidden_width_match_reference(name):
+    """The reference takes any num_knots / hidden_dim (src/flows/flows.py:51); combinations that are not compiled as templates
+    run on the generic kernels.  Same fixtures as the compiled combinations, produced by the reference's own flow
+    (make_flow_golden.py generic): forward in both layouts, prior log-prob, inverse, conditional inverse at 1e-5 (log-det 2e-5),
+    gradient against autograd, Adam trajectory against the reference's optimiser."""
+    import os
+
+    c = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"flowG_{name}.npz")))
+    d = int(c["d"])
+    x = torch.tensor(c["x"])
+    f = make_flow(c)
+    z, ld = f.forward(x)
+    assert _relmax(z.numpy(), c["z_ref"]) <= BAR and _relmax(ld.numpy(), c["ld_ref"]) <= BAR_LOGDET
+    g = make_flow(c, reference_layout=False)
+    z, ld = g.forward(x)
+    assert _relmax(z.numpy(), c["z_col"]) <= BAR and _relmax(ld.numpy(), c["ld_col"]) <= BAR_LOGDET
+    lp = g.log_prob(x).numpy()
+    want = c["ld_col"] - 0.5 * (c["z_col"].astype(np.float64) ** 2).sum(1) - 0.5 * d * np.log(2 * np.pi)
+    assert _relmax(lp, want) <= BAR
+    xi, ldi = f.inverse(torch.tensor(c["zin"]))
+    assert _relmax(xi.numpy(), c["x_inv"]) <= BAR and _relmax(ldi.numpy(), c["ld_inv"]) <= BAR_LOGDET
+    sep = int(c["sep"])
+    xc = f.inverse_given_separator(torch.tensor(c["zin_f"]), torch.tensor(c["x_sep"]) if sep else None)
+    assert _relmax(xc.numpy(), c["x_cond"]) <= BAR
+    loss, grad = g.loss_and_grad(x)
+    assert abs(loss - float(c["loss"])) <= 1e-5 * abs(float(c["loss"]))
+    assert np.max(np.abs(grad - c["grad"])) <= 2e-4 * np.max(np.abs(c["grad"]))
+    steps = len(c["adam_loss"])
+    hist, ran = g.fit(x, steps, float(c["adam_lr"]), average_window=0)
+    # Against the reference's float32 optimiser the curve is compared tightly over the first steps only: at K = 20 (narrow bins)
+    # the reference's own float32 run leaves the float64 trajectory at step 4 (12.9157 against 12.9234 in float64 AND in this
+    # kernel), so the whole curve is pinned to the float64 oracle and only loosely to the reference.
+    assert ran == steps and np.allclose(hist[:4], c["adam_loss"][:4], rtol=2e-5, atol=1e-5), (hist, c["adam_loss"])
+    assert np.allclose(hist, c["adam_loss"], rtol=3e-2)           # same bound as test_adam_trajectory_golden
+    _, hist64, _ = orc.train(c["theta"], d, int(c["K"]), int(c["H"]), float(c["B"]), c["x"], steps, float(c["adam_lr"]), average_window=0,
+                             dtype=np.float64)
+    assert np.allclose(hist, np.asarray(hist64)[:steps], rtol=1e-4), (hist, hist64)
+    # the early-stop window works on this path too (same rule as the compiled kernels)
+    g.load_flat_parameters(c["theta"])
+    hist2, ran2 = g.fit(x, 200, 0.01, average_window=10, loss_delta_tol=0.5)
+    assert ran2 == 20 and np.all(hist2[ran2:] == 0.0)

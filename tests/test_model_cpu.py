@@ -89,3 +89,25 @@ def test_host_shortcuts_are_bit_identical_to_the_reference_calls():
     for _ in range(30):
         x = rng.standard_normal((int(rng.integers(5, 2000)), int(rng.integers(1, 5)))) * rng.uniform(0.1, 3) + rng.uniform(-4, 4)
         assert np.array_equal(circmean(x, high=np.pi, low=-np.pi, axis=0), scipy_circmean(x, high=np.pi, low=-np.pi, axis=0))
+
+
+def test_conditioner_modules_are_inspectable():
+    """flow.layers[i](x) works like in the reference (src/flows/flows.py:26-41, 77-83): the lazily materialised FCNN mirrors hold the
+    flow's parameters, so a conditioner evaluated through torch equals W3 tanh(W2 tanh(W1 x + b1) + b2) + b3 of the flat vector."""
+    from nfisam_b200.flows import NSF_AR
+
+    torch.manual_seed(5)
+    flow = NSF_AR(dim=4, K=5, hidden_dim=8)
+    theta = flow.flat_parameters()
+    x = torch.randn(7, 2)
+    out = flow.layers[1](x)                      # conditioner of dim 2: two inputs
+    P, H = 14, 8
+    off = P + (H * 1 + H + H * H + H + P * H + P)
+    W1 = theta[off:off + 2 * H].reshape(H, 2); off += 2 * H
+    b1 = theta[off:off + H]; off += H
+    W2 = theta[off:off + H * H].reshape(H, H); off += H * H
+    b2 = theta[off:off + H]; off += H
+    W3 = theta[off:off + P * H].reshape(P, H); off += P * H
+    b3 = theta[off:off + P]
+    want = np.tanh(np.tanh(x.numpy() @ W1.T + b1) @ W2.T + b2) @ W3.T + b3
+    assert out.shape == (7, P) and np.allclose(out.detach().numpy(), want, atol=1e-5)
