@@ -90,9 +90,21 @@ __device__ __forceinline__ float nf_sqrt(float v) {
 #endif
 }
 // tanh(v) = 1 - 2 / (exp(2v) + 1): 2 MUFU + 3 FP32 ops, absolute error ~1e-7 (saturates cleanly)
+// NF_TANH_MUFU = 1 (A/B builds only): the single-instruction tanh.approx.f32 -- one MUFU instead of two, but its relative
+// error is 2^-11, five hundred times the 1e-5 parity bar (profiles/r2_forward_kernel.md has the measured error table).
+#ifndef NF_TANH_MUFU
+#define NF_TANH_MUFU 0
+#endif
+__device__ __forceinline__ float nf_tanh_mufu(float v) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ float nf_tanh(float v) {
 #if NF_ACCURATE_MATH
     return tanhf(v);
+#elif NF_TANH_MUFU
+    return nf_tanh_mufu(v);
 #else
     const float t = nf_ex2(v * 2.8853900817779268f);
     return fmaf(-2.0f, nf_rcp(t + 1.0f), 1.0f);
@@ -159,6 +171,8 @@ __device__ __forceinline__ float2 nf_rcp2(float a, float b) {
 __device__ __forceinline__ float2 nf_tanh2(float2 a) {
 #if NF_ACCURATE_MATH
     return make_float2(tanhf(a.x), tanhf(a.y));
+#elif NF_TANH_MUFU
+    return make_float2(nf_tanh_mufu(a.x), nf_tanh_mufu(a.y));
 #else
     float2 t = nf_mul2(a, nf_dup(2.8853900817779268f));
 #if NF_MUFU_LEAN

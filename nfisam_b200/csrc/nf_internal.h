@@ -93,6 +93,9 @@ struct NfTrainArgs {
     float* partials;        // (NF_TRAIN_PLAIN_MAX_BLOCKS, n_packed)
     float* loss_partials;   // (NF_TRAIN_PLAIN_MAX_BLOCKS, d)
     int n_packed;
+    // blocks that work on dim i in the large-batch launch (cost-weighted split of the resident block slots, filled by the
+    // launcher); the grid is (max over dims, d) and the blocks past a dim's count only write a zero partial
+    unsigned char plain_blocks[NF_MAX_DIM];
     // row-sharded training over several GPUs (nf_shard.cu): this rank holds `n` of the n_total rows; 0 = not sharded
     int64_t n_total;
     NfShardView shard;

@@ -20,6 +20,7 @@
 // All reductions run in a fixed order: results are bitwise reproducible run to run.
 #include <cooperative_groups.h>
 #include <cstdio>
+#include <algorithm>
 
 // the unrolled first-layer switch of nf_common.cuh pays in the forward / inverse kernels (-4 %) but not here (n = 2000: 6.2 -> 6.5 us
 // per iteration, 1e6 x 12: 1.52 -> 1.55 ms: larger code, same latency chain)
@@ -372,11 +373,14 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     // cluster mode: the C blocks of a cluster share one dim; plain (large-batch) mode: gridDim.x independent blocks
     // per dim that leave their partial gradient in global memory for nf_adam_kernel
     cg::cluster_group cluster = cg::this_cluster();
-    const int C = plain ? (int)gridDim.x : (int)cluster.num_blocks();
-    const int r = plain ? (int)blockIdx.x : (int)cluster.block_rank();
     const int i = blockIdx.y;                      // the dim / conditioner this cluster trains
+    const int C = plain ? (int)a.plain_blocks[i] : (int)cluster.num_blocks();
+    const int r = plain ? (int)blockIdx.x : (int)cluster.block_rank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = W * 32;
+#ifdef NF_TRAIN_DIM_TIMING
+    const long long dim_t0 = clock64();            // scratch builds: cost of one block per dim (calibrates the plain-mode block split)
+#endif
 
     // local offsets inside block i
     const int oW1 = 0, ob1 = i * H, oW2 = ob1 + H, ob2 = oW2 + H * H, oW3 = ob2 + H, ob3 = i == 0 ? 0 : oW3 + H * PP;
@@ -385,6 +389,14 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     const int Gs = (G + C - 1) / C;                // slice per cluster rank
     const int p_lo = r * Gs, p_hi = min(G, p_lo + Gs);
     const int dp = (i + 1) | 1;
+    if (plain && r >= C) {
+        // large-batch mode gives dim i only plain_blocks[i] of the gridDim.x block columns (the dims differ in cost: dim 0 has no
+        // conditioner network); the others contribute a zero partial so that nf_adam_kernel sums gridDim.x rows for every dim
+        float* dst = a.partials + (size_t)r * a.n_packed + goff;
+        for (int p = threadIdx.x; p < G; p += T) dst[p] = 0.0f;
+        if (threadIdx.x == 0) a.loss_partials[r * d + i] = 0.0f;
+        return;
+    }
 
     extern __shared__ __align__(16) float smem[];
     float* s_w = smem;                              // [G]  (G is a multiple of 4)
@@ -735,6 +747,10 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
             float* dst = a.partials + (size_t)r * a.n_packed + goff;
             for (int p = threadIdx.x; p < G; p += T) dst[p] = s_g[p];
             if (threadIdx.x == 0) a.loss_partials[r * d + i] = s_misc[0];
+#ifdef NF_TRAIN_DIM_TIMING
+            if (threadIdx.x == 0 && (r == 0 || r == C - 1) && it_begin == 3)
+                printf("dim timing d=%d dim %2d block %2d of %2d: %lld cycles\n", d, i, r, C, clock64() - dim_t0);
+#endif
             return;                                               // one iteration per launch in this mode
         }
         NF_T(5);
@@ -925,6 +941,16 @@ nf_adam_sharded_kernel(NfTrainArgs a, int d, int blocks, int it, int launch_idx)
     }
 }
 
+// Relative cost of one 32-sample tile of dim i in the large-batch launch (forward + backward + outer products), fitted to the
+// per-dim block times of a -DNF_TRAIN_DIM_TIMING build on B200 (profiles/r2_train_kernel.md; K = 9, hidden 8, d = 12 and 18):
+// the spline, its gradient and the tile staging are common to all dims (dim 0, which has no network, costs half of dim 1);
+// the network part grows with the input count of the first layer.  Scaled with K and the hidden width for the other builds.
+static inline float nf_plain_dim_cost(int i, int K, int H) {
+    const float spline = (float)K / 9.0f;
+    if (i == 0) return spline;
+    return spline + ((float)H / 8.0f) * (0.9f * (float)(H + 3 * K - 1) / 34.0f + 0.065f * (float)i);
+}
+
 template <int K, int H, int W>
 size_t train_smem_bytes(int i_max, int C, int mt_res) {
     constexpr int PP = ((3 * K - 1) + 3) & ~3;
@@ -959,11 +985,28 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_big, W * 32, smem);
         if (per_sm < 1) per_sm = 1;
-        int blocks = (nf_sm_count(device) * per_sm + d - 1) / d;
-        const int64_t want = (ntiles + W - 1) / W;
-        if (blocks > want) blocks = (int)want;
-        if (blocks > NF_TRAIN_PLAIN_MAX_BLOCKS) blocks = NF_TRAIN_PLAIN_MAX_BLOCKS;
-        if (blocks < 1) blocks = 1;
+        // Split the resident block slots over the dims in proportion to their cost per tile (greedy: the next slot goes to the dim
+        // with the most work per block), so that all blocks finish together; an even split (ceil(slots / d) per dim) left the
+        // blocks of dim 0 idle after a fifth of the launch and put the overflow blocks into a second wave.
+        NfTrainArgs ab = a;
+        int cap = (int)std::min<int64_t>((ntiles + W - 1) / W, NF_TRAIN_PLAIN_MAX_BLOCKS);
+        if (cap < 1) cap = 1;
+        int nb[NF_MAX_DIM], used = d;
+        for (int i = 0; i < d; ++i) nb[i] = 1;
+        const int slots = nf_sm_count(device) * per_sm;
+        while (used < slots) {
+            int best = -1;
+            float load = 0.0f;
+            for (int i = 0; i < d; ++i) {
+                const float l = nf_plain_dim_cost(i, K, H) / (float)nb[i];
+                if (nb[i] < cap && l > load) { load = l; best = i; }
+            }
+            if (best < 0) break;
+            ++nb[best];
+            ++used;
+        }
+        int blocks = 1;
+        for (int i = 0; i < d; ++i) { ab.plain_blocks[i] = (unsigned char)nb[i]; blocks = std::max(blocks, nb[i]); }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(blocks, d, 1);
         cfg.blockDim = dim3(W * 32, 1, 1);
@@ -980,7 +1023,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         const int adam_blocks = (a.n_packed + (sharded ? d : 0) + 255) / 256;
         for (int it = 0; it < a.max_iters; ++it) {
             const int launch_idx = it / window;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern_big, a, d, fd.B, 2, 0, it, it + 1, launch_idx, 1, 0);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern_big, ab, d, fd.B, 2, 0, it, it + 1, launch_idx, 1, 0);
             if (e != cudaSuccess) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, plain)");
             if (sharded) nf_adam_sharded_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
             else nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
