@@ -426,7 +426,8 @@ def run_gpu(args):
         hbm_peak, hbm_src = measured_peaks()
         hbm_ach = alg_bytes / (per_launch_ms * 1e-3) * 1e-9
         roofline = {
-            "bound": "fp32_fma", "kernel": "nf_log_prob_pair_kernel<K=9,H=8> (log-prob, two samples per thread; batches below 5e5 rows use nf_forward_kernel)",
+            "bound": "fp32_fma", "kernel": "nf_log_prob_pair_kernel<K=9,H=8> (log-prob, two samples per thread, cp.async tile prefetch; batches below 5e5 rows use "
+                                          "nf_forward_kernel)",
             "achieved": achieved_tflops, "peak": fp32_peak.value, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak.value if fp32_peak.value > 0 else None,
             "peak_source": "measured live: best of the FFMA / FFMA2 probe kernels (nfisam_probe_pipe_peaks); "
@@ -439,9 +440,10 @@ def run_gpu(args):
             "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                     "algorithmic_bytes_per_sample": 4 * D + 4, "peak_source": hbm_src},
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the `ncu --set full` capture of this
-            # same command (profiles/r1_forward_kernel.md, capture F: 480.2 + 38.4 MB); algorithmic bytes: (4 d + 4) n = 520 MB
-            "traffic": 518.6e6 * (n / 1.0e7), "traffic_unit": "bytes per launch",
-            "traffic_source": "ncu capture F (profiles/r1_forward_kernel.md), scaled by n / 1e7", "algorithmic_bytes_per_launch": alg_bytes,
+            # same command (profiles/r2_forward_kernel.md, capture r2_prof_fwd_b: 480.2 + 37.5 MB); algorithmic bytes: (4 d + 4) n = 520 MB
+            "traffic": 517.7e6 * (n / 1.0e7), "traffic_unit": "bytes per launch",
+            "traffic_source": "ncu --set full capture r2_prof_fwd_b of this round's kernel (profiles/r2_forward_kernel.md), scaled by n / 1e7",
+            "algorithmic_bytes_per_launch": alg_bytes,
             "launch_ms": per_launch_ms,
         }
         cpu = cpu_baseline_block(theta) if world == 1 and not args.no_cpu else None

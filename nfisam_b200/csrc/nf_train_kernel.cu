@@ -943,12 +943,12 @@ nf_adam_sharded_kernel(NfTrainArgs a, int d, int blocks, int it, int launch_idx)
 
 // Relative cost of one 32-sample tile of dim i in the large-batch launch (forward + backward + outer products), fitted to the
 // per-dim block times of a -DNF_TRAIN_DIM_TIMING build on B200 (profiles/r2_train_kernel.md; K = 9, hidden 8, d = 12 and 18):
-// the spline, its gradient and the tile staging are common to all dims (dim 0, which has no network, costs half of dim 1);
+// the spline, its gradient and the tile staging are common to all dims (dim 0, which has no network, costs 0.56 of dim 1);
 // the network part grows with the input count of the first layer.  Scaled with K and the hidden width for the other builds.
 static inline float nf_plain_dim_cost(int i, int K, int H) {
     const float spline = (float)K / 9.0f;
     if (i == 0) return spline;
-    return spline + ((float)H / 8.0f) * (0.9f * (float)(H + 3 * K - 1) / 34.0f + 0.065f * (float)i);
+    return spline + ((float)H / 8.0f) * (0.72f * (float)(H + 3 * K - 1) / 34.0f + 0.072f * (float)i);
 }
 
 template <int K, int H, int W>
