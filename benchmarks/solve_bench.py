@@ -45,6 +45,11 @@ def run_solve(robots=1, poses=100, landmarks=4, ada_prob=0.0, iters=500, samples
     per_step, splits, widths, trained = [], [], [], []
     launches0 = _lib.launch_count()
     cur = None
+    # objects of whatever ran before in this process (bench.py runs several solves back to back) go to the permanent generation:
+    # full collections inside the timed steps then only scan this solve's own objects (they showed up as 0.1 s outlier steps)
+    import gc
+    gc.collect()
+    gc.freeze()
     for sn, sf in steps:
         for v in sn:
             solver.add_node(v)
@@ -63,6 +68,7 @@ def run_solve(robots=1, poses=100, landmarks=4, ada_prob=0.0, iters=500, samples
         per_step.append(time.perf_counter() - t0)
         splits.append(timer)
         trained.append(len(solver._temp_training_loss))
+    gc.unfreeze()
     pose_err = [float(np.linalg.norm(cur[v].mean(0)[:2] - truth[v][:2])) for v in cur if v.type.value == "Pose"]
     lmk_err = [float(np.linalg.norm(cur[v].mean(0)[:2] - truth[v][:2])) for v in cur if v.type.value == "Landmark"]
     order = solver.elimination_ordering
