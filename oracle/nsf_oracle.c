@@ -6,6 +6,9 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define REAL float
 #define SUFFIX _f32
@@ -22,7 +25,6 @@
 /* Thread count of the OpenMP loops (bench.py sets it explicitly: torchrun exports OMP_NUM_THREADS=1).  Returns the
  * count in effect. */
 #ifdef _OPENMP
-#include <omp.h>
 int nsf_set_num_threads(int n) {
     if (n > 0) omp_set_num_threads(n);
     return omp_get_max_threads();

@@ -301,9 +301,22 @@ int FN(nsf_loss_grad)(const REAL* theta, int d, int K, int H, REAL B,
     const REAL half_log_2pi = (REAL)0.91893853320467274178;
     double loss_acc = 0.0;
     for (int64_t p = 0; p < np_; ++p) grad[p] = 0;
-    #pragma omp parallel
+    /* per-thread partial sums, added in thread order afterwards: with the static schedule the result is reproducible run to
+     * run for a given thread count (a critical section would add them in arrival order) */
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    REAL* gl_all = (REAL*)calloc((size_t)np_ * (size_t)nthreads, sizeof(REAL));
+    double* la_all = (double*)calloc((size_t)nthreads, sizeof(double));
+    if (gl_all == NULL || la_all == NULL) { free(gl_all); free(la_all); return -2; }
+    #pragma omp parallel num_threads(nthreads)
     {
-        REAL* gl = (REAL*)calloc((size_t)np_, sizeof(REAL));
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        REAL* gl = gl_all + (size_t)tid * (size_t)np_;
         double la = 0.0;
         #pragma omp for schedule(static)
         for (int64_t s = 0; s < n; ++s) {
@@ -339,13 +352,15 @@ int FN(nsf_loss_grad)(const REAL* theta, int d, int K, int H, REAL B,
                 }
             }
         }
-        #pragma omp critical
-        {
-            for (int64_t p = 0; p < np_; ++p) grad[p] += gl[p];
-            loss_acc += la;
-        }
-        free(gl);
+        la_all[tid] = la;
     }
+    for (int t = 0; t < nthreads; ++t) {
+        const REAL* gl = gl_all + (size_t)t * (size_t)np_;
+        for (int64_t p = 0; p < np_; ++p) grad[p] += gl[p];
+        loss_acc += la_all[t];
+    }
+    free(gl_all);
+    free(la_all);
     const REAL sc = -(REAL)1 / (REAL)n;
     for (int64_t p = 0; p < np_; ++p) grad[p] *= sc;
     *loss_out = (REAL)(-loss_acc / (double)n);
