@@ -70,6 +70,56 @@ def main():
     mix = [f for f in factors if hasattr(f, "posterior_weights")][0]
     col = jf._col_of
     mix.posterior_weights({v: xx[:, col[v]:col[v] + v.dim] for v in mix.vars})
+    # ---- round 2: generic (K, hidden) kernels, tensor-core gradient reduction at hidden 16, state export / import, sharded Adam
+    # (one-rank group), batched mixture weights, marginal statistics, R2 factors through a small solve
+    import torch.distributed as dist
+
+    from nfisam_b200.factors import GaussianPriorFactor, R2RangeGaussianLikelihoodFactor, R2RelativeGaussianLikelihoodFactor
+    from nfisam_b200.factors.factors import posterior_weights_batch
+    from nfisam_b200.flows.flows import ShardGroup
+    from nfisam_b200.slam import R2Variable
+    from nfisam_b200.slam.nfisam import NFiSAM, NFiSAMArgs
+    from nfisam_b200.utils.statistics import marginal_mean_cov
+
+    fg_ = NSF_AR(dim=5, K=7, hidden_dim=12)
+    xg = torch.tensor(rng.standard_normal((301, 5)).astype(np.float32) * 2.0)
+    fg_.forward(xg)
+    fg_.log_prob(xg)
+    fg_.inverse(xg)
+    fg_.inverse_given_separator(xg[:, :3].contiguous(), xg[:, :2].contiguous())
+    fg_.loss_and_grad(xg)
+    fg_.fit(xg, 6, 0.01, average_window=3)
+    fe = NSF_AR(dim=6, K=9, hidden_dim=8)
+    xe = torch.tensor(rng.standard_normal((900, 6)).astype(np.float32)).cuda()
+    rec = torch.zeros(fe.state_floats(8), device="cuda")
+    fe.fit_launch(xe, 8, 0.01, average_window=4)
+    fe.fit_export(rec.data_ptr(), 8)
+    torch.cuda.synchronize()
+    fi = NSF_AR(dim=6, K=9, hidden_dim=8)
+    fi.adopt_state(rec.data_ptr())
+    fi.log_prob(xe)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29761", rank=0, world_size=1)
+    try:
+        group = ShardGroup(dist.group.WORLD, torch.cuda.current_device(), NSF_AR.packed_size(6, 9, 8) + 6)
+        big6 = torch.tensor(rng.standard_normal((16500, 6)).astype(np.float32)).cuda()
+        fs = NSF_AR(dim=6, K=9, hidden_dim=8)
+        fs.fit_launch(big6, 4, 0.01, average_window=2, shard=group, n_total=16500)
+        fs.fit_finish()
+        assert not group.timed_out()
+    finally:
+        dist.destroy_process_group()
+    mixes = [f for f in factors if hasattr(f, "posterior_weights")]
+    posterior_weights_batch(mixes, {v: xx[:, col[v]:col[v] + v.dim] for v in nodes})
+    marginal_mean_cov(xx.astype(np.float32), nodes)
+    x0, x1, l1 = (R2Variable(n) for n in ("x0", "x1", "l1"))
+    solver = NFiSAM(NFiSAMArgs(num_knots=9, flow_iterations=10, local_sample_num=300, posterior_sample_num=100, hidden_dim=8))
+    for v in (l1, x0, x1):
+        solver.add_node(v)
+    solver.add_factor(GaussianPriorFactor(var=l1, mean=np.array([5.0, 5.0]), covariance=np.identity(2) * 0.5))
+    solver.add_factor(R2RangeGaussianLikelihoodFactor(var1=x0, var2=l1, observation=7.0, sigma=0.5))
+    solver.add_factor(R2RelativeGaussianLikelihoodFactor(var1=x0, var2=x1, observation=np.array([5.0, -5.0]), covariance=np.identity(2) * 0.25))
+    solver.update_physical_and_working_graphs()
+    solver.incremental_inference()
     torch.cuda.synchronize()
     print("sanitize_smoke: done")
 
