@@ -457,6 +457,8 @@ def run_gpu(args):
                        "parallelism": "replicas: samples sharded over ranks, no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 4 * D * n, "d2h_bytes_per_step": 4 * n,
                     "api": "nfisam_flow_log_prob_host (C ABI, pinned host buffers, 2-stream chunked pipeline)",
+                    # what bounds it: the host link.  Per-GPU H2D rate the timed region sustained (the D2H of the results overlaps)
+                    "h2d_gbs_per_gpu": 4 * D * e2e_value / world * 1e-9,
                     "host_cores_bound_near_gpu": bound_cores, "host_cores_visible": os.cpu_count()},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 
 def run_solve(robots=1, poses=100, landmarks=4, ada_prob=0.0, iters=500, samples=2000, posterior=1000, lr=0.02, knots=9,
-              max_steps=0, seed=0, process_group=None, device=None):
+              max_steps=0, seed=0, process_group=None, device=None, detail=False):
     """One incremental solve of a synthetic graph through the drop-in NFiSAM API; every rank of `process_group` calls this
     (None = single process).  Returns the result dict on every rank (times are the max over ranks)."""
     import hashlib
@@ -83,7 +83,9 @@ def run_solve(robots=1, poses=100, landmarks=4, ada_prob=0.0, iters=500, samples
         same = all(bool(torch.equal(hs[0], x)) for x in hs)
     per_step = t.cpu().numpy()
     sp = np.array(splits)
+    extra = {"per_step": [float(v) for v in per_step], "splits": [[float(x) for x in row] for row in sp]} if detail else {}
     return {
+        **extra,
         "bench": "incremental_solve", "n_gpus": world, "robots": robots, "poses_per_robot": poses,
         "landmarks": landmarks, "steps": len(steps), "variables": len(cur),
         "config": {"K": knots, "hidden": 8, "train_samples": samples, "max_iters": iters, "lr": lr,

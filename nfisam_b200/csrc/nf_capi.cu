@@ -9,6 +9,8 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <map>
+#include <set>
 #include <vector>
 
 #include "nf_internal.h"
@@ -40,6 +42,29 @@ int nf_check_launch(const char* what) {
     return NF_OK;
 }
 void nf_count_launch(int64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+int nf_allow_max_smem(const void* func, int device) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> done;
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_pair(func, device);
+    const auto it = done.find(key);
+    if (it != done.end()) return it->second;
+    int max_smem = 0;
+    cudaFuncAttributes attr;
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
+        cudaFuncGetAttributes(&attr, func) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    const int dyn = max_smem - (int)attr.sharedSizeBytes;          // the opt-in limit covers static + dynamic shared memory
+    if (dyn <= 0 || cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    done[key] = dyn;
+    return dyn;
+}
+
 int nf_sm_count(int device) {
     static int cache[64];
     static std::mutex mu;

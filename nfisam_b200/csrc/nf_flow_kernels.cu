@@ -413,16 +413,14 @@ int launch_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_
     const bool z_tile = (mode & WANT_Z) && !(mode & REF_LAYOUT);
     const size_t smem = sizeof(float) * ((size_t)wcount + (z_tile ? 2 : 1) * (size_t)TPB * dp);
     auto kern = nf_forward_kernel<K, H>;
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return nf_set_error(NF_ERR_UNSUPPORTED, "flow does not fit in shared memory");
-    }
+    if (smem > 48 * 1024 && (size_t)nf_allow_max_smem_k(kern, device) < smem)
+        return nf_set_error(NF_ERR_UNSUPPORTED, "flow does not fit in shared memory");
     static const int pair_env = getenv("NFISAM_FWD_PAIR") ? (getenv("NFISAM_FWD_PAIR")[0] == '1' ? 1 : 0) : -1;
     const bool pair = pair_env >= 0 ? pair_env == 1 : n >= NF_PAIR_MIN_ROWS;
     if (pair && mode == WANT_LP) {                 // two samples per thread (log-prob only)
         auto kern2 = nf_log_prob_pair_kernel<K, H>;
         const size_t smem2 = sizeof(float) * ((size_t)wcount + (NF_FWD_PREFETCH + 1) * 2 * (size_t)TPB * dp);
-        if (smem2 > 48 * 1024 && cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
+        if (smem2 > 48 * 1024 && (size_t)nf_allow_max_smem_k(kern2, device) < smem2)
             return nf_set_error(NF_ERR_UNSUPPORTED, "flow does not fit in shared memory");
         const int64_t tiles2 = (n + 2 * TPB - 1) / (2 * TPB);
         const int grid2 = grid_for(kern2, smem2, tiles2, device);
@@ -451,10 +449,8 @@ int launch_inverse(const NfFlowDims& fd, const float* pk, const float* zin, cons
     const int dp = d_end | 1;
     const size_t smem = sizeof(float) * ((size_t)wcount + 2 * (size_t)TPB * dp);
     auto kern = nf_inverse_kernel<K, H, GATHER>;
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return nf_set_error(NF_ERR_UNSUPPORTED, "flow does not fit in shared memory");
-    }
+    if (smem > 48 * 1024 && (size_t)nf_allow_max_smem_k(kern, device) < smem)
+        return nf_set_error(NF_ERR_UNSUPPORTED, "flow does not fit in shared memory");
     const int64_t tiles = (n + TPB - 1) / TPB;
     const int grid = grid_for(kern, smem, tiles, device);
     kern<<<grid, TPB, smem, st>>>(pk, w_first, wcount, d_end, sep, fd.B, zin, xsep, n, xout, logdet, mean, stdv, circ, bad, ga);
@@ -527,8 +523,7 @@ int nf_launch_posterior_pass(const NfFlowDims& fd, const NfPassItem* items_dev, 
 #define NF_CASE(KK, HH)                                                                                                    \
     if (fd.K == KK && fd.H == HH) {                                                                                        \
         auto kern = nf_posterior_pass_kernel<KK, HH>;                                                                      \
-        if (smem > 40 * 1024 &&                                                                                            \
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)             \
+        if (smem > 40 * 1024 && (size_t)nf_allow_max_smem_k(kern, device) < smem)                                          \
             return nf_set_error(NF_ERR_UNSUPPORTED, "flows do not fit in shared memory");                                  \
         kern<<<grid, PASS_ROWS, smem, st>>>(items_dev, groups_dev, fd.B, z, ld_z, s_mat, ld_s, n, bad, w_floats, dp_max);  \
         nf_count_launch();                                                                                                 \

@@ -24,6 +24,14 @@ int nf_check_launch(const char* what);
 int nf_cuda_fail(cudaError_t e, const char* what);
 void nf_count_launch(int64_t k = 1);
 int nf_sm_count(int device);
+// Raises cudaFuncAttributeMaxDynamicSharedMemorySize of `func` to the device's opt-in maximum, ONCE per (kernel, device).
+// Calling cudaFuncSetAttribute with a new value per launch (the exact size of that launch) stalled the host for 4-13 ms
+// whenever the value changed while earlier launches of the same kernel were still running -- cliques of one tree level
+// have different flow dimensions -- which showed up as 0.1 s outlier steps in the multi-robot solves.
+// Returns the dynamic shared memory the kernel may now use (opt-in maximum minus its static shared memory; 0 on error).
+int nf_allow_max_smem(const void* func, int device);
+template <typename KernelT>
+inline int nf_allow_max_smem_k(KernelT kernel, int device) { return nf_allow_max_smem(reinterpret_cast<const void*>(kernel), device); }
 
 #define NF_CUDA(expr)                                            \
     do {                                                         \

@@ -981,7 +981,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         // ---- large-batch mode: two launches per iteration, about two blocks per SM over all dims
         const size_t smem = train_smem_bytes<K, H, W>(d - 1, 1, 2);    // two tile slots per warp: the next tile is prefetched
         if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
-        NF_CUDA(cudaFuncSetAttribute(kern_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((size_t)nf_allow_max_smem_k(kern_big, device) < smem) { *fits = false; return NF_OK; }
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_big, W * 32, smem);
         if (per_sm < 1) per_sm = 1;
@@ -1045,7 +1045,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         // several runs in flight (clique scheduler): the <= 128-register build lets two blocks -- two cliques -- share an
         // SM, which hides the latency chains of one run behind the other; same arithmetic, bit-identical results
         if (a.co_resident && 2 * (smem + 1024) <= 227 * 1024) kern = kern_big;
-        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((size_t)nf_allow_max_smem_k(kern, device) < smem) { *fits = false; return NF_OK; }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(C, d, 1);
         cfg.blockDim = dim3(W * 32, 1, 1);
