@@ -446,7 +446,6 @@ def run_gpu(args):
             "algorithmic_bytes_per_launch": alg_bytes,
             "launch_ms": per_launch_ms,
         }
-        cpu = cpu_baseline_block(theta) if world == 1 and not args.no_cpu else None
         line = {
             "metric": "rqs_flow_log_prob_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -464,8 +463,6 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": roofline,
         }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
     # ---- companion metric "clique-flow train+sample s/incr-step".  Everything below that involves the solver runs on
     # ALL ranks (round 1 ran it on rank 0 only while the other ranks sat in a barrier: mismatched collectives, NCCL abort).
     extra = None
@@ -481,6 +478,10 @@ def run_gpu(args):
     if rank == 0:
         if extra is not None:
             line["incr_step"] = extra
+        if world == 1 and not args.no_cpu:
+            # LAST: the OpenMP oracle runs on every host core and raises the thread count of the libgomp instance torch shares;
+            # run before the solves it left them with 0.1 s outlier steps (host threads spinning next to the Python thread)
+            line["cpu_baseline"] = cpu_baseline_block(theta)
         print(json.dumps(line))
 
 
@@ -493,7 +494,15 @@ def clique_parallel_solves(group, local_rank):
     out = {}
     # warm-up: module loads, kernel attribute set-up, NCCL channels
     run_solve(robots=8, poses=4, ada_prob=0.4, iters=500, samples=2000, process_group=group, device=local_rank)
-    out["solve_mr8x64"] = run_solve(robots=8, poses=64, ada_prob=0.4, iters=500, samples=2000, process_group=group, device=local_rank)
+    detail = bool(os.environ.get("NFISAM_BENCH_DETAIL"))          # diagnostics: per-step times and phase splits on stderr
+    out["solve_mr8x64"] = run_solve(robots=8, poses=64, ada_prob=0.4, iters=500, samples=2000, process_group=group, device=local_rank,
+                                    detail=detail)
+    if detail:
+        ps, sp = np.array(out["solve_mr8x64"].pop("per_step")), np.array(out["solve_mr8x64"].pop("splits"))
+        gcs = np.array(out["solve_mr8x64"].pop("gc_s"))
+        for i in np.argsort(ps)[::-1][:8]:
+            print(f"[detail] step {i}: {ps[i]:.4f} s, graph/sim/train/posterior {np.round(sp[i], 4)}, unaccounted {ps[i] - sp[i].sum():.4f}, "
+                  f"gc {gcs[i]:.4f}", file=sys.stderr)
     out["solve_mr8x16_n50k"] = run_solve(robots=8, poses=16, ada_prob=0.4, iters=500, samples=50000, process_group=group,
                                         device=local_rank)
     return out

@@ -50,6 +50,16 @@ def run_solve(robots=1, poses=100, landmarks=4, ada_prob=0.0, iters=500, samples
     import gc
     gc.collect()
     gc.freeze()
+    gc_s, gc_step = [0.0, 0.0], []
+
+    def gc_cb(phase, info):
+        if phase == "start":
+            gc_s[1] = time.perf_counter()
+        else:
+            gc_s[0] += time.perf_counter() - gc_s[1]
+
+    if detail:
+        gc.callbacks.append(gc_cb)
     for sn, sf in steps:
         for v in sn:
             solver.add_node(v)
@@ -59,6 +69,7 @@ def run_solve(robots=1, poses=100, landmarks=4, ada_prob=0.0, iters=500, samples
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier(group=process_group)
+        gc_s[0] = 0.0
         t0 = time.perf_counter()
         solver.update_physical_and_working_graphs(timer=timer)
         levels = solver.working_bayes_tree.levels()
@@ -66,8 +77,11 @@ def run_solve(robots=1, poses=100, landmarks=4, ada_prob=0.0, iters=500, samples
         cur = solver.incremental_inference(timer=timer)
         torch.cuda.synchronize()
         per_step.append(time.perf_counter() - t0)
+        gc_step.append(gc_s[0])
         splits.append(timer)
         trained.append(len(solver._temp_training_loss))
+    if detail:
+        gc.callbacks.remove(gc_cb)
     gc.unfreeze()
     pose_err = [float(np.linalg.norm(cur[v].mean(0)[:2] - truth[v][:2])) for v in cur if v.type.value == "Pose"]
     lmk_err = [float(np.linalg.norm(cur[v].mean(0)[:2] - truth[v][:2])) for v in cur if v.type.value == "Landmark"]
@@ -83,7 +97,8 @@ def run_solve(robots=1, poses=100, landmarks=4, ada_prob=0.0, iters=500, samples
         same = all(bool(torch.equal(hs[0], x)) for x in hs)
     per_step = t.cpu().numpy()
     sp = np.array(splits)
-    extra = {"per_step": [float(v) for v in per_step], "splits": [[float(x) for x in row] for row in sp]} if detail else {}
+    extra = {"per_step": [float(v) for v in per_step], "splits": [[float(x) for x in row] for row in sp],
+             "gc_s": [float(v) for v in gc_step]} if detail else {}
     return {
         **extra,
         "bench": "incremental_solve", "n_gpus": world, "robots": robots, "poses_per_robot": poses,

@@ -306,6 +306,20 @@ int nfisam_flow_create(int dim, int K, int hidden, float tail_bound, int device,
     int ndev = 0;
     NF_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return nf_set_error(NF_ERR_BAD_ARG, "device %d of %d", device, ndev);
+    {
+        // first flow of this shape on this device: one-time kernel set-up (nf_allow_max_smem) away from the solve's hot loop
+        static std::mutex mu;
+        static std::set<std::array<int, 3>> prepared;
+        std::lock_guard<std::mutex> lk(mu);
+        if (prepared.insert({K, hidden, device}).second && nf_kh_compiled(K, hidden)) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            cudaSetDevice(device);
+            nf_flow_prepare_kernels(K, hidden, device);
+            nf_train_prepare_kernels(K, hidden, device);
+            cudaSetDevice(cur);
+        }
+    }
     nf_flow* f = new (std::nothrow) nf_flow();
     if (!f) return nf_set_error(NF_ERR_OOM, "host allocation failed");
     f->device = device;

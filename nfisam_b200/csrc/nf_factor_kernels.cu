@@ -283,7 +283,8 @@ int launch_params(const nf_factor_desc* descs_host, int n_desc, const double* x,
     static thread_local DescPack<N> pack;
     memcpy(pack.d, descs_host, sizeof(nf_factor_desc) * (size_t)n_desc);
     auto kern = nf_factor_logpdf_kernel<N>;
-    if (smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024 && (size_t)nf_allow_max_smem_k(kern, device) < smem)
+        return nf_set_error(NF_ERR_UNSUPPORTED, "rows of %d columns do not fit in shared memory", D);
     kern<<<factor_grid(kern, smem, n, device), FTPB, smem, st>>>(pack, n_desc, x, n, D, out, per_factor);
     nf_count_launch();
     return nf_check_launch("nf_factor_logpdf_kernel");
@@ -307,8 +308,7 @@ int nf_launch_factor_logpdf(const nf_factor_desc* descs_host, int n_desc, const 
     cudaError_t e = cudaMemcpyAsync(d_desc, descs_host, sizeof(nf_factor_desc) * (size_t)n_desc, cudaMemcpyHostToDevice, st);
     int rc = NF_OK;
     if (e == cudaSuccess) {
-        if (smem > 48 * 1024)
-            e = cudaFuncSetAttribute(nf_factor_logpdf_buf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024 && (size_t)nf_allow_max_smem_k(nf_factor_logpdf_buf_kernel, device) < smem) e = cudaErrorInvalidValue;
         if (e == cudaSuccess) {
             nf_factor_logpdf_buf_kernel<<<factor_grid(nf_factor_logpdf_buf_kernel, smem, n, device), FTPB, smem, st>>>(
                 d_desc, n_desc, x, n, D, out, per_factor);

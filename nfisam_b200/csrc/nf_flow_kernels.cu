@@ -504,6 +504,22 @@ int nf_launch_inverse_gather(const NfFlowDims& fd, const float* pk, const float*
                               ld_z, z_col0, st);
 }
 
+// Raise the shared-memory limits of every kernel of the (K, H) instantiation now (first flow of that shape on the device): the
+// one-time cudaFuncSetAttribute calls otherwise land in the middle of a solve step, behind running kernels.
+void nf_flow_prepare_kernels(int K, int H, int device) {
+#define NF_CASE(KK, HH)                                                  \
+    if (K == KK && H == HH) {                                            \
+        nf_allow_max_smem_k(nf_forward_kernel<KK, HH>, device);          \
+        nf_allow_max_smem_k(nf_log_prob_pair_kernel<KK, HH>, device);    \
+        nf_allow_max_smem_k(nf_inverse_kernel<KK, HH, false>, device);   \
+        nf_allow_max_smem_k(nf_inverse_kernel<KK, HH, true>, device);    \
+        nf_allow_max_smem_k(nf_posterior_pass_kernel<KK, HH>, device);   \
+        return;                                                          \
+    }
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+}
+
 bool nf_kh_compiled(int K, int H) {
 #define NF_CASE(KK, HH) \
     if (K == KK && H == HH) return true;

@@ -145,6 +145,8 @@ int nf_launch_mixture_weights_batch(const nf_factor_desc* descs_dev, const int2*
 #define NF_GENERIC_MAX_H 64
 bool nf_generic_supported(int K, int H);
 bool nf_kh_compiled(int K, int H);
+void nf_flow_prepare_kernels(int K, int H, int device);      // one-time shared-memory limits of the (K, H) kernels
+void nf_train_prepare_kernels(int K, int H, int device);
 int nf_generic_forward(const NfFlowDims& fd, const float* pk, const float* x, int64_t n, int d_in, float* z, float* logdet, float* logp,
                        float* ws, int layout, cudaStream_t st);
 int nf_generic_inverse(const NfFlowDims& fd, const float* pk, const float* zin, const float* xsep, int64_t n, int sep, int out_dim,

@@ -159,7 +159,9 @@ int nf_launch_rbf_sum(const double* x, int64_t m, const double* y, int64_t n, in
     const bool wide = smem > 96 * 1024;              // more than 64 columns: column-chunked kernel
     if (wide) smem = sizeof(double) * ((size_t)DC * XS + (size_t)YT * DC + (size_t)YT * XT);
     auto kern = wide ? nf_rbf_sum_wide_kernel : nf_rbf_sum_kernel;
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    int device = 0;
+    cudaGetDevice(&device);
+    if (smem > 48 * 1024 && (size_t)nf_allow_max_smem_k(kern, device) < smem)
         return nf_set_error(NF_ERR_UNSUPPORTED, "rows of %d columns do not fit in shared memory", d);
     kern<<<dim3((unsigned)gx, (unsigned)gy), XT, smem, st>>>(x, m, y, n, d, -0.5 / (sigma * sigma), skip_diag, partial);
     nf_count_launch();

@@ -1117,6 +1117,32 @@ int launch_train(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStr
 #endif
 int nf_launch_train_part1(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaStream_t st);
 
+void nf_train_prepare_kernels_part1(int K, int H, int device);
+#if NF_TRAIN_PART == 0
+void nf_train_prepare_kernels(int K, int H, int device) {
+#define NF_CASE(KK, HH)                                                                      \
+    if (HH == 8 && K == KK && H == HH) {                                                     \
+        nf_allow_max_smem_k(nf_train_kernel<KK, (HH == 8 ? HH : 8), 8, 1>, device);          \
+        nf_allow_max_smem_k(nf_train_kernel<KK, (HH == 8 ? HH : 8), 8, 2>, device);          \
+        return;                                                                              \
+    }
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+    nf_train_prepare_kernels_part1(K, H, device);
+}
+#else
+void nf_train_prepare_kernels_part1(int K, int H, int device) {
+#define NF_CASE(KK, HH)                                                                      \
+    if (HH != 8 && K == KK && H == HH) {                                                     \
+        nf_allow_max_smem_k(nf_train_kernel<KK, (HH != 8 ? HH : 16), 8, 1>, device);         \
+        nf_allow_max_smem_k(nf_train_kernel<KK, (HH != 8 ? HH : 16), 8, 2>, device);         \
+        return;                                                                              \
+    }
+    NF_FOREACH_KH(NF_CASE)
+#undef NF_CASE
+}
+#endif
+
 #if NF_TRAIN_PART == 0
 int nf_launch_adam_plain(const NfTrainArgs& a, int d, int blocks, int it, int launch_idx, int adam_blocks, cudaStream_t st) {
     nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
