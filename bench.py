@@ -132,6 +132,15 @@ class ClockSampler:
         if self.thread is not None:
             self.stop_flag = True
             self.thread.join(timeout=2)
+            if not self.sm:
+                # the poller never got a sample in (slow NVML calls on a busy host): one synchronous reading, GPU still warm
+                try:
+                    import pynvml as nv
+
+                    h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                except Exception:
+                    pass
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
                     "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 2 ms polling"}
         if self.proc is None:
