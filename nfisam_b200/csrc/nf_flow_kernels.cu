@@ -28,7 +28,6 @@ __global__ void __launch_bounds__(TPB, NF_FWD_MINB)
 nf_forward_kernel(const float* __restrict__ pk, int wcount, int d_in, float B, const float* __restrict__ x, int64_t n,
                   float* __restrict__ z, float* __restrict__ logdet, float* __restrict__ logp, float* __restrict__ ws,
                   int mode) {
-    constexpr int PP = ((3 * K - 1) + 3) & ~3;
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;
     const int dp = d_in | 1;                      // odd row stride: conflict-free per-thread rows
@@ -196,7 +195,6 @@ nf_inverse_kernel(const float* __restrict__ pk, int w_first, int wcount, int d, 
                   const float* __restrict__ xsep, int64_t n, float* __restrict__ xout, float* __restrict__ logdet,
                   const float* __restrict__ mean, const float* __restrict__ stdv, const uint8_t* __restrict__ circ,
                   unsigned long long* __restrict__ bad_count, const __grid_constant__ NfGather ga) {
-    constexpr int PP = ((3 * K - 1) + 3) & ~3;
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;
     const int dp = d | 1;

@@ -158,15 +158,6 @@ __device__ __forceinline__ void nf_load_a(NfFragA& f, float a0, float a1, float 
     nf_split_tf32(a2, f.hi[2], f.lo[2]);
     nf_split_tf32(a3, f.hi[3], f.lo[3]);
 }
-// c += A B at fp32-level accuracy; the small cross terms are added first
-__device__ __forceinline__ void nf_mma_3x(float (&c)[4], const NfFragA& a, float b0, float b1) {
-    uint32_t bh0, bl0, bh1, bl1;
-    nf_split_tf32(b0, bh0, bl0);
-    nf_split_tf32(b1, bh1, bl1);
-    nf_mma_tf32(c, a.lo, bh0, bh1);
-    nf_mma_tf32(c, a.hi, bl0, bl1);
-    nf_mma_tf32(c, a.hi, bh0, bh1);
-}
 // Accumulator fragments of one warp for conditioner i (see the layout comment above):
 //   c3[m][n]  dW3:   A = gout^T (rows p = 16 m + g, + 8),  B = h2  -> (p, k = 8 n + 2 t, + 1)
 //   c2[n]     dW2:   A = g2^T   (rows j; H = 8: the lower half of the tile is zero),  B = h1  -> (j, k)
@@ -364,9 +355,9 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     constexpr int P = 3 * K - 1;
     constexpr int PP = (P + 3) & ~3;
     constexpr int NC3 = (PP + 31) / 32;            // W3 columns owned per lane
-    constexpr int N2 = H * H / 32;                 // W2 entries owned per lane
+    [[maybe_unused]] constexpr int N2 = H * H / 32;                 // W2 entries owned per lane
     constexpr int LG = 32 / H;                     // lane groups (distinct k per pass)
-    constexpr int M1 = (NF_MAX_DIM + LG - 1) / LG; // W1 entries owned per lane (upper bound)
+    [[maybe_unused]] constexpr int M1 = (NF_MAX_DIM + LG - 1) / LG; // W1 entries owned per lane (upper bound)
     constexpr int STG = PP + 4 * H;                // staging row: gout | h2 | g2 | h1 | g1
     static_assert(H % 4 == 0 && 32 % H == 0, "hidden width must divide 32 and be a multiple of 4");
 
@@ -401,15 +392,20 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     extern __shared__ __align__(16) float smem[];
     float* s_w = smem;                              // [G]  (G is a multiple of 4)
     float* s_g = s_w + G;                           // [G]
-    float* s_wg = s_g + G;                          // [W][G]
-    float* s_m = s_wg + W * G;                      // [Gs]
+    float* s_m = s_g + G;                           // [Gs]
     float* s_v = s_m + Gs;                          // [Gs]
     float* s_loss = s_v + Gs;                       // [W]
     float* s_misc = s_loss + W;                     // [8]
     // [W][32][STG], 16-byte aligned.  The offset is rounded, not the pointer: a round trip through uintptr_t turns every later
     // access into a generic-address load (LD.E instead of LDS in the SASS).
-    float* s_stage = smem + (((2 + W) * G + 2 * Gs + W + 8 + 3) & ~3);
+    float* s_stage = smem + ((2 * G + 2 * Gs + W + 8 + 3) & ~3);
     float* s_x = s_stage + W * 32 * STG;            // [W][mt_res][32][dp]
+    // The per-warp gradient partials [W][G] of the block reduction live in the warps' own staging regions (G <= 32 STG, checked
+    // by the launcher): a warp writes them after the outer products of its last tile have read the region, and the next
+    // iteration stages again only behind a barrier.  Saves W G floats (15 KB at d = 18): two blocks per SM up to d = 21 in the
+    // large-batch mode instead of d = 15.
+    constexpr int WG_STRIDE = 32 * STG;
+    float* s_wg = s_stage;                          // [W][WG_STRIDE], first G entries of each used
 
     // val_pass: this launch only evaluates the validation loss (forward pass over a.val) for check `launch_idx`
     const int64_t n = val_pass ? a.n_val : a.n;
@@ -669,7 +665,7 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
         }
         // ---------------- per-warp partials -> shared ----------------
         {
-            float* wg = s_wg + warp * G;
+            float* wg = s_wg + warp * WG_STRIDE;
 #if NF_TRAIN_MMA
             if (i == 0) {
 #pragma unroll
@@ -723,7 +719,7 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
         for (int p = threadIdx.x; p < G; p += T) {
             float acc = 0.0f;
 #pragma unroll
-            for (int w = 0; w < W; ++w) acc += s_wg[w * G + p];
+            for (int w = 0; w < W; ++w) acc += s_wg[w * WG_STRIDE + p];
             s_g[p] = acc;
         }
         if (threadIdx.x == 0) {
@@ -958,7 +954,8 @@ size_t train_smem_bytes(int i_max, int C, int mt_res) {
     const int G = nf_block_size(i_max, H, PP);
     const int Gs = (G + C - 1) / C;
     const int dp = (i_max + 1) | 1;
-    size_t fl = (size_t)G * (2 + W) + 2 * (size_t)Gs + W + 8 + 4 /*align slack*/ + (size_t)W * 32 * STG +
+    if (G > 32 * STG) return ~(size_t)0 >> 1;                          // the gradient partials alias the staging regions
+    size_t fl = (size_t)G * 2 + 2 * (size_t)Gs + W + 8 + 4 /*align slack*/ + (size_t)W * 32 * STG +
                 (size_t)W * mt_res * 32 * dp;
     return fl * sizeof(float);
 }
