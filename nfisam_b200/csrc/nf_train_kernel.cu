@@ -26,6 +26,7 @@
 // per iteration, 1e6 x 12: 1.52 -> 1.55 ms: larger code, same latency chain)
 #define NF_L1_SWITCH 0
 
+
 #include "nf_internal.h"
 
 namespace cg = cooperative_groups;
@@ -351,7 +352,7 @@ __device__ __forceinline__ void nf_reduce_tile(const float* __restrict__ stage, 
 template <int K, int H, int W, int MINB>
 __global__ void __launch_bounds__(W * 32, MINB)
 nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_begin, int it_end, int launch_idx,
-                int plain, int val_pass) {
+                int plain, int val_pass, int alias_wg) {
     constexpr int P = 3 * K - 1;
     constexpr int PP = (P + 3) & ~3;
     constexpr int NC3 = (PP + 31) / 32;            // W3 columns owned per lane
@@ -392,20 +393,22 @@ nf_train_kernel(NfTrainArgs a, int d, float B, int mt_res, int resident, int it_
     extern __shared__ __align__(16) float smem[];
     float* s_w = smem;                              // [G]  (G is a multiple of 4)
     float* s_g = s_w + G;                           // [G]
-    float* s_m = s_g + G;                           // [Gs]
+    // The per-warp gradient partials [W][G] of the block reduction either have their own buffer behind s_g or (alias_wg) live in
+    // the warps' own staging regions (G <= 32 STG, checked by the launcher): a warp writes them after the outer products of its
+    // last tile have read the region, and the next iteration stages again only behind a barrier.  Aliasing saves W G floats
+    // (15 KB at d = 18): two blocks per SM up to d = 21 in the large-batch mode instead of d = 15 (200k x 18: 544 -> 437 us per
+    // iteration); where the block count does not change it is 4 % slower (1e6 x 12: 1192 -> 1245 us), so the launcher decides.
+    const int wg_own = alias_wg ? 0 : W * G;
+    float* s_m = s_g + G + wg_own;                  // [Gs]
     float* s_v = s_m + Gs;                          // [Gs]
     float* s_loss = s_v + Gs;                       // [W]
     float* s_misc = s_loss + W;                     // [8]
     // [W][32][STG], 16-byte aligned.  The offset is rounded, not the pointer: a round trip through uintptr_t turns every later
     // access into a generic-address load (LD.E instead of LDS in the SASS).
-    float* s_stage = smem + ((2 * G + 2 * Gs + W + 8 + 3) & ~3);
+    float* s_stage = smem + ((2 * G + wg_own + 2 * Gs + W + 8 + 3) & ~3);
     float* s_x = s_stage + W * 32 * STG;            // [W][mt_res][32][dp]
-    // The per-warp gradient partials [W][G] of the block reduction live in the warps' own staging regions (G <= 32 STG, checked
-    // by the launcher): a warp writes them after the outer products of its last tile have read the region, and the next
-    // iteration stages again only behind a barrier.  Saves W G floats (15 KB at d = 18): two blocks per SM up to d = 21 in the
-    // large-batch mode instead of d = 15.
-    constexpr int WG_STRIDE = 32 * STG;
-    float* s_wg = s_stage;                          // [W][WG_STRIDE], first G entries of each used
+    const int WG_STRIDE = alias_wg ? 32 * STG : G;
+    float* s_wg = alias_wg ? s_stage : s_g + G;     // [W][WG_STRIDE], first G entries of each used
 
     // val_pass: this launch only evaluates the validation loss (forward pass over a.val) for check `launch_idx`
     const int64_t n = val_pass ? a.n_val : a.n;
@@ -948,14 +951,14 @@ static inline float nf_plain_dim_cost(int i, int K, int H) {
 }
 
 template <int K, int H, int W>
-size_t train_smem_bytes(int i_max, int C, int mt_res) {
+size_t train_smem_bytes(int i_max, int C, int mt_res, bool alias_wg) {
     constexpr int PP = ((3 * K - 1) + 3) & ~3;
     constexpr int STG = PP + 4 * H;
     const int G = nf_block_size(i_max, H, PP);
     const int Gs = (G + C - 1) / C;
     const int dp = (i_max + 1) | 1;
-    if (G > 32 * STG) return ~(size_t)0 >> 1;                          // the gradient partials alias the staging regions
-    size_t fl = (size_t)G * 2 + 2 * (size_t)Gs + W + 8 + 4 /*align slack*/ + (size_t)W * 32 * STG +
+    if (alias_wg && G > 32 * STG) return ~(size_t)0 >> 1;              // the gradient partials would not fit their staging region
+    size_t fl = (size_t)G * (alias_wg ? 2 : 2 + W) + 2 * (size_t)Gs + W + 8 + 4 /*align slack*/ + (size_t)W * 32 * STG +
                 (size_t)W * mt_res * 32 * dp;
     return fl * sizeof(float);
 }
@@ -976,11 +979,17 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
     const int window = a.grad_only ? 1 : (a.average_window > 0 ? a.average_window : 64);
     if (a.partials != nullptr && a.loss_partials != nullptr) {
         // ---- large-batch mode: two launches per iteration, about two blocks per SM over all dims
-        const size_t smem = train_smem_bytes<K, H, W>(d - 1, 1, 2);    // two tile slots per warp: the next tile is prefetched
-        if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
-        if ((size_t)nf_allow_max_smem_k(kern_big, device) < smem) { *fits = false; return NF_OK; }
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_big, W * 32, smem);
+        // two tile slots per warp: the next tile is prefetched.  The gradient partials alias the staging regions only where that
+        // buys a resident block (see the kernel's layout comment)
+        const size_t smem_own = train_smem_bytes<K, H, W>(d - 1, 1, 2, false), smem_alias = train_smem_bytes<K, H, W>(d - 1, 1, 2, true);
+        const size_t allowed = (size_t)nf_allow_max_smem_k(kern_big, device);
+        if (smem_alias > (size_t)max_smem || allowed < smem_alias) { *fits = false; return NF_OK; }
+        int per_sm_own = 0, per_sm_alias = 0;
+        if (smem_own <= allowed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_own, kern_big, W * 32, smem_own);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_alias, kern_big, W * 32, smem_alias);
+        const int alias_wg = per_sm_alias > per_sm_own ? 1 : 0;
+        const size_t smem = alias_wg ? smem_alias : smem_own;
+        int per_sm = alias_wg ? per_sm_alias : per_sm_own;
         if (per_sm < 1) per_sm = 1;
         // Split the resident block slots over the dims in proportion to their cost per tile (greedy: the next slot goes to the dim
         // with the most work per block), so that all blocks finish together; an even split (ceil(slots / d) per dim) left the
@@ -1020,7 +1029,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         const int adam_blocks = (a.n_packed + (sharded ? d : 0) + 255) / 256;
         for (int it = 0; it < a.max_iters; ++it) {
             const int launch_idx = it / window;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern_big, ab, d, fd.B, 2, 0, it, it + 1, launch_idx, 1, 0);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern_big, ab, d, fd.B, 2, 0, it, it + 1, launch_idx, 1, 0, alias_wg);
             if (e != cudaSuccess) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, plain)");
             if (sharded) nf_adam_sharded_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
             else nf_adam_kernel<<<adam_blocks, 256, 0, st>>>(a, d, blocks, it, launch_idx);
@@ -1035,9 +1044,9 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         int mt = (int)((ntiles + TW - 1) / TW);
         if (mt < 1) mt = 1;
         int resident = 1;
-        size_t smem = train_smem_bytes<K, H, W>(d - 1, C, mt);
-        if (smem > 100 * 1024) { resident = 0; mt = 2; smem = train_smem_bytes<K, H, W>(d - 1, C, 2); }    // streamed: 2 slots per warp
-        if (a.n_val > 0 && mt < 2) { mt = 2; smem = train_smem_bytes<K, H, W>(d - 1, C, 2); }            // the validation pass streams its tiles
+        size_t smem = train_smem_bytes<K, H, W>(d - 1, C, mt, true);
+        if (smem > 100 * 1024) { resident = 0; mt = 2; smem = train_smem_bytes<K, H, W>(d - 1, C, 2, true); }    // streamed: 2 slots per warp
+        if (a.n_val > 0 && mt < 2) { mt = 2; smem = train_smem_bytes<K, H, W>(d - 1, C, 2, true); }            // the validation pass streams its tiles
         if (smem > (size_t)max_smem) { *fits = false; return NF_OK; }
         // several runs in flight (clique scheduler): the <= 128-register build lets two blocks -- two cliques -- share an
         // SM, which hides the latency chains of one run behind the other; same arithmetic, bit-identical results
@@ -1064,10 +1073,10 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
                 const int it1 = ((launch_idx + 1) * vi - 1) < a.max_iters ? ((launch_idx + 1) * vi - 1) : a.max_iters;
                 cudaError_t e = cudaSuccess;
                 if (launch_idx > 0) {
-                    e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, 0, it0, it0 + 1, launch_idx, 0, 1);
+                    e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, 0, it0, it0 + 1, launch_idx, 0, 1, 1);
                     nf_count_launch();
                 }
-                if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0, 0);
+                if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0, 0, 1);
                 if (e != cudaSuccess) {
                     cudaGetLastError();
                     if (launch_idx > 0 || C == 1) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel, validation)");
@@ -1082,7 +1091,7 @@ int launch_train_w(const NfFlowDims& fd, const NfTrainArgs& a, int device, cudaS
         }
         for (int it0 = 0; it0 < a.max_iters; it0 += window, ++launch_idx) {
             const int it1 = it0 + window < a.max_iters ? it0 + window : a.max_iters;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0, 0);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, d, fd.B, mt, resident, it0, it1, launch_idx, 0, 0, 1);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 if (launch_idx > 0 || C == 1) return nf_cuda_fail(e, "cudaLaunchKernelEx(nf_train_kernel)");
