@@ -2,6 +2,7 @@
 // with plain cudaMalloc / cudaFree that was ~10 driver allocations and as many device-wide synchronisations (cudaFree)
 // per clique.  Blocks are cached per device by size and handed out again once the event recorded after their last use
 // has completed -- no synchronisation, no driver call on the steady-state path.
+#include <cstdlib>
 #include <deque>
 #include <map>
 #include <mutex>
@@ -14,7 +15,18 @@ namespace {
 
 constexpr int MAX_DEV = 64;
 constexpr size_t GRAIN = 4096;                       // block sizes are multiples of 4 KB
-constexpr size_t POOL_LIMIT = (size_t)1 << 30;       // cached (idle) bytes per device above which blocks go back to the driver
+// Cached (idle) bytes per device above which blocks go back to the driver.  cudaFree synchronises the device, so hitting the limit
+// in the middle of a solve serialises the concurrent training runs (measured: +0.13 s per step on the 50 000-row multi-robot
+// solve when it ran after other work in the same process with the former 1 GB limit).  A B200 has 180 GB: 16 GB of cache is
+// cheap, and NFISAM_POOL_LIMIT_MB overrides it.
+static size_t pool_limit() {
+    static const size_t v = [] {
+        const char* e = getenv("NFISAM_POOL_LIMIT_MB");
+        const long mb = e ? atol(e) : 0;
+        return mb > 0 ? (size_t)mb << 20 : (size_t)16 << 30;
+    }();
+    return v;
+}
 
 struct EventPool {
     std::mutex mu;
@@ -142,7 +154,7 @@ static void pool_free(DevPool& pool, void* p, NfEventRef after, bool pinned) {
     if (it == pool.live.end()) return;               // not ours
     const size_t cap = it->second;
     pool.live.erase(it);
-    if (pool.idle_bytes + cap > POOL_LIMIT) {
+    if (pool.idle_bytes + cap > pool_limit()) {
         if (pinned) {
             if (after) cudaEventSynchronize(after->ev);
             cudaFreeHost(p);
