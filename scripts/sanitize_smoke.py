@@ -108,6 +108,10 @@ def main():
         assert not group.timed_out()
     finally:
         dist.destroy_process_group()
+    # aliased gradient-partials layout: cluster mode (always) and the large-batch mode at a flow dimension where it buys a block
+    fa = NSF_AR(dim=17, K=9, hidden_dim=8)
+    fa.fit(torch.tensor(rng.standard_normal((700, 17)).astype(np.float32)), 6, 0.01, average_window=3)
+    fa.fit(torch.tensor(rng.standard_normal((16500, 17)).astype(np.float32)), 2, 0.01, average_window=0)
     mixes = [f for f in factors if hasattr(f, "posterior_weights")]
     posterior_weights_batch(mixes, {v: xx[:, col[v]:col[v] + v.dim] for v in nodes})
     marginal_mean_cov(xx.astype(np.float32), nodes)
