@@ -3,8 +3,10 @@
  (b) the CPU oracle (oracle/nsf_oracle.c) on larger seeded inputs,
  (c) size-independent properties (forward/inverse round trip, layout permutation, loss invariance).
 
-Tolerances (float32 flow, north_star: 1e-5 relative): max-norm relative error <= 2e-5 plus
-allclose(rtol=1e-5, atol=5e-5) -- see SURVEY.md section 7 "tolerance reality check"."""
+Tolerances (float32 flow, north_star: 1e-5 relative): max-norm relative error <= 1e-5 for z / x against the reference's float32
+results and the oracle; per-sample log-determinants (sums of d terms of either sign) by allclose(rtol=1e-5, atol=5e-5 .. 1e-4)
+here and by the 2e-5 max-norm bar of the error-table tests below, which also print and record the achieved numbers
+(profiles/r2_flow_error_table.md).  Scalar losses: 2e-5 relative (float32 mean over n d terms)."""
 import numpy as np
 import pytest
 import torch
@@ -50,7 +52,7 @@ def test_forward_reference_layout_golden(flow_cases):
         f = make_flow(c)
         z, ld = f.forward(torch.tensor(c["x"]))
         assert z.shape == c["z_ref"].shape and not z.is_cuda
-        assert _relmax(z.numpy(), c["z_ref"]) < 2e-5, name
+        assert _relmax(z.numpy(), c["z_ref"]) < 1e-5, name
         assert np.allclose(ld.numpy(), c["ld_ref"], rtol=1e-5, atol=1e-4), name
 
 
@@ -59,7 +61,7 @@ def test_forward_per_sample_golden(flow_cases):
         f = make_flow(c, reference_layout=False)
         z, ld = f.forward(torch.tensor(c["x"]).cuda())
         assert z.is_cuda
-        assert _relmax(z.cpu().numpy(), c["z_col"]) < 2e-5, name
+        assert _relmax(z.cpu().numpy(), c["z_col"]) < 1e-5, name
         assert np.allclose(ld.cpu().numpy(), c["ld_col"], rtol=1e-5, atol=5e-5), name
 
 
@@ -85,7 +87,7 @@ def test_prefix_forward_matches_oracle(flow_cases):
         x = c["x"][:, :d_in].copy()
         z, ld = f.forward(torch.tensor(x))
         zo, ldo = orc.forward(c["theta"], d, K, H, B, x)
-        assert _relmax(z.numpy(), zo) < 2e-5
+        assert _relmax(z.numpy(), zo) < 1e-5
         assert np.allclose(ld.numpy(), ldo, rtol=1e-5, atol=5e-5)
         lp = f.log_prob(torch.tensor(x))
         assert np.allclose(lp.numpy(), orc.log_prob(c["theta"], d, K, H, B, x), rtol=1e-5, atol=1e-4)
@@ -95,11 +97,11 @@ def test_inverse_golden(flow_cases):
     for name, c in flow_cases.items():
         f = make_flow(c)
         x, ld = f.inverse(torch.tensor(c["zin"]))
-        assert _relmax(x.numpy(), c["x_inv"]) < 2e-5, name
+        assert _relmax(x.numpy(), c["x_inv"]) < 1e-5, name
         assert np.allclose(ld.numpy(), c["ld_inv"], rtol=1e-5, atol=1e-4), name
         sep = int(c["sep"])
         xc = f.inverse_given_separator(torch.tensor(c["zin_f"]), torch.tensor(c["x_sep"]) if sep else None)
-        assert _relmax(xc.numpy(), c["x_cond"]) < 2e-5, name
+        assert _relmax(xc.numpy(), c["x_cond"]) < 1e-5, name
 
 
 def test_inverse_fused_normalisation(flow_cases):
@@ -159,13 +161,13 @@ def test_ragged_sizes_vs_oracle(flow_cases, n):
     f = make_flow(c, reference_layout=False)
     z, ld = f.forward(torch.tensor(x))
     zo, ldo = orc.forward(c["theta"], d, K, H, B, x)
-    assert _relmax(z.numpy(), zo) < 2e-5
+    assert _relmax(z.numpy(), zo) < 1e-5
     assert np.allclose(ld.numpy(), ldo, rtol=1e-5, atol=5e-5)
     zin = rng.standard_normal((n, d)).astype(np.float32)
     xi, ldi = f.inverse(torch.tensor(zin))
     xo, ldo2, bad = orc.inverse(c["theta"], d, K, H, B, zin)
     assert bad == 0
-    assert _relmax(xi.numpy(), xo) < 2e-5
+    assert _relmax(xi.numpy(), xo) < 1e-5
     assert np.allclose(ldi.numpy(), ldo2, rtol=1e-5, atol=1e-4)
     loss, g = f.loss_and_grad(torch.tensor(x))
     lo, go = orc.loss_grad(c["theta"], d, K, H, B, x, dtype=np.float64)
@@ -528,7 +530,7 @@ def test_large_batch_log_prob_pair_kernel_matches_single_sample_kernel():
     ref = orc.log_prob(f.flat_parameters(), d, 9, 8, 5.0, x[-3000:].numpy())
     got = big[-3000:].cpu().numpy()
     assert np.allclose(got, ref, rtol=1e-5, atol=2e-4)
-    assert _relmax(got, ref) < 2e-5
+    assert _relmax(got, ref) < 1e-5
 
 
 

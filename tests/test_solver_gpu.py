@@ -33,7 +33,7 @@ def mmd_b(x, y, sigma):
 
 def test_wrapper_matches_reference_outputs():
     g = dict(np.load(os.path.join(HERE, "golden", "model.npz")))
-    check_wrapper(g, rtol=2e-5)
+    check_wrapper(g, rtol=1e-5)
 
 
 def solve(case, _reseed=True, **kw):
