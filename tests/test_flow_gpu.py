@@ -381,6 +381,33 @@ def test_large_batch_training_mode_matches_oracle():
     assert abs(loss - lo) < 2e-5 * abs(lo) and _relmax(g, go) < 5e-4
 
 
+def test_large_batch_training_at_multi_robot_clique_dimension():
+    """Flow dimension 17 (the cliques of the multi-robot graphs) in the large-batch mode: the block slots are split over 17 dims by
+    cost, the blocks past a dim's share only write a zero partial, and the per-warp gradient partials alias the staging regions so
+    that two blocks fit per SM.  Loss curve and gradient against the oracle, and bitwise reproducibility of the run."""
+    from nfisam_b200.flows import NSF_AR
+
+    rng = np.random.default_rng(17)
+    d, K, H, n = 17, 9, 8, 16_500
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    for i in range(1, d):
+        x[:, i] = 0.6 * x[:, i] + 0.5 * np.tanh(x[:, i - 1]) ** 2
+    x = (x - x.mean(0)) / x.std(0)
+    torch.manual_seed(4)
+    f = NSF_AR(dim=d, K=K, hidden_dim=H)
+    theta0 = f.flat_parameters()
+    loss, g = f.loss_and_grad(torch.tensor(x))
+    lo, go = orc.loss_grad(theta0, d, K, H, 5.0, x, dtype=np.float64)
+    assert abs(loss - lo) < 2e-5 * abs(lo) and _relmax(g, go) < 5e-4
+    hist, ran = f.fit(torch.tensor(x), 8, 0.01, average_window=0)
+    _, hist_o, _ = orc.train(theta0, d, K, H, 5.0, x, 8, 0.01, average_window=0)
+    assert ran == 8 and np.allclose(hist, hist_o, rtol=2e-5)
+    f2 = NSF_AR(dim=d, K=K, hidden_dim=H)
+    f2.load_flat_parameters(theta0)
+    hist2, _ = f2.fit(torch.tensor(x), 8, 0.01, average_window=0)
+    assert np.array_equal(hist, hist2) and np.array_equal(f.flat_parameters(), f2.flat_parameters())
+
+
 def test_validation_set_slower_stop_matches_reference_loop():
     """training_set_frac < 1 path: validation loss every `validation_interval` iterations, first increase fixes
     slower_stop_iter = int(rate * (i + 1)) (src/slam/NFiSAM.py:452-468).  Golden: the reference's loop body run with
